@@ -1,0 +1,48 @@
+/* OptB200.h -- extension entry points of libOpt.so beyond the reference's Opt.h.
+ *
+ * Plain C ABI (pointers, ints, doubles).  Nothing here is needed by a reference caller; these exist so
+ * that (a) the parity tests can compare individual hot-path kernels -- PCGInit1 / PCGStep1 / cost,
+ * reference API/src/solverGPUGaussNewton.t:361-434,580-592 -- against the CPU oracle, (b) bench.py can
+ * read device-side timings and launch counts, and (c) a multi-GPU host can shard a problem
+ * (SURVEY.md section 8e).  All vectors use the plan's flat layout: the spec's unknown arrays
+ * concatenated in declaration order, each starting at a 64-scalar-aligned offset
+ * (OptB200_PlanUnknownLayout).
+ */
+#pragma once
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#include "Opt.h"
+
+/* library identification: returns "opt_b200 <version> sm_100a" */
+const char* OptB200_Version(void);
+
+/* padded length (in scalars) of every PCG vector of the plan */
+long OptB200_PlanNumUnknowns(Opt_Plan* plan);
+/* fills up to maxArrays entries; returns the number of unknown arrays of the spec */
+int OptB200_PlanUnknownLayout(Opt_Plan* plan, int maxArrays, long* offsets, long* elements, int* channels);
+
+/* PCGInit1 at the current unknowns.  Host outputs (may be NULL): cost = 1/2 sum r^2,
+ * negJtF = r0 = -J^T F, preInv = the inverted Jacobi preconditioner, rDotP = r0 . (preInv*r0). */
+void OptB200_EvalJTF(Opt_Plan* plan, void** problemparams, double* cost, void* negJtF, void* preInv, double* rDotP);
+/* PCGStep1: out = J^T J x linearised at the current unknowns; x and out are HOST vectors in the flat layout. */
+void OptB200_ApplyJTJ(Opt_Plan* plan, void** problemparams, const void* x, void* out, double* xDotOut);
+
+/* Debug hook for iteration-level parity: when k >= 0, Opt_ProblemStep runs PCGInit1 and only k PCG
+ * iterations, leaves delta/r/z/p/Ap_X in place for OptB200_ReadVector and does NOT update the unknowns. */
+void OptB200_SetMaxLinearIterations(Opt_Plan* plan, int k);
+/* name in {delta,r,z,p,Ap_X,preconditioner,CtC,b}; returns 0 on success */
+int OptB200_ReadVector(Opt_Plan* plan, const char* name, void* hostOut);
+/* name in {scanAlphaDenominator,rz0,rz1,q,flags,trust_region_radius,cost,modelCost} */
+double OptB200_ReadScalar(Opt_Plan* plan, const char* name);
+
+/* Order the plan's work after `stream` (a cudaStream_t) instead of the legacy NULL stream. */
+void OptB200_PlanSetStream(Opt_Plan* plan, void* stream);
+/* kernels launched by the last Opt_ProblemStep, and device time (ms, CUDA events) of its inner PCG loop */
+int OptB200_LaunchesLastStep(Opt_Plan* plan);
+float OptB200_PcgLoopMsLastStep(Opt_Plan* plan);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,314 @@
+// energy_image_warping.cu -- hand-written sm_100a kernels for the image_warping (2-D ARAP) energy.
+//
+// Energy (reference examples/image_warping/image_warping.t:1-23), per pixel i with 4-neighbours j:
+//     r_reg(i,j) = w_reg * [ (O_i - O_j) - R(a_i) (U_i - U_j) ]     valid iff j in bounds, Mask_j==0, Mask_i==0
+//     r_fit(i)   = w_fit * (O_i - C_i)                              valid iff C_i.x>=0 and C_i.y>=0
+//     Exclude(Mask_i != 0);  UsePreconditioner(true);  unknowns O (2 ch) and a (1 ch).
+// What the reference generates symbolically for this spec (o.t createjtjcentered :2029-2089,
+// createjtfcentered :2129-2172, createcost :2375-2385, computeCtCcentered :2255-2287,
+// createmodelcost :2174-2199) is written out here in closed form.  With v_ij the (symmetric) validity
+// of the pair, d_ij = U_i - U_j, R' = dR/da and e_i = R'(a_i) d_ij:
+//     (J^T J p)_O(i) = w^2 sum_j v_ij [ 2 (pO_i - pO_j) - e_i pa_i - e_j pa_j ] + w_fit^2 vfit_i pO_i
+//     (J^T J p)_a(i) = w^2 sum_j v_ij [ |e_i|^2 pa_i - e_i . (pO_i - pO_j) ]
+//     (J^T F)_O(i)   = w sum_j v_ij [ r_ij - r_ji ] + w_fit r_fit(i)
+//     (J^T F)_a(i)   = -w sum_j v_ij e_i . r_ij
+//     diag_O(i) = 2 w^2 #valid + w_fit^2 vfit ,  diag_a(i) = w^2 sum_j v_ij |e_i|^2
+// (the sum over j collects both the residual centred at i and the one centred at j that reads O_i,
+// o.t residualsincludingX00 :1996-2006).
+//
+// B200 mapping: the unknowns are fixed during the inner PCG loop, so PCGInit1 packs everything
+// JtJ needs into plan-owned arrays -- geom = (cos a, sin a, Ux, Uy) as one 16-byte vector per pixel
+// and a flag byte (pair validity x4, fit validity, active) -- and the inner loop never touches the
+// caller's buffers, never evaluates sin/cos (the reference's generated Step1 evaluates ~5 per
+// pixel), and reads 7 floats + 1 byte per pixel instead of the spec's 9 + mask.  HBM-bound stencil:
+// one thread per pixel over 32x8 tiles, neighbours through L1/L2, persistent grid sized to the SMs.
+#include <cstdint>
+#include "solver.h"
+
+namespace optb {
+
+template <class T> struct alignas(sizeof(T) * 2) Vec2 { T x, y; };
+template <class T> struct alignas(16) Vec4 { T x, y, z, w; };
+
+template <class T>
+struct IWData {
+    int W, H, tilesX, numTiles;
+    const Vec2<T>* Offset; const T* Angle; const Vec2<T>* UrShape; const Vec2<T>* Constraints; const T* Mask;
+    T w, wf;                 // w_regSqrt, w_fitSqrt (float Params cast to opt_float on use, o.t:1699)
+    long offA;               // offset of the Angle block inside the flat PCG vectors
+    Vec4<T>* geom; uint8_t* flags;
+};
+
+constexpr int kTileW = 32, kTileH = 8;
+__device__ __forceinline__ void sincosT(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void sincosT(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ float guardedInvert(float v) { float s = 1.0f + sqrtf(v); return 1.0f / (s * s); }    // CERES variant, solverGPUGaussNewton.t:323-332
+__device__ __forceinline__ double guardedInvert(double v) { double s = 1.0 + sqrt(v); return 1.0 / (s * s); }
+
+#define IW_TILE_LOOP(D)                                                                   \
+    for (int tile = blockIdx.x; tile < (D).numTiles; tile += gridDim.x)                   \
+        for (int _once = 0, x = (tile % (D).tilesX) * kTileW + (threadIdx.x & 31),        \
+                 y = (tile / (D).tilesX) * kTileH + (threadIdx.x >> 5);                   \
+             _once < 1; ++_once)                                                          \
+            if (x < (D).W && y < (D).H)
+
+// neighbour k of the spec's Stencil {{1,0},{-1,0},{0,1},{0,-1}}
+__device__ __forceinline__ bool neighbour(int k, int x, int y, int W, int H, long* j) {
+    const int nx = x + (k == 0 ? 1 : (k == 1 ? -1 : 0));
+    const int ny = y + (k == 2 ? 1 : (k == 3 ? -1 : 0));
+    *j = (long)ny * W + nx;
+    return nx >= 0 && nx < W && ny >= 0 && ny < H;
+}
+
+// ------------------------------------------------------------------------------------ PCGInit1
+// solverGPUGaussNewton.t:361-397 specialised to this energy; also packs geom/flags.
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_iwInit(IWData<T> D, ReduceWorkspace ws, int rzSlot, T* __restrict__ delta, T* __restrict__ r,
+                                                   T* __restrict__ pre, T* __restrict__ p) {
+    T acc = T(0);
+    IW_TILE_LOOP(D) {
+        const long i = (long)y * D.W + x;
+        const Vec2<T> Ui = D.UrShape[i];
+        const T ai = D.Angle[i];
+        T s, c; sincosT(ai, &s, &c);
+        D.geom[i] = Vec4<T>{ c, s, Ui.x, Ui.y };
+        uint8_t fl = 0;
+        Vec2<T> rO{ T(0), T(0) }, pO{ T(0), T(0) }, preO{ T(0), T(0) };
+        T rA = T(0), pA = T(0), preA = T(0);
+        if (D.Mask[i] == T(0)) {
+            const Vec2<T> Oi = D.Offset[i];
+            T gx = T(0), gy = T(0), gA = T(0), dO = T(0), dA = T(0);
+            const T w = D.w, w2 = D.w * D.w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                long j;
+                if (neighbour(k, x, y, D.W, D.H, &j) && D.Mask[j] == T(0)) {
+                    fl |= (uint8_t)(1u << k);
+                    const Vec2<T> Oj = D.Offset[j], Uj = D.UrShape[j];
+                    T sj, cj; sincosT(D.Angle[j], &sj, &cj);
+                    const T dx = Ui.x - Uj.x, dy = Ui.y - Uj.y;
+                    const T ox = Oi.x - Oj.x, oy = Oi.y - Oj.y;
+                    const T rijx = w * (ox - (c * dx - s * dy)), rijy = w * (oy - (s * dx + c * dy));
+                    const T rjix = w * (-ox + (cj * dx - sj * dy)), rjiy = w * (-oy + (sj * dx + cj * dy));
+                    gx += w * (rijx - rjix); gy += w * (rijy - rjiy);
+                    const T ex = -s * dx - c * dy, ey = c * dx - s * dy;   // e_i = R'(a_i) d
+                    gA -= w * (ex * rijx + ey * rijy);
+                    dO += T(2) * w2;
+                    dA += w2 * (ex * ex + ey * ey);
+                }
+            }
+            const Vec2<T> C = D.Constraints[i];
+            if (C.x >= T(0) && C.y >= T(0)) {
+                fl |= 16;
+                gx += D.wf * (D.wf * (Oi.x - C.x)); gy += D.wf * (D.wf * (Oi.y - C.y));
+                dO += D.wf * D.wf;
+            }
+            fl |= 32;
+            rO = Vec2<T>{ -gx, -gy }; rA = -gA;
+            const T io = guardedInvert(dO), ia = guardedInvert(dA);
+            preO = Vec2<T>{ io, io }; preA = ia;
+            pO = Vec2<T>{ io * rO.x, io * rO.y }; pA = ia * rA;
+            acc += rO.x * pO.x + rO.y * pO.y + rA * pA;
+        }
+        D.flags[i] = fl;
+        reinterpret_cast<Vec2<T>*>(delta)[i] = Vec2<T>{ T(0), T(0) }; delta[D.offA + i] = T(0);
+        reinterpret_cast<Vec2<T>*>(r)[i] = rO; r[D.offA + i] = rA;
+        reinterpret_cast<Vec2<T>*>(pre)[i] = preO; pre[D.offA + i] = preA;
+        reinterpret_cast<Vec2<T>*>(p)[i] = pO; p[D.offA + i] = pA;
+    }
+    gridReduceTo<kBlock>((double)acc, ws, rzSlot);
+}
+
+// ------------------------------------------------------------------------------------ PCGStep1 (+ fused PCGStep3)
+// solverGPUGaussNewton.t:421-434 (and :537-550 when FUSE3): out = (J^T J [+CtC]) p, dot = p.out.
+// FUSE3: p = z + beta*pOld is formed on the fly for the centre and its neighbours; the centre value
+// is written to pNew (double-buffered so neighbours in other CTAs still see pOld).
+template <class T, bool FUSE3, bool LM>
+__global__ void __launch_bounds__(kBlock) k_iwApplyJTJ(IWData<T> D, ReduceWorkspace ws, int dotSlot, int rzNew, int rzOld,
+                                                       const T* __restrict__ pIn, const T* __restrict__ z, T* __restrict__ pOut,
+                                                       T* __restrict__ out, const T* __restrict__ CtC) {
+    T beta = T(0);
+    if (FUSE3) {
+        const T rn = (T)ws.scalars[rzNew], ro = (T)ws.scalars[rzOld];
+        if (ro > T(0)) beta = rn / ro;
+    }
+    const Vec2<T>* pInO = reinterpret_cast<const Vec2<T>*>(pIn);
+    const T* pInA = pIn + D.offA;
+    const Vec2<T>* zO = reinterpret_cast<const Vec2<T>*>(z);
+    const T* zA = z + D.offA;
+    const T w2 = D.w * D.w, wf2 = D.wf * D.wf;
+    T acc = T(0);
+    IW_TILE_LOOP(D) {
+        const long i = (long)y * D.W + x;
+        const unsigned fl = D.flags[i];
+        Vec2<T> oO{ T(0), T(0) }; T oA = T(0);
+        Vec2<T> pi{ T(0), T(0) }; T pai = T(0);
+        if (fl & 32u) {
+            const Vec4<T> gi = D.geom[i];
+            pi = pInO[i]; pai = pInA[i];
+            if (FUSE3) { const Vec2<T> zi = zO[i]; pi.x = zi.x + beta * pi.x; pi.y = zi.y + beta * pi.y; pai = zA[i] + beta * pai; }
+            T ax = T(0), ay = T(0), aa = T(0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (fl & (1u << k)) {
+                    long j; neighbour(k, x, y, D.W, D.H, &j);
+                    const Vec4<T> gj = D.geom[j];
+                    Vec2<T> pj = pInO[j]; T paj = pInA[j];
+                    if (FUSE3) { const Vec2<T> zj = zO[j]; pj.x = zj.x + beta * pj.x; pj.y = zj.y + beta * pj.y; paj = zA[j] + beta * paj; }
+                    const T dx = gi.z - gj.z, dy = gi.w - gj.w;
+                    const T eix = -gi.y * dx - gi.x * dy, eiy = gi.x * dx - gi.y * dy;
+                    const T ejx = -gj.y * dx - gj.x * dy, ejy = gj.x * dx - gj.y * dy;
+                    const T px = pi.x - pj.x, py = pi.y - pj.y;
+                    ax += T(2) * px - eix * pai - ejx * paj;
+                    ay += T(2) * py - eiy * pai - ejy * paj;
+                    aa += (eix * eix + eiy * eiy) * pai - (eix * px + eiy * py);
+                }
+            }
+            oO.x = w2 * ax; oO.y = w2 * ay; oA = w2 * aa;
+            if (fl & 16u) { oO.x += wf2 * pi.x; oO.y += wf2 * pi.y; }
+            if (LM) {
+                const Vec2<T> cO = reinterpret_cast<const Vec2<T>*>(CtC)[i];
+                oO.x += cO.x * pi.x; oO.y += cO.y * pi.y; oA += CtC[D.offA + i] * pai;
+            }
+            acc += pi.x * oO.x + pi.y * oO.y + pai * oA;
+        }
+        reinterpret_cast<Vec2<T>*>(out)[i] = oO; out[D.offA + i] = oA;
+        if (FUSE3) { reinterpret_cast<Vec2<T>*>(pOut)[i] = pi; pOut[D.offA + i] = pai; }
+    }
+    if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
+}
+
+// ------------------------------------------------------------------------------------ computeCost
+// solverGPUGaussNewton.t:580-592 + o.t:2375-2385: 1/2 sum r^2 over residuals centred at active pixels.
+// MODEL: computeModelCost (:666-678, o.t:2174-2199): 1/2 sum (r + J delta)^2.
+template <class T, bool MODEL>
+__global__ void __launch_bounds__(kBlock) k_iwCost(IWData<T> D, ReduceWorkspace ws, int slot, const T* __restrict__ delta) {
+    T acc = T(0);
+    const Vec2<T>* dO = reinterpret_cast<const Vec2<T>*>(delta);
+    const T* dA = MODEL ? delta + D.offA : nullptr;
+    IW_TILE_LOOP(D) {
+        const long i = (long)y * D.W + x;
+        if (D.Mask[i] == T(0)) {
+            const Vec2<T> Oi = D.Offset[i], Ui = D.UrShape[i];
+            T s, c; sincosT(D.Angle[i], &s, &c);
+            Vec2<T> di{ T(0), T(0) }; T dai = T(0);
+            if (MODEL) { di = dO[i]; dai = dA[i]; }
+            T e = T(0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                long j;
+                if (neighbour(k, x, y, D.W, D.H, &j) && D.Mask[j] == T(0)) {
+                    const Vec2<T> Oj = D.Offset[j], Uj = D.UrShape[j];
+                    const T dx = Ui.x - Uj.x, dy = Ui.y - Uj.y;
+                    T rx = D.w * ((Oi.x - Oj.x) - (c * dx - s * dy)), ry = D.w * ((Oi.y - Oj.y) - (s * dx + c * dy));
+                    if (MODEL) {
+                        const Vec2<T> dj = dO[j];
+                        const T ex = -s * dx - c * dy, ey = c * dx - s * dy;
+                        rx += D.w * ((di.x - dj.x) - ex * dai); ry += D.w * ((di.y - dj.y) - ey * dai);
+                    }
+                    e += rx * rx + ry * ry;
+                }
+            }
+            const Vec2<T> C = D.Constraints[i];
+            if (C.x >= T(0) && C.y >= T(0)) {
+                T fx = D.wf * (Oi.x - C.x), fy = D.wf * (Oi.y - C.y);
+                if (MODEL) { fx += D.wf * di.x; fy += D.wf * di.y; }
+                e += fx * fx + fy * fy;
+            }
+            acc += T(0.5) * e;
+        }
+    }
+    gridReduceTo<kBlock>((double)acc, ws, slot);
+}
+
+// ------------------------------------------------------------------------------------ PCGComputeCtC
+// :616-622 + o.t:2255-2287: CtC = diag(J^T J) / radius, from the packed linearisation.
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_iwCtC(IWData<T> D, T* __restrict__ CtC, T invRadius) {
+    const T w2 = D.w * D.w, wf2 = D.wf * D.wf;
+    IW_TILE_LOOP(D) {
+        const long i = (long)y * D.W + x;
+        const unsigned fl = D.flags[i];
+        T dO = T(0), dA = T(0);
+        if (fl & 32u) {
+            const Vec4<T> gi = D.geom[i];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (fl & (1u << k)) {
+                    long j; neighbour(k, x, y, D.W, D.H, &j);
+                    const Vec4<T> gj = D.geom[j];
+                    const T dx = gi.z - gj.z, dy = gi.w - gj.w;
+                    const T ex = -gi.y * dx - gi.x * dy, ey = gi.x * dx - gi.y * dy;
+                    dO += T(2) * w2 * invRadius;
+                    dA += w2 * (ex * ex + ey * ey) * invRadius;
+                }
+            }
+            if (fl & 16u) dO += wf2 * invRadius;
+        }
+        reinterpret_cast<Vec2<T>*>(CtC)[i] = Vec2<T>{ dO, dO }; CtC[D.offA + i] = dA;
+    }
+}
+
+// ====================================================================================== host side
+template <class T>
+struct ImageWarpingOps : EnergyOps<T> {
+    IWData<T> D{};
+    float wFit = 0, wReg = 0;
+    int gridInit = 0, gridJTJ = 0, gridJTJF = 0, gridCost = 0;
+    ImageWarpingOps(const unsigned* dims) {
+        D.W = (int)dims[0]; D.H = (int)dims[1];
+        D.tilesX = (D.W + kTileW - 1) / kTileW; D.numTiles = D.tilesX * ((D.H + kTileH - 1) / kTileH);
+        const long N = (long)D.W * D.H;
+        this->unknowns.resize(2);
+        this->unknowns[0].elements = N; this->unknowns[0].channels = 2;   // Offset
+        this->unknowns[1].elements = N; this->unknowns[1].channels = 1;   // Angle
+        this->layoutUnknowns();
+        D.offA = this->unknowns[1].offset;
+        this->usePreconditioner = true;
+        OPT_CUDA_CHECK(cudaMalloc((void**)&D.geom, N * sizeof(Vec4<T>)));
+        OPT_CUDA_CHECK(cudaMalloc((void**)&D.flags, N));
+        OPT_CUDA_CHECK(cudaMemset(D.flags, 0, N));
+        int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        auto gridOf = [&](const void* fn) {
+            int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBlock, 0);
+            if (occ < 1) occ = 1;
+            long g = (long)sms * occ; if (g > D.numTiles) g = D.numTiles; if (g > kMaxPartials) g = kMaxPartials; if (g < 1) g = 1;
+            return (int)g;
+        };
+        gridInit = gridOf((const void*)k_iwInit<T>);
+        gridJTJ = gridOf((const void*)k_iwApplyJTJ<T, false, false>);
+        gridJTJF = gridOf((const void*)k_iwApplyJTJ<T, true, false>);
+        gridCost = gridOf((const void*)k_iwCost<T, false>);
+    }
+    ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); }
+    const char* name() const override { return "image_warping"; }
+    void bind(void** q) override {   // positions: image_warping.t:2-8
+        this->unknowns[0].user = q[0]; this->unknowns[1].user = q[1];
+        D.Offset = (const Vec2<T>*)q[0]; D.Angle = (const T*)q[1]; D.UrShape = (const Vec2<T>*)q[2];
+        D.Constraints = (const Vec2<T>*)q[3]; D.Mask = (const T*)q[4];
+        wFit = *(const float*)q[5]; wReg = *(const float*)q[6];
+        D.wf = (T)wFit; D.w = (T)wReg;
+    }
+    void pcgInit(const LaunchCtx& c, T* delta, T* r, T* pre, T* p, int rzSlot) override {
+        k_iwInit<T><<<gridInit, kBlock, 0, c.stream>>>(D, c.ws, rzSlot, delta, r, pre, p);
+    }
+    void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot) override {
+        if (CtC) k_iwApplyJTJ<T, false, true><<<gridJTJ, kBlock, 0, c.stream>>>(D, c.ws, dotSlot, 0, 0, x, nullptr, nullptr, out, CtC);
+        else k_iwApplyJTJ<T, false, false><<<gridJTJ, kBlock, 0, c.stream>>>(D, c.ws, dotSlot, 0, 0, x, nullptr, nullptr, out, nullptr);
+    }
+    bool step3ApplyJTJ(const LaunchCtx& c, const T* z, const T* pOld, T* pNew, T* out, const T* CtC, int rzNew, int rzOld, int dotSlot) override {
+        if (dotSlot == -2) return true;
+        if (CtC) k_iwApplyJTJ<T, true, true><<<gridJTJF, kBlock, 0, c.stream>>>(D, c.ws, dotSlot, rzNew, rzOld, pOld, z, pNew, out, CtC);
+        else k_iwApplyJTJ<T, true, false><<<gridJTJF, kBlock, 0, c.stream>>>(D, c.ws, dotSlot, rzNew, rzOld, pOld, z, pNew, out, nullptr);
+        return true;
+    }
+    void cost(const LaunchCtx& c) override { k_iwCost<T, false><<<gridCost, kBlock, 0, c.stream>>>(D, c.ws, kCost, nullptr); }
+    void modelCost(const LaunchCtx& c, const T* delta) override { k_iwCost<T, true><<<gridCost, kBlock, 0, c.stream>>>(D, c.ws, kModelCost, delta); }
+    void computeCtC(const LaunchCtx& c, T* CtC, T invRadius) override { k_iwCtC<T><<<gridJTJ, kBlock, 0, c.stream>>>(D, CtC, invRadius); }
+};
+
+template <class T> EnergyOps<T>* makeImageWarping(const unsigned* dims) { return new ImageWarpingOps<T>(dims); }
+template EnergyOps<float>* makeImageWarping<float>(const unsigned*);
+template EnergyOps<double>* makeImageWarping<double>(const unsigned*);
+
+}  // namespace optb

@@ -1,0 +1,505 @@
+// solver.cu -- generic Gauss-Newton / Levenberg-Marquardt driver with Jacobi-PCG, sm_100a.
+//
+// Restates the control flow of the reference solver (API/src/solverGPUGaussNewton.t: init :956-1007,
+// step :1016-1177) over flat unknown vectors.  Differences that are design, not semantics:
+//   * PCG vectors are flat, 64-scalar-aligned concatenations of the unknown arrays; excluded and
+//     padding entries hold r = p = Ap = 0, so the streaming kernels (Step2/Step3/update) need no
+//     Exclude() test -- they keep zeros at zeros (the reference tests fmap.exclude in every kernel,
+//     :371,:424,:450,:539,:554).
+//   * reductions are two-level and deterministic (common.cuh) instead of float atomics to one word;
+//     the r.z scalar ping-pongs between two slots instead of the per-iteration D2D copy (:1091).
+//   * the whole inner PCG loop of a nonlinear iteration is one CUDA graph launch; LM's zeta early-out
+//     (:1093-1102, a blocking D2H per PCG step in the reference) is evaluated on the device and turns
+//     the remaining captured kernels into no-ops.
+//   * PCGStep3 of iteration k is fused into PCGStep1 of iteration k+1 when the energy provides it.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include "solver.h"
+
+namespace optb {
+
+template <class T> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int N = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
+
+template <class T> __device__ __forceinline__ void unpack(const float4& v, T* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+template <class T> __device__ __forceinline__ void unpack(const double2& v, T* a) { a[0] = v.x; a[1] = v.y; }
+__device__ __forceinline__ float4 pack(const float* a) { return make_float4(a[0], a[1], a[2], a[3]); }
+__device__ __forceinline__ double2 pack(const double* a) { return make_double2(a[0], a[1]); }
+
+// ------------------------------------------------------------------------------------ PCGStep2
+// solverGPUGaussNewton.t:446-489.  alpha = rz_old / pAp (guarded), delta += alpha p, r -= alpha Ap,
+// z = pre*r, rz_new = z.r ; LM: q = 1/2 delta.(r+b).
+template <class T, bool LM, bool USEPRE>
+__global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, ReduceWorkspace ws, int rzOld, int rzNew,
+                                                     T* __restrict__ delta, const T* __restrict__ p, T* __restrict__ r,
+                                                     const T* __restrict__ Ap, const T* __restrict__ pre,
+                                                     const T* __restrict__ b, T* __restrict__ z) {
+    using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
+    if (LM && ws.scalars[kFlags] != 0.0) return;
+    const T num = (T)ws.scalars[rzOld], den = (T)ws.scalars[kPAp];
+    T alpha = T(0);
+    if (den > T(0)) alpha = num / den;
+    T accRz = T(0), accQ = T(0);
+    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
+        T d[N], pp[N], rr[N], ap[N], pr[N], bb[N], zz[N];
+        unpack(reinterpret_cast<const V*>(delta)[i], d);
+        unpack(reinterpret_cast<const V*>(p)[i], pp);
+        unpack(reinterpret_cast<const V*>(r)[i], rr);
+        unpack(reinterpret_cast<const V*>(Ap)[i], ap);
+        if (USEPRE) unpack(reinterpret_cast<const V*>(pre)[i], pr);
+        if (LM) unpack(reinterpret_cast<const V*>(b)[i], bb);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            d[k] = d[k] + alpha * pp[k];
+            rr[k] = rr[k] - alpha * ap[k];
+            zz[k] = USEPRE ? pr[k] * rr[k] : rr[k];
+            accRz += zz[k] * rr[k];
+            if (LM) accQ += T(0.5) * (d[k] * (rr[k] + bb[k]));
+        }
+        reinterpret_cast<V*>(delta)[i] = pack(d);
+        reinterpret_cast<V*>(r)[i] = pack(rr);
+        reinterpret_cast<V*>(z)[i] = pack(zz);
+    }
+    gridReduceTo<kBlock>((double)accRz, ws, rzNew);
+    if (LM) gridReduceTo<kBlock>((double)accQ, ws, kQ);
+}
+
+// PCGStep2_1stHalf (:491-503): delta += alpha p
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_pcgStep2FirstHalf(long nVec, ReduceWorkspace ws, int rzOld, T* __restrict__ delta, const T* __restrict__ p) {
+    using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
+    if (ws.scalars[kFlags] != 0.0) return;
+    const T num = (T)ws.scalars[rzOld], den = (T)ws.scalars[kPAp];
+    T alpha = T(0);
+    if (den > T(0)) alpha = num / den;
+    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
+        T d[N], pp[N];
+        unpack(reinterpret_cast<const V*>(delta)[i], d); unpack(reinterpret_cast<const V*>(p)[i], pp);
+#pragma unroll
+        for (int k = 0; k < N; ++k) d[k] = d[k] + alpha * pp[k];
+        reinterpret_cast<V*>(delta)[i] = pack(d);
+    }
+}
+// PCGStep2_2ndHalf (:505-534): r = b - Adelta, z = pre*r, rz_new, q
+template <class T, bool USEPRE>
+__global__ void __launch_bounds__(kBlock) k_pcgStep2SecondHalf(long nVec, ReduceWorkspace ws, int rzNew, const T* __restrict__ delta,
+                                                               T* __restrict__ r, const T* __restrict__ Adelta, const T* __restrict__ pre,
+                                                               const T* __restrict__ b, T* __restrict__ z) {
+    using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
+    if (ws.scalars[kFlags] != 0.0) return;
+    T accRz = T(0), accQ = T(0);
+    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
+        T d[N], ad[N], pr[N], bb[N], rr[N], zz[N];
+        unpack(reinterpret_cast<const V*>(delta)[i], d); unpack(reinterpret_cast<const V*>(Adelta)[i], ad);
+        unpack(reinterpret_cast<const V*>(b)[i], bb);
+        if (USEPRE) unpack(reinterpret_cast<const V*>(pre)[i], pr);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            rr[k] = bb[k] - ad[k];
+            zz[k] = USEPRE ? pr[k] * rr[k] : rr[k];
+            accRz += zz[k] * rr[k];
+            accQ += T(0.5) * (d[k] * (rr[k] + bb[k]));
+        }
+        reinterpret_cast<V*>(r)[i] = pack(rr); reinterpret_cast<V*>(z)[i] = pack(zz);
+    }
+    gridReduceTo<kBlock>((double)accRz, ws, rzNew);
+    gridReduceTo<kBlock>((double)accQ, ws, kQ);
+}
+
+// ------------------------------------------------------------------------------------ PCGStep3
+// :537-550.  beta = rz_new / rz_old (guarded), p = z + beta p
+template <class T, bool LM>
+__global__ void __launch_bounds__(kBlock) k_pcgStep3(long nVec, ReduceWorkspace ws, int rzNew, int rzOld, const T* __restrict__ z, T* __restrict__ p) {
+    using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
+    if (LM && ws.scalars[kFlags] != 0.0) return;
+    const T rn = (T)ws.scalars[rzNew], ro = (T)ws.scalars[rzOld];
+    T beta = T(0);
+    if (ro > T(0)) beta = rn / ro;
+    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
+        T zz[N], pp[N];
+        unpack(reinterpret_cast<const V*>(z)[i], zz); unpack(reinterpret_cast<const V*>(p)[i], pp);
+#pragma unroll
+        for (int k = 0; k < N; ++k) pp[k] = zz[k] + beta * pp[k];
+        reinterpret_cast<V*>(p)[i] = pack(pp);
+    }
+}
+
+// LM zeta early-out on the device (:1093-1102): zeta = (l+1)(Q1-Q0)/Q1 < q_tolerance => stop iterating
+template <class T>
+__global__ void k_lmZeta(ReduceWorkspace ws, int lIter, T qTol) {
+    if (ws.scalars[kFlags] != 0.0) return;
+    T Q1 = (T)ws.scalars[kQ], Q0 = (T)ws.scalars[kQPrev];
+    T zeta = T(lIter + 1) * (Q1 - Q0) / Q1;
+    if (zeta < qTol) ws.scalars[kFlags] = 1.0 + lIter;   // remembers the breaking iteration
+    ws.scalars[kQPrev] = (double)Q1;
+}
+
+// ------------------------------------------------------------------------------------ small vector kernels
+template <class T> __global__ void __launch_bounds__(kBlock) k_axpyInto(long n, T* __restrict__ x, const T* __restrict__ d) {   // PCGLinearUpdate :552-557
+    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long)gridDim.x * kBlock) x[i] = x[i] + d[i];
+}
+template <class T> __global__ void __launch_bounds__(kBlock) k_copy(long n, T* __restrict__ dst, const T* __restrict__ src) {
+    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long)gridDim.x * kBlock) dst[i] = src[i];
+}
+// PCGFinalizeDiagonal (:631-664).  `pre` holds guardedInvert(diag) from PCGInit1 on entry (0 on
+// excluded/padding entries, which stay inert), the true LM preconditioner on exit.
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, ReduceWorkspace ws, int rzSlot, T* __restrict__ CtC, const T* __restrict__ SSq,
+                                                               T* __restrict__ pre, const T* __restrict__ r, T* __restrict__ b, T* __restrict__ p,
+                                                               const T* __restrict__ delta, T radius, T minDiag, T maxDiag) {
+    T accD = T(0), accQ = T(0);
+    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long)gridDim.x * kBlock) {
+        T ssq = SSq[i];
+        if (ssq > T(0)) {
+            T unclamped = CtC[i];
+            T invS = T(1) / ssq;
+            T clampMul = invS / radius;
+            T mn = minDiag * clampMul, mx = maxDiag * clampMul;
+            T c = fmin(fmax(unclamped, mn), mx);
+            CtC[i] = c;
+            T pr = T(1) / (c + radius * unclamped);
+            pre[i] = pr;
+            T res = r[i];
+            b[i] = res;
+            T pp = pr * res;
+            p[i] = pp;
+            accD += res * pp;
+            accQ += T(0.5) * (delta[i] * (res + res));
+        } else {
+            CtC[i] = T(0); pre[i] = T(0); b[i] = T(0); p[i] = T(0);
+        }
+    }
+    gridReduceTo<kBlock>((double)accQ, ws, kQ);
+    gridReduceTo<kBlock>((double)accD, ws, rzSlot);
+}
+__global__ void k_setScalar(ReduceWorkspace ws, int slot, double v) { ws.scalars[slot] = v; }
+__global__ void k_copyScalar(ReduceWorkspace ws, int dst, int src) { ws.scalars[dst] = ws.scalars[src]; }
+
+// ====================================================================================== Plan<T>
+template <class T>
+struct Plan : PlanBase {
+    EnergyOps<T>* E;
+    bool lm;
+    SolverParameters sp;
+    int verbosity, collectTiming;
+    long n = 0;                 // padded unknown count
+    T *delta = nullptr, *r = nullptr, *z = nullptr, *p = nullptr, *Ap = nullptr, *pre = nullptr;
+    T *p2 = nullptr, *pFinal = nullptr;   // second direction buffer for the fused Step3+Step1 path; where p lives after the loop
+    T *b = nullptr, *Adelta = nullptr, *CtC = nullptr, *SSq = nullptr, *prevX = nullptr;   // LM only
+    ReduceWorkspace ws{};
+    double* hScalars = nullptr;  // pinned mirror
+    cudaStream_t stream = nullptr, userStream = nullptr;
+    bool ownStream = true;
+    cudaEvent_t evEntry = nullptr, evLoop0 = nullptr, evLoop1 = nullptr;
+    int numSMs = 148;
+    int gridStream = 0;          // CTAs for the streaming kernels
+    cudaGraphExec_t loopExec = nullptr; int loopExecIters = -1; bool loopExecFused = false;
+    bool useGraph = true, useFusion = true;
+    // nonlinear state (:994-1006)
+    int nIter = 0;
+    T prevCost = 0;
+    T trust_region_radius = 0, radius_decrease_factor = 0, min_lm_diagonal = 0, max_lm_diagonal = 0;
+    int maxLinIters = -1;
+    int launches = 0; float loopMs = 0;
+    bool finished = false;
+
+    Plan(EnergyOps<T>* e, bool isLM, int verb, int timing) : E(e), lm(isLM), verbosity(verb), collectTiming(timing) {
+        int dev = 0; OPT_CUDA_CHECK(cudaGetDevice(&dev));
+        OPT_CUDA_CHECK(cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev));
+        n = E->layoutUnknowns();
+        auto alloc = [&](T** v) { OPT_CUDA_CHECK(cudaMalloc((void**)v, n * sizeof(T))); OPT_CUDA_CHECK(cudaMemset(*v, 0, n * sizeof(T))); };
+        alloc(&delta); alloc(&r); alloc(&z); alloc(&p); alloc(&Ap); alloc(&pre); alloc(&p2); pFinal = p;
+        if (lm) { alloc(&b); alloc(&Adelta); alloc(&CtC); alloc(&SSq); alloc(&prevX); }
+        OPT_CUDA_CHECK(cudaMalloc((void**)&ws.partials, sizeof(double) * kNumScalars * kMaxPartials));
+        OPT_CUDA_CHECK(cudaMalloc((void**)&ws.counters, sizeof(unsigned) * kNumScalars));
+        OPT_CUDA_CHECK(cudaMalloc((void**)&ws.scalars, sizeof(double) * kNumScalars));
+        OPT_CUDA_CHECK(cudaMemset(ws.counters, 0, sizeof(unsigned) * kNumScalars));
+        OPT_CUDA_CHECK(cudaMemset(ws.scalars, 0, sizeof(double) * kNumScalars));
+        OPT_CUDA_CHECK(cudaMallocHost((void**)&hScalars, sizeof(double) * kNumScalars));
+        OPT_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        OPT_CUDA_CHECK(cudaEventCreateWithFlags(&evEntry, cudaEventDisableTiming));
+        OPT_CUDA_CHECK(cudaEventCreate(&evLoop0)); OPT_CUDA_CHECK(cudaEventCreate(&evLoop1));
+        long nVec = n / VecOf<T>::N;
+        gridStream = (int)std::min<long>((nVec + kBlock - 1) / kBlock, (long)numSMs * 8);
+        if (gridStream < 1) gridStream = 1;
+        if (const char* s = getenv("OPTB_NO_GRAPH")) useGraph = atoi(s) == 0;
+        if (const char* s = getenv("OPTB_NO_FUSION")) useFusion = atoi(s) == 0;
+        if (collectTiming && getenv("OPTB_TIMING_TABLE")) useGraph = false;
+        if (verbosity > 1) printf("opt_b200: plan %s %s %s: %ld unknowns (padded), %d SMs\n", E->name(), lm ? "LM" : "GN", sizeof(T) == 8 ? "fp64" : "fp32", n, numSMs);
+    }
+    ~Plan() override {
+        cudaStreamSynchronize(stream);
+        if (loopExec) cudaGraphExecDestroy(loopExec);
+        for (T* v : { delta, r, z, p, p2, Ap, pre, b, Adelta, CtC, SSq, prevX }) if (v) cudaFree(v);
+        cudaFree(ws.partials); cudaFree(ws.counters); cudaFree(ws.scalars); cudaFreeHost(hScalars);
+        cudaEventDestroy(evEntry); cudaEventDestroy(evLoop0); cudaEventDestroy(evLoop1);
+        if (ownStream) cudaStreamDestroy(stream);
+        delete E;
+    }
+    LaunchCtx ctx() const { return LaunchCtx{ stream, ws, numSMs }; }
+
+    void setParameter(const char* name, const void* v) override {   // :1205-1221
+        std::string s(name);
+#define SPF(x) if (s == #x) { sp.x = *(const float*)v; return; }
+#define SPI(x) if (s == #x) { sp.x = *(const int*)v; return; }
+        SPF(min_relative_decrease) SPF(min_trust_region_radius) SPF(max_trust_region_radius) SPF(q_tolerance)
+        SPF(function_tolerance) SPF(trust_region_radius) SPF(radius_decrease_factor) SPF(min_lm_diagonal) SPF(max_lm_diagonal)
+        SPI(residual_reset_period) SPI(nIterations) SPI(lIterations)
+#undef SPF
+#undef SPI
+        if (verbosity > 0) printf("Warning: tried to set nonexistent solver parameter %s\n", name);
+    }
+    void setStream(cudaStream_t s) override { userStream = s; }
+    void setMaxLinearIterations(int k) override { maxLinIters = k; }
+    int launchesLastStep() const override { return launches; }
+    float pcgLoopMsLastStep() const override { return loopMs; }
+    long numUnknowns() const override { return n; }
+    int unknownLayout(int maxArrays, long* offsets, long* elements, int* channels) const override {
+        int k = 0;
+        for (auto& u : E->unknowns) { if (k < maxArrays) { offsets[k] = u.offset; elements[k] = u.elements; channels[k] = u.channels; } ++k; }
+        return k;
+    }
+    double currentCost() const override { return (double)prevCost; }
+
+    // order our stream after whatever the caller queued on its stream (default: the legacy NULL stream,
+    // which is what the reference runs on, util.t:828)
+    void enter() {
+        OPT_CUDA_CHECK(cudaEventRecord(evEntry, userStream));
+        OPT_CUDA_CHECK(cudaStreamWaitEvent(stream, evEntry, 0));
+    }
+    void readScalars() {
+        OPT_CUDA_CHECK(cudaMemcpyAsync(hScalars, ws.scalars, sizeof(double) * kNumScalars, cudaMemcpyDeviceToHost, stream));
+        OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    T computeCost() {   // :790-797
+        E->cost(ctx()); ++launches;
+        readScalars();
+        return (T)hScalars[kCost];
+    }
+
+    void init(void** params) override {   // :956-1007
+        E->bind(params);
+        enter();
+        nIter = 0; finished = false; launches = 0;
+        trust_region_radius = (T)sp.trust_region_radius; radius_decrease_factor = (T)sp.radius_decrease_factor;
+        min_lm_diagonal = (T)sp.min_lm_diagonal; max_lm_diagonal = (T)sp.max_lm_diagonal;
+        E->precompute(ctx());
+        prevCost = computeCost();
+        if (verbosity > 0) printf("initial cost=%f\n", (double)prevCost);
+    }
+
+    // ---- one PCG iteration, launched on `stream` (captured into the loop graph or issued directly)
+    void launchStep2(int rzOld, int rzNew, T* p) {
+        long nVec = n / VecOf<T>::N;
+        if (lm) {
+            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            else k_pcgStep2<T, true, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+        } else {
+            if (E->usePreconditioner) k_pcgStep2<T, false, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            else k_pcgStep2<T, false, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+        }
+        ++launches;
+    }
+    void launchStep3(int rzNew, int rzOld, T* p) {
+        long nVec = n / VecOf<T>::N;
+        if (lm) k_pcgStep3<T, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzNew, rzOld, z, p);
+        else k_pcgStep3<T, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzNew, rzOld, z, p);
+        ++launches;
+    }
+    // Emits iterations [0, L).  rz slot convention: iteration l reads rz[l&1] as "old", writes rz[(l+1)&1].
+    // pendingStep3: when fusing, Step3 of iteration l is executed at the start of iteration l+1's JTJ kernel.
+    void emitLoop(int L, bool fuse) {
+        LaunchCtx c = ctx();
+        const T* ctc = lm ? CtC : nullptr;
+        bool pending = false;
+        T *cur = p, *alt = p2;
+        for (int l = 0; l < L; ++l) {
+            int rzOld = l & 1, rzNew = (l + 1) & 1;
+            if (pending) {
+                // Step3 of iteration l-1 (beta = rz[rzOld_now]/rz[rzNew_now^...]) fused into this Step1
+                E->step3ApplyJTJ(c, z, cur, alt, Ap, ctc, /*rzNew of l-1*/ rzOld, /*rzOld of l-1*/ rzNew, kPAp);
+                std::swap(cur, alt);
+                ++launches; pending = false;
+            } else {
+                E->applyJTJ(c, cur, Ap, ctc, kPAp); ++launches;   // PCGStep1 (+_Graph)
+            }
+            bool reset = lm && ((l + 1) % sp.residual_reset_period) == 0;
+            if (reset) {   // :1077-1083
+                long nVec = n / VecOf<T>::N;
+                k_pcgStep2FirstHalf<T><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, delta, cur); ++launches;
+                E->applyJTJ(c, delta, Adelta, ctc, -1); ++launches;
+                if (E->usePreconditioner) k_pcgStep2SecondHalf<T, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzNew, delta, r, Adelta, pre, b, z);
+                else k_pcgStep2SecondHalf<T, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzNew, delta, r, Adelta, pre, b, z);
+                ++launches;
+            } else {
+                launchStep2(rzOld, rzNew, cur);
+            }
+            if (fuse && !lm && l + 1 < L) pending = true;   // defer Step3 into the next Step1
+            else launchStep3(rzNew, rzOld, cur);
+            if (lm) { k_lmZeta<T><<<1, 1, 0, stream>>>(ws, l, (T)sp.q_tolerance); ++launches; }
+        }
+        pFinal = cur;
+    }
+    void runLoop(int L) {
+        bool fuse = useFusion && !lm;
+        if (fuse) {   // probe support once (no launch): energies that do not implement it return false
+            fuse = E->step3ApplyJTJ(ctx(), nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, -2);
+        }
+        OPT_CUDA_CHECK(cudaEventRecord(evLoop0, stream));
+        if (useGraph && L > 0) {
+            if (!loopExec || loopExecIters != L || loopExecFused != fuse) {
+                if (loopExec) { cudaGraphExecDestroy(loopExec); loopExec = nullptr; }
+                cudaGraph_t g;
+                int saved = launches;
+                OPT_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                emitLoop(L, fuse);
+                OPT_CUDA_CHECK(cudaStreamEndCapture(stream, &g));
+                OPT_CUDA_CHECK(cudaGraphInstantiate(&loopExec, g, 0));
+                OPT_CUDA_CHECK(cudaGraphDestroy(g));
+                loopExecIters = L; loopExecFused = fuse;
+                loopLaunchCount = launches - saved; launches = saved; loopPFinal = pFinal;
+            }
+            pFinal = loopPFinal;
+            OPT_CUDA_CHECK(cudaGraphLaunch(loopExec, stream));
+            launches += loopLaunchCount;
+        } else {
+            emitLoop(L, fuse);
+        }
+        OPT_CUDA_CHECK(cudaEventRecord(evLoop1, stream));
+    }
+    int loopLaunchCount = 0; T* loopPFinal = nullptr;
+
+    int step(void** params) override {   // :1016-1177
+        E->bind(params);
+        if (finished || !(nIter < sp.nIterations)) { finished = true; return 0; }
+        enter();
+        launches = 0;
+        LaunchCtx c = ctx();
+        E->pcgInit(c, delta, r, pre, p, kRz0); ++launches;          // PCGInit1 (+_Graph,+_Finish)
+        if (lm) {   // :1038-1053
+            if (nIter == 0) { k_copy<T><<<gridStream, kBlock, 0, stream>>>(n, SSq, pre); ++launches; }   // PCGSaveSSq
+            E->computeCtC(c, CtC, T(1) / trust_region_radius); ++launches;
+            k_lmFinalizeDiagonal<T><<<gridStream, kBlock, 0, stream>>>(n, ws, kRz0, CtC, SSq, pre, r, b, p, delta, trust_region_radius, min_lm_diagonal, max_lm_diagonal); ++launches;
+            k_copyScalar<<<1, 1, 0, stream>>>(ws, kQPrev, kQ);          // Q0 = fetchQ
+            k_setScalar<<<1, 1, 0, stream>>>(ws, kFlags, 0.0); launches += 2;
+        }
+        int L = sp.lIterations; if (maxLinIters >= 0 && maxLinIters < L) L = maxLinIters;
+        runLoop(L);
+        if (maxLinIters >= 0) { OPT_CUDA_CHECK(cudaStreamSynchronize(stream)); return 1; }   // debug hook: PCG state left for inspection
+        T model_cost_change = 0;
+        if (lm) {   // :1108-1113
+            E->modelCost(c, delta); ++launches;
+            for (auto& u : E->unknowns) { long cnt = u.elements * u.channels; k_copy<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, prevX + u.offset, (const T*)u.user); ++launches; }   // savePreviousUnknowns
+        }
+        for (auto& u : E->unknowns) {   // PCGLinearUpdate :552-557 (delta is 0 on excluded entries)
+            long cnt = u.elements * u.channels;
+            k_axpyInto<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, (T*)u.user, delta + u.offset); ++launches;
+        }
+        E->precompute(c);
+        T newCost = computeCost();    // syncs; hScalars also carries the model cost and the loop timing is complete
+        OPT_CUDA_CHECK(cudaEventElapsedTime(&loopMs, evLoop0, evLoop1));
+        int ret = 1;
+        if (lm) {   // :1119-1157
+            T model_cost = (T)hScalars[kModelCost];
+            model_cost_change = prevCost - model_cost;
+            T cost_change = prevCost - newCost;
+            T relative_decrease = cost_change / model_cost_change;
+            if (verbosity > 0) printf(" cost=%f model_cost=%f model_cost_change=%f newCost=%f\n", (double)prevCost, (double)model_cost, (double)model_cost_change, (double)newCost);
+            if (cost_change >= 0 && relative_decrease > (T)sp.min_relative_decrease) {
+                T absolute_function_tolerance = prevCost * (T)sp.function_tolerance;
+                if (cost_change <= absolute_function_tolerance) {
+                    if (verbosity > 0) printf("\nFunction tolerance reached, exiting\n");
+                    finished = true; return 0;
+                }
+                T step_quality = relative_decrease;
+                double min_factor = 1.0 / 3.0;
+                double tmp_factor = 1.0 - pow(2.0 * (double)step_quality - 1.0, 3.0);
+                trust_region_radius = (T)((double)trust_region_radius / fmax(min_factor, tmp_factor));
+                trust_region_radius = (T)fmin((double)trust_region_radius, (double)(T)sp.max_trust_region_radius);
+                radius_decrease_factor = T(2.0);
+                prevCost = newCost;
+            } else {
+                for (auto& u : E->unknowns) { long cnt = u.elements * u.channels; k_copy<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, (T*)u.user, prevX + u.offset); }   // revertUpdate
+                trust_region_radius = trust_region_radius / radius_decrease_factor;
+                if (verbosity > 0) printf(" trust_region_radius=%f \nREVERT\n", (double)trust_region_radius);
+                radius_decrease_factor = T(2.0) * radius_decrease_factor;
+                if (trust_region_radius <= (T)sp.min_trust_region_radius) {
+                    if (verbosity > 0) printf("\nTrust_region_radius is less than the min, exiting\n");
+                    OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
+                    finished = true; return 0;
+                }
+                E->precompute(c);
+                OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
+            }
+        } else {
+            if (verbosity > 0) printf("cost: %f -> %f\n", (double)prevCost, (double)newCost);
+            prevCost = newCost;
+        }
+        ++nIter;
+        return ret;
+    }
+    int gridFor(long cnt) const { long g = (cnt + kBlock - 1) / kBlock; if (g > (long)numSMs * 8) g = (long)numSMs * 8; return g < 1 ? 1 : (int)g; }
+
+    // ---- extension entry points used by the parity tests (include/OptB200.h)
+    void evalJTF(void** params, double* costOut, void* negJtF, void* preInv, double* rDotP) override {
+        E->bind(params); enter();
+        LaunchCtx c = ctx();
+        E->precompute(c);
+        E->cost(c);
+        E->pcgInit(c, delta, r, pre, p, kRz0);
+        readScalars();
+        if (costOut) *costOut = hScalars[kCost];
+        if (rDotP) *rDotP = hScalars[kRz0];
+        if (negJtF) OPT_CUDA_CHECK(cudaMemcpy(negJtF, r, n * sizeof(T), cudaMemcpyDeviceToHost));
+        if (preInv) OPT_CUDA_CHECK(cudaMemcpy(preInv, pre, n * sizeof(T), cudaMemcpyDeviceToHost));
+    }
+    void applyJTJ(void** params, const void* x, void* out, double* xDotOut) override {
+        E->bind(params); enter();
+        LaunchCtx c = ctx();
+        E->precompute(c);
+        E->pcgInit(c, delta, r, pre, p, kRz0);   // refresh the linearisation
+        OPT_CUDA_CHECK(cudaMemcpyAsync(p, x, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+        E->applyJTJ(c, p, Ap, nullptr, kPAp);
+        readScalars();
+        if (xDotOut) *xDotOut = hScalars[kPAp];
+        OPT_CUDA_CHECK(cudaMemcpy(out, Ap, n * sizeof(T), cudaMemcpyDeviceToHost));
+    }
+    int readVector(const char* name, void* hostOut) override {
+        std::string s(name); const T* v = nullptr;
+        if (s == "delta") v = delta; else if (s == "r") v = r; else if (s == "p") v = pFinal; else if (s == "z") v = z;
+        else if (s == "Ap_X") v = Ap; else if (s == "preconditioner") v = pre; else if (s == "CtC") v = CtC; else if (s == "b") v = b;
+        if (!v) return -1;
+        OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
+        OPT_CUDA_CHECK(cudaMemcpy(hostOut, v, n * sizeof(T), cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    double readScalar(const char* name) override {
+        std::string s(name);
+        readScalars();
+        if (s == "scanAlphaDenominator") return hScalars[kPAp];
+        if (s == "rz0") return hScalars[kRz0]; if (s == "rz1") return hScalars[kRz1];
+        if (s == "q") return hScalars[kQ]; if (s == "flags") return hScalars[kFlags];
+        if (s == "trust_region_radius") return (double)trust_region_radius;
+        if (s == "cost") return hScalars[kCost]; if (s == "modelCost") return hScalars[kModelCost];
+        return NAN;
+    }
+};
+
+template <class T>
+static EnergyOps<T>* makeEnergy(const std::string& energy, const unsigned* dims) {
+    if (energy == "image_warping") return makeImageWarping<T>(dims);
+    return nullptr;
+}
+
+PlanBase* makePlan(const std::string& energy, bool lm, bool doublePrecision, const unsigned* dims, int verbosity, int collectTiming) {
+    if (doublePrecision) {
+        EnergyOps<double>* e = makeEnergy<double>(energy, dims);
+        return e ? new Plan<double>(e, lm, verbosity, collectTiming) : nullptr;
+    }
+    EnergyOps<float>* e = makeEnergy<float>(energy, dims);
+    return e ? new Plan<float>(e, lm, verbosity, collectTiming) : nullptr;
+}
+
+}  // namespace optb

@@ -1,0 +1,117 @@
+// solver.h -- host-side plan: the generic GN/LM driver and the per-energy kernel interface.
+//
+// Mirrors the split the reference makes between the generic solver (API/src/solverGPUGaussNewton.t,
+// `PlanData` :167-214, init :956-1007, step :1016-1177) and the per-problem function map
+// `fmap.{cost,evalJTF,applyJTJ,computeCtC,modelcost,precompute,exclude}` the front end hands it
+// (API/src/o.t:2425-2460).  Here the function map is a C++ interface (EnergyOps) implemented by
+// hand-written sm_100a kernels, one translation unit per energy.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+namespace optb {
+
+// Solver parameters: names, types and defaults of the reference (solverGPUGaussNewton.t:26-39,
+// :148-163): the nine LM parameters are `float` even in double-precision mode, the counters `int`.
+struct SolverParameters {
+    float min_relative_decrease = 1e-3f;
+    float min_trust_region_radius = 1e-32f;
+    float max_trust_region_radius = 1e16f;
+    float q_tolerance = 0.0001f;
+    float function_tolerance = 0.000001f;
+    float trust_region_radius = 1e4f;
+    float radius_decrease_factor = 2.0f;
+    float min_lm_diagonal = 1e-6f;
+    float max_lm_diagonal = 1e32f;
+    int residual_reset_period = 10;
+    int nIterations = 10;
+    int lIterations = 10;
+};
+
+// One Unknown(...) image of the spec inside the solver's flat unknown vector.
+struct UnknownArray {
+    void* user = nullptr;   // caller's device buffer (AoS, `channels` scalars per element), updated in place
+    long elements = 0;
+    int channels = 1;
+    long offset = 0;        // start inside every PCG vector, in scalars; 64-scalar aligned
+};
+
+struct LaunchCtx {
+    cudaStream_t stream;
+    ReduceWorkspace ws;
+    int numSMs;
+};
+
+// Per-energy kernels ("function map").  T = opt_float (float or double).
+template <class T>
+struct EnergyOps {
+    std::vector<UnknownArray> unknowns;
+    long nUnknownsPadded = 0;          // length of every PCG vector
+    bool usePreconditioner = true;     // spec's UsePreconditioner(); default false (o.t:214)
+    bool usesGraph = false;
+    virtual ~EnergyOps() {}
+    // positional re-binding of the caller's table; called at Init and at every Step (util.t:664-692)
+    virtual void bind(void** problemparams) = 0;
+    // PCGInit1 (+_Graph,+_Finish): delta=0, r=-J^T F, pre=guardedInvert(diag J^T J), p=pre*r,
+    // scalars[rzSlot] = r.p ; also refreshes whatever per-linearisation data applyJTJ needs.
+    virtual void pcgInit(const LaunchCtx& c, T* delta, T* r, T* pre, T* p, int rzSlot) = 0;
+    // PCGStep1 (+_Graph): out = (J^T J [+ diag(CtC)]) x, scalars[dotSlot] = x.out  (dotSlot<0: no reduction)
+    virtual void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot) = 0;
+    // optional fusion of PCGStep3 into PCGStep1:  p <- z + beta*p  (beta = rz[new]/rz[old], guarded),
+    // then out = (J^T J [+CtC]) p and scalars[dotSlot] = p.out.  Return false if not implemented.
+    // p is double-buffered by the caller (pOld read incl. neighbours, pNew written) so the stencil never
+    // sees a half-updated direction.  Called with dotSlot == -2 it only reports support (no launch).
+    virtual bool step3ApplyJTJ(const LaunchCtx&, const T* /*z*/, const T* /*pOld*/, T* /*pNew*/, T* /*out*/, const T* /*CtC*/,
+                               int /*rzNew*/, int /*rzOld*/, int /*dotSlot*/) { return false; }
+    // computeCost (+_Graph): scalars[kCost] = 1/2 sum r^2
+    virtual void cost(const LaunchCtx& c) = 0;
+    // LM: CtC <- diag(J^T J)/radius (PCGComputeCtC), scalars[kModelCost] = 1/2 sum (r + J delta)^2
+    virtual void computeCtC(const LaunchCtx&, T* /*CtC*/, T /*invRadius*/) { unsupported("computeCtC (LM)"); }
+    virtual void modelCost(const LaunchCtx&, const T* /*delta*/) { unsupported("modelCost (LM)"); }
+    // ComputedArray refresh (kernels.precompute, solverGPUGaussNewton.t:607-614)
+    virtual void precompute(const LaunchCtx&) {}
+    virtual const char* name() const = 0;
+    static void unsupported(const char* what) {
+        fprintf(stderr, "opt_b200: %s is not implemented for this energy\n", what);
+        exit(2);
+    }
+    long layoutUnknowns() {   // assigns 64-scalar-aligned offsets
+        long o = 0;
+        for (auto& u : unknowns) { u.offset = o; o += (u.elements * u.channels + 63) / 64 * 64; }
+        nUnknownsPadded = o;
+        return o;
+    }
+};
+
+struct KernelTiming { std::string name; float ms = 0; int count = 0; };
+
+struct PlanBase {
+    virtual ~PlanBase() {}
+    virtual void setParameter(const char* name, const void* value) = 0;
+    virtual void init(void** params) = 0;
+    virtual int step(void** params) = 0;
+    virtual double currentCost() const = 0;
+    // ---- extension entry points (include/OptB200.h)
+    virtual long numUnknowns() const = 0;
+    virtual int unknownLayout(int maxArrays, long* offsets, long* elements, int* channels) const = 0;
+    virtual void evalJTF(void** params, double* cost, void* negJtF, void* preInv, double* rDotP) = 0;
+    virtual void applyJTJ(void** params, const void* x, void* out, double* xDotOut) = 0;
+    virtual int readVector(const char* name, void* hostOut) = 0;
+    virtual double readScalar(const char* name) = 0;
+    virtual void setMaxLinearIterations(int k) = 0;
+    virtual void setStream(cudaStream_t s) = 0;
+    virtual int launchesLastStep() const = 0;
+    virtual float pcgLoopMsLastStep() const = 0;
+};
+
+// factory implemented in solver.cu
+PlanBase* makePlan(const std::string& energy, bool lm, bool doublePrecision, const unsigned* dims,
+                   int verbosity, int collectTiming);
+
+// per-energy factories (energy_*.cu); return nullptr when the energy/precision is not built
+template <class T> EnergyOps<T>* makeImageWarping(const unsigned* dims);
+template <class T> EnergyOps<T>* makeArapMesh(const unsigned* dims);
+
+}  // namespace optb

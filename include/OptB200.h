@@ -42,6 +42,13 @@ void OptB200_PlanSetStream(Opt_Plan* plan, void* stream);
 /* kernels launched by the last Opt_ProblemStep, and device time (ms, CUDA events) of its inner PCG loop */
 int OptB200_LaunchesLastStep(Opt_Plan* plan);
 float OptB200_PcgLoopMsLastStep(Opt_Plan* plan);
+/* Replays each inner-loop kernel `reps` times between two CUDA events on the plan's stream and
+ * returns the average duration per launch (ms).  names[i] point at static strings.  The PCG state
+ * is scratch afterwards -- call Opt_ProblemInit before solving again.  Returns the entry count. */
+int OptB200_ProfileKernels(Opt_Plan* plan, void** problemparams, int reps, int maxOut, const char** names, float* avgMs);
+/* Front-end probe (no GPU needed): writes the registry name of the energy in `filename` to `out` and
+ * returns 0, or writes the rejection message and returns 1. */
+int OptB200_SpecEnergyName(const char* filename, char* out, int outLen);
 
 #ifdef __cplusplus
 }

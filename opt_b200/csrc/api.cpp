@@ -110,5 +110,11 @@ double OptB200_ReadScalar(Opt_Plan* plan, const char* name) { return plan->impl-
 void OptB200_PlanSetStream(Opt_Plan* plan, void* stream) { plan->impl->setStream((cudaStream_t)stream); }
 int OptB200_LaunchesLastStep(Opt_Plan* plan) { return plan->impl->launchesLastStep(); }
 float OptB200_PcgLoopMsLastStep(Opt_Plan* plan) { return plan->impl->pcgLoopMsLastStep(); }
+int OptB200_ProfileKernels(Opt_Plan* plan, void** pp, int reps, int maxOut, const char** names, float* avgMs) { return plan->impl->profileKernels(pp, reps, maxOut, names, avgMs); }
+int OptB200_SpecEnergyName(const char* filename, char* out, int outLen) {
+    optb::SpecMatch m = optb::matchSpecFile(filename);
+    snprintf(out, outLen, "%s", m.ok ? m.energy.c_str() : m.message.c_str());
+    return m.ok ? 0 : 1;
+}
 
 }  // extern "C"

@@ -23,6 +23,9 @@
 // pixel), and reads 7 floats + 1 byte per pixel instead of the spec's 9 + mask.  HBM-bound stencil:
 // one thread per pixel over 32x8 tiles, neighbours through L1/L2, persistent grid sized to the SMs.
 #include <cstdint>
+#include <map>
+#include <type_traits>
+#include <cuda.h>
 #include "solver.h"
 
 namespace optb {
@@ -178,6 +181,157 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJ(IWData<T> D, ReduceWorksp
     if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
 }
 
+// ------------------------------------------------------------------------------------ PCGStep1, TMA-tiled (fp32)
+// Same arithmetic as k_iwApplyJTJ, different data movement: a persistent CTA walks 64x8-pixel tiles; one
+// elected thread streams each tile (+1 halo) of z, p and geom into shared memory with
+// cp.async.bulk.tensor (TMA) under an mbarrier, kStages tiles ahead of the math, so HBM latency is
+// hidden by the copy engine instead of by warp occupancy (the direct-load version stalls on
+// long_scoreboard, profiles/r1_*).  Out-of-image halo cells are zero-filled by the TMA unit.  With
+// FUSE3 the new direction p = z + beta*pOld is formed once per staged cell in shared memory.
+constexpr int kTW = 64, kTH = 8, kStages = 3;
+// TMA rule (measured, tools/scratch/tma_probe.cu): the innermost box coordinate must start on a 16-byte
+// boundary, so 2-channel rows are staged from pixel x0-2 and 1-channel rows from pixel x0-4.
+constexpr int kRowO = 2 * (kTW + 4);      // floats per staged row of a 2-channel image (pixels x0-2 .. x0+TW+1)
+constexpr int kRowA = kTW + 8;            // floats per staged row of a 1-channel image (pixels x0-4 .. x0+TW+3)
+constexpr int kRows = kTH + 2;
+constexpr int kBytesO = kRows * kRowO * 4, kBytesA = kRows * kRowA * 4, kBytesG = kRows * (kTW + 2) * 16;
+constexpr int align128(int v) { return (v + 127) / 128 * 128; }
+constexpr int kOffPO = 0, kOffPA = kOffPO + align128(kBytesO), kOffG = kOffPA + align128(kBytesA);
+constexpr int kOffZO = kOffG + align128(kBytesG), kOffZA = kOffZO + align128(kBytesO);
+constexpr int kStageBytesPlain = kOffZO, kStageBytesFused = kOffZA + align128(kBytesA);
+
+struct IWMaps { CUtensorMap pO, pA, zO, zA, geom; };
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count)); }
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smemAddr(dst)), "l"(map), "r"(smemAddr(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tmaLoad3D(void* dst, const CUtensorMap* map, uint64_t* bar, int c, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smemAddr(dst)), "l"(map), "r"(smemAddr(bar)), "r"(c), "r"(x), "r"(y) : "memory");
+}
+
+template <bool FUSE3, bool LM>
+__global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const __grid_constant__ IWMaps M, ReduceWorkspace ws, int dotSlot, int rzNew,
+                                                          int rzOld, float* __restrict__ pOut, float* __restrict__ out, const float* __restrict__ CtC,
+                                                          int tilesX, int numTiles) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[kStages];
+    constexpr int stageBytes = FUSE3 ? kStageBytesFused : kStageBytesPlain;
+    const int tid = threadIdx.x;
+    float beta = 0.f;
+    if (FUSE3) {
+        const float rn = (float)ws.scalars[rzNew], ro = (float)ws.scalars[rzOld];
+        if (ro > 0.f) beta = rn / ro;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbarInit(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int stage) {   // one thread
+        unsigned char* base = smem + (size_t)stage * stageBytes;
+        const int x0 = (tile % tilesX) * kTW, y0 = (tile / tilesX) * kTH;
+        mbarExpectTx(&bars[stage], (unsigned)(kBytesO + kBytesA + kBytesG + (FUSE3 ? kBytesO + kBytesA : 0)));
+        tmaLoad2D(base + kOffPO, &M.pO, &bars[stage], 2 * (x0 - 2), y0 - 1);
+        tmaLoad2D(base + kOffPA, &M.pA, &bars[stage], x0 - 4, y0 - 1);
+        tmaLoad3D(base + kOffG, &M.geom, &bars[stage], 0, x0 - 1, y0 - 1);
+        if (FUSE3) {
+            tmaLoad2D(base + kOffZO, &M.zO, &bars[stage], 2 * (x0 - 2), y0 - 1);
+            tmaLoad2D(base + kOffZA, &M.zA, &bars[stage], x0 - 4, y0 - 1);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { const int t = blockIdx.x + s * gridDim.x; if (t < numTiles) issue(t, s); }
+    }
+    const float w2 = D.w * D.w, wf2 = D.wf * D.wf;
+    const int lx = tid & (kTW - 1), lyBase = (tid >> 6) * 2;   // 256 threads = 64 columns x 4 row pairs
+    float acc = 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
+        const int stage = it % kStages;
+        const unsigned parity = (unsigned)((it / kStages) & 1);
+        unsigned char* base = smem + (size_t)stage * stageBytes;
+        const int x0 = (tile % tilesX) * kTW, y0 = (tile / tilesX) * kTH;
+        const int gx = x0 + lx;
+        unsigned fl[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { const int gy = y0 + lyBase + q; fl[q] = (gx < D.W && gy < D.H) ? D.flags[(long)gy * D.W + gx] : 0u; }
+        mbarWait(&bars[stage], parity);
+        float* sPO = reinterpret_cast<float*>(base + kOffPO);
+        float* sPA = reinterpret_cast<float*>(base + kOffPA);
+        const float4* sG = reinterpret_cast<const float4*>(base + kOffG);
+        if (FUSE3) {   // p = z + beta * pOld for every staged cell (halo included), in place
+            const float4* zO4 = reinterpret_cast<const float4*>(base + kOffZO); float4* pO4 = reinterpret_cast<float4*>(sPO);
+            for (int i = tid; i < kRows * kRowO / 4; i += kBlock) { float4 zv = zO4[i], pv = pO4[i]; pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y; pv.z = zv.z + beta * pv.z; pv.w = zv.w + beta * pv.w; pO4[i] = pv; }
+            const float4* zA4 = reinterpret_cast<const float4*>(base + kOffZA); float4* pA4 = reinterpret_cast<float4*>(sPA);
+            for (int i = tid; i < kRows * kRowA / 4; i += kBlock) { float4 zv = zA4[i], pv = pA4[i]; pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y; pv.z = zv.z + beta * pv.z; pv.w = zv.w + beta * pv.w; pA4[i] = pv; }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int ly = lyBase + q, gy = y0 + ly;
+            if (gx < D.W && gy < D.H) {
+                const long i = (long)gy * D.W + gx;
+                float2 oO = make_float2(0.f, 0.f); float oA = 0.f;
+                float2 pi = make_float2(0.f, 0.f); float pai = 0.f;
+                if (fl[q] & 32u) {
+                    const int r = ly + 1, c = lx + 1;             // staged coordinates of the centre
+                    const float4 gi = sG[r * (kTW + 2) + c];
+                    pi = *reinterpret_cast<const float2*>(&sPO[r * kRowO + 2 * (c + 1)]);
+                    pai = sPA[r * kRowA + c + 3];
+                    float ax = 0.f, ay = 0.f, aa = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (fl[q] & (1u << k)) {
+                            const int rr = r + (k == 2 ? 1 : (k == 3 ? -1 : 0)), cc = c + (k == 0 ? 1 : (k == 1 ? -1 : 0));
+                            const float4 gj = sG[rr * (kTW + 2) + cc];
+                            const float2 pj = *reinterpret_cast<const float2*>(&sPO[rr * kRowO + 2 * (cc + 1)]);
+                            const float paj = sPA[rr * kRowA + cc + 3];
+                            const float dx = gi.z - gj.z, dy = gi.w - gj.w;
+                            const float eix = -gi.y * dx - gi.x * dy, eiy = gi.x * dx - gi.y * dy;
+                            const float ejx = -gj.y * dx - gj.x * dy, ejy = gj.x * dx - gj.y * dy;
+                            const float px = pi.x - pj.x, py = pi.y - pj.y;
+                            ax += 2.f * px - eix * pai - ejx * paj;
+                            ay += 2.f * py - eiy * pai - ejy * paj;
+                            aa += (eix * eix + eiy * eiy) * pai - (eix * px + eiy * py);
+                        }
+                    }
+                    oO.x = w2 * ax; oO.y = w2 * ay; oA = w2 * aa;
+                    if (fl[q] & 16u) { oO.x += wf2 * pi.x; oO.y += wf2 * pi.y; }
+                    if (LM) {
+                        const float2 cO = reinterpret_cast<const float2*>(CtC)[i];
+                        oO.x += cO.x * pi.x; oO.y += cO.y * pi.y; oA += CtC[D.offA + i] * pai;
+                    }
+                    acc += pi.x * oO.x + pi.y * oO.y + pai * oA;
+                }
+                reinterpret_cast<float2*>(out)[i] = oO; out[D.offA + i] = oA;
+                if (FUSE3) { reinterpret_cast<float2*>(pOut)[i] = pi; pOut[D.offA + i] = pai; }
+            }
+        }
+        __syncthreads();   // every thread is done with this stage
+        if (tid == 0) {
+            const int next = tile + kStages * gridDim.x;
+            if (next < numTiles) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(next, stage); }
+        }
+    }
+    if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
+}
+
 // ------------------------------------------------------------------------------------ computeCost
 // solverGPUGaussNewton.t:580-592 + o.t:2375-2385: 1/2 sum r^2 over residuals centred at active pixels.
 // MODEL: computeModelCost (:666-678, o.t:2174-2199): 1/2 sum (r + J delta)^2.
@@ -255,6 +409,58 @@ struct ImageWarpingOps : EnergyOps<T> {
     IWData<T> D{};
     float wFit = 0, wReg = 0;
     int gridInit = 0, gridJTJ = 0, gridJTJF = 0, gridCost = 0;
+    // TMA path (fp32, W % 4 == 0): tensor maps are cached per (p vector, z vector) pair
+    bool tmaOk = false; int tmaTilesX = 0, tmaTiles = 0, gridTma = 0, gridTmaF = 0;
+    std::map<std::pair<const void*, const void*>, IWMaps> mapCache;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeFn encode = nullptr;
+    CUtensorMap map2D(const float* base, long innerFloats, long rows, long pitchFloats, int boxInner, int boxRows) {
+        CUtensorMap m; cuuint64_t dims[2] = { (cuuint64_t)innerFloats, (cuuint64_t)rows }; cuuint64_t strides[1] = { (cuuint64_t)pitchFloats * 4 };
+        cuuint32_t box[2] = { (cuuint32_t)boxInner, (cuuint32_t)boxRows }, es[2] = { 1, 1 };
+        CUresult rc = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) { fprintf(stderr, "opt_b200: cuTensorMapEncodeTiled(2D) failed: %d\n", (int)rc); exit(3); }
+        return m;
+    }
+    CUtensorMap mapGeom() {
+        CUtensorMap m; cuuint64_t dims[3] = { 4, (cuuint64_t)D.W, (cuuint64_t)D.H }; cuuint64_t strides[2] = { 16, (cuuint64_t)D.W * 16 };
+        cuuint32_t box[3] = { 4, (cuuint32_t)(kTW + 2), (cuuint32_t)kRows }, es[3] = { 1, 1, 1 };
+        CUresult rc = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)D.geom, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) { fprintf(stderr, "opt_b200: cuTensorMapEncodeTiled(3D) failed: %d\n", (int)rc); exit(3); }
+        return m;
+    }
+    const IWMaps& mapsFor(const float* pIn, const float* z) {
+        auto key = std::make_pair((const void*)pIn, (const void*)z);
+        auto it = mapCache.find(key);
+        if (it != mapCache.end()) return it->second;
+        IWMaps m;
+        m.pO = map2D(pIn, 2L * D.W, D.H, 2L * D.W, kRowO, kRows);
+        m.pA = map2D(pIn + D.offA, D.W, D.H, D.W, kRowA, kRows);
+        const float* zz = z ? z : pIn;
+        m.zO = map2D(zz, 2L * D.W, D.H, 2L * D.W, kRowO, kRows);
+        m.zA = map2D(zz + D.offA, D.W, D.H, D.W, kRowA, kRows);
+        m.geom = mapGeom();
+        return mapCache.emplace(key, m).first->second;
+    }
+    void setupTma(int sms) {
+        if (!std::is_same<T, float>::value || D.W % 4 != 0 || getenv("OPTB_NO_TMA")) return;
+        void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) return;
+        encode = (EncodeFn)fn;
+        tmaTilesX = (D.W + kTW - 1) / kTW; tmaTiles = tmaTilesX * ((D.H + kTH - 1) / kTH);
+        auto prep = [&](const void* f, int bytes) {
+            OPT_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, kBlock, bytes); if (occ < 1) occ = 1;
+            long g = (long)sms * occ; if (g > tmaTiles) g = tmaTiles; if (g > kMaxPartials) g = kMaxPartials; return (int)(g < 1 ? 1 : g);
+        };
+        gridTma = prep((const void*)k_iwApplyJTJTma<false, false>, kStages * kStageBytesPlain);
+        prep((const void*)k_iwApplyJTJTma<false, true>, kStages * kStageBytesPlain);
+        gridTmaF = prep((const void*)k_iwApplyJTJTma<true, false>, kStages * kStageBytesFused);
+        prep((const void*)k_iwApplyJTJTma<true, true>, kStages * kStageBytesFused);
+        tmaOk = true;
+    }
     ImageWarpingOps(const unsigned* dims) {
         D.W = (int)dims[0]; D.H = (int)dims[1];
         D.tilesX = (D.W + kTileW - 1) / kTileW; D.numTiles = D.tilesX * ((D.H + kTileH - 1) / kTileH);
@@ -279,6 +485,7 @@ struct ImageWarpingOps : EnergyOps<T> {
         gridJTJ = gridOf((const void*)k_iwApplyJTJ<T, false, false>);
         gridJTJF = gridOf((const void*)k_iwApplyJTJ<T, true, false>);
         gridCost = gridOf((const void*)k_iwCost<T, false>);
+        setupTma(sms);
     }
     ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); }
     const char* name() const override { return "image_warping"; }
@@ -293,11 +500,27 @@ struct ImageWarpingOps : EnergyOps<T> {
         k_iwInit<T><<<gridInit, kBlock, 0, c.stream>>>(D, c.ws, rzSlot, delta, r, pre, p);
     }
     void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot) override {
+        if constexpr (std::is_same<T, float>::value) {
+            if (tmaOk) {
+                const IWMaps& m = mapsFor(x, nullptr);
+                if (CtC) k_iwApplyJTJTma<false, true><<<gridTma, kBlock, kStages * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, CtC, tmaTilesX, tmaTiles);
+                else k_iwApplyJTJTma<false, false><<<gridTma, kBlock, kStages * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, nullptr, tmaTilesX, tmaTiles);
+                return;
+            }
+        }
         if (CtC) k_iwApplyJTJ<T, false, true><<<gridJTJ, kBlock, 0, c.stream>>>(D, c.ws, dotSlot, 0, 0, x, nullptr, nullptr, out, CtC);
         else k_iwApplyJTJ<T, false, false><<<gridJTJ, kBlock, 0, c.stream>>>(D, c.ws, dotSlot, 0, 0, x, nullptr, nullptr, out, nullptr);
     }
     bool step3ApplyJTJ(const LaunchCtx& c, const T* z, const T* pOld, T* pNew, T* out, const T* CtC, int rzNew, int rzOld, int dotSlot) override {
         if (dotSlot == -2) return true;
+        if constexpr (std::is_same<T, float>::value) {
+            if (tmaOk) {
+                const IWMaps& m = mapsFor(pOld, z);
+                if (CtC) k_iwApplyJTJTma<true, true><<<gridTmaF, kBlock, kStages * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, CtC, tmaTilesX, tmaTiles);
+                else k_iwApplyJTJTma<true, false><<<gridTmaF, kBlock, kStages * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, nullptr, tmaTilesX, tmaTiles);
+                return true;
+            }
+        }
         if (CtC) k_iwApplyJTJ<T, true, true><<<gridJTJF, kBlock, 0, c.stream>>>(D, c.ws, dotSlot, rzNew, rzOld, pOld, z, pNew, out, CtC);
         else k_iwApplyJTJ<T, true, false><<<gridJTJF, kBlock, 0, c.stream>>>(D, c.ws, dotSlot, rzNew, rzOld, pOld, z, pNew, out, nullptr);
         return true;

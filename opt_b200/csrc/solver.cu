@@ -466,6 +466,43 @@ struct Plan : PlanBase {
         if (xDotOut) *xDotOut = hScalars[kPAp];
         OPT_CUDA_CHECK(cudaMemcpy(out, Ap, n * sizeof(T), cudaMemcpyDeviceToHost));
     }
+    // Event-timed replay of each inner-loop kernel on the plan's stream (average over `reps` back-to-back
+    // launches after 3 warm-ups).  Destroys the PCG state; callers re-Init afterwards.
+    int profileKernels(void** params, int reps, int maxOut, const char** names, float* avgMs) override {
+        E->bind(params); enter();
+        LaunchCtx c = ctx();
+        E->precompute(c);
+        E->pcgInit(c, delta, r, pre, p, kRz0);
+        const T* ctc = lm ? CtC : nullptr;
+        if (lm) { E->computeCtC(c, CtC, T(1) / (T)sp.trust_region_radius); OPT_CUDA_CHECK(cudaMemsetAsync(b, 0, n * sizeof(T), stream)); }
+        bool fused = E->step3ApplyJTJ(c, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, -2);
+        struct K { const char* name; int id; } ks[] = { { "PCGInit1", 0 }, { "PCGStep1", 1 }, { "PCGStep3+PCGStep1(fused)", 2 }, { "PCGStep2", 3 }, { "PCGStep3", 4 }, { "computeCost", 5 } };
+        int k = 0;
+        cudaEvent_t e0, e1; OPT_CUDA_CHECK(cudaEventCreate(&e0)); OPT_CUDA_CHECK(cudaEventCreate(&e1));
+        for (auto& kk : ks) {
+            if (kk.id == 2 && !fused) continue;
+            if (k >= maxOut) break;
+            auto launch = [&]() {
+                switch (kk.id) {
+                    case 0: E->pcgInit(c, delta, r, pre, p, kRz0); break;
+                    case 1: E->applyJTJ(c, p, Ap, ctc, kPAp); break;
+                    case 2: E->step3ApplyJTJ(c, z, p, p2, Ap, ctc, kRz1, kRz0, kPAp); break;
+                    case 3: launchStep2(kRz0, kRz1, p); break;
+                    case 4: launchStep3(kRz1, kRz0, p); break;
+                    case 5: E->cost(c); break;
+                }
+            };
+            for (int w = 0; w < 3; ++w) launch();
+            OPT_CUDA_CHECK(cudaEventRecord(e0, stream));
+            for (int i = 0; i < reps; ++i) launch();
+            OPT_CUDA_CHECK(cudaEventRecord(e1, stream));
+            OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
+            float ms = 0; OPT_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            names[k] = kk.name; avgMs[k] = ms / reps; ++k;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return k;
+    }
     int readVector(const char* name, void* hostOut) override {
         std::string s(name); const T* v = nullptr;
         if (s == "delta") v = delta; else if (s == "r") v = r; else if (s == "p") v = pFinal; else if (s == "z") v = z;

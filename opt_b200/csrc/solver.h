@@ -104,6 +104,7 @@ struct PlanBase {
     virtual void setStream(cudaStream_t s) = 0;
     virtual int launchesLastStep() const = 0;
     virtual float pcgLoopMsLastStep() const = 0;
+    virtual int profileKernels(void** params, int reps, int maxOut, const char** names, float* avgMs) = 0;
 };
 
 // factory implemented in solver.cu

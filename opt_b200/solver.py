@@ -150,3 +150,18 @@ class OptSolver:
 
     def pcg_loop_ms_last_step(self):
         return self.L.OptB200_PcgLoopMsLastStep(self.plan)
+
+    def profile_kernels(self, problem_params, reps=20):
+        """{kernel name: average ms per launch}, CUDA events on the plan's stream (OptB200_ProfileKernels)"""
+        t = ParamTable(problem_params)
+        names = (ctypes.c_char_p * 16)(); ms = (ctypes.c_float * 16)()
+        k = self.L.OptB200_ProfileKernels(self.plan, t.ptr, int(reps), 16, names, ms)
+        return {names[i].decode(): float(ms[i]) for i in range(k)}
+
+
+def spec_energy_name(filename):
+    """front-end probe: (ok, energy-name-or-message); needs no GPU"""
+    L = capi.lib()
+    buf = ctypes.create_string_buffer(512)
+    rc = L.OptB200_SpecEnergyName(os.fsencode(filename), buf, 512)
+    return rc == 0, buf.value.decode()

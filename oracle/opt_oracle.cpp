@@ -111,7 +111,7 @@ template <class T> struct DualAcc {
 // ------------------------------------------------------------------ energy interface
 // A term group = one Energy(...) statement of the spec (all its vector components together),
 // instantiated over a domain: every element of an index space (centered) or every hyperedge (graph).
-struct GroupInfo { long count; int nres; bool centered; };
+struct GroupInfo { long count; int nres; bool centered; int ndeps = KMAX; };   // ndeps: max distinct unknown scalars per instance
 
 template <class T>
 struct Energy {
@@ -180,7 +180,7 @@ struct ImageWarping : Energy<T> {
         w_fitSqrt = *(const float*)p[5]; w_regSqrt = *(const float*)p[6];
     }
     int numGroups() const override { return 5; }
-    GroupInfo group(int) const override { return { (long)W * H, 2, true }; }
+    GroupInfo group(int g) const override { return { (long)W * H, 2, true, g < 4 ? 5 : 2 }; }
     bool excluded(int, long e) const override { return !(Mask[e] == T(0)); }   // Exclude(Not(eq(Mask,0)))
     template <class A> void eval(int g, long i, A& X, typename A::S* out) const {
         using S = typename A::S;
@@ -226,7 +226,7 @@ struct ArapMesh : Energy<T> {
         nEdges = *(const int*)p[6]; v0 = (const int*)p[7]; v1 = (const int*)p[8];
     }
     int numGroups() const override { return 2; }
-    GroupInfo group(int g) const override { return g == 0 ? GroupInfo{ N, 3, true } : GroupInfo{ (long)nEdges, 3, false }; }
+    GroupInfo group(int g) const override { return g == 0 ? GroupInfo{ N, 3, true, 3 } : GroupInfo{ (long)nEdges, 3, false, 9 }; }
     template <class A> void eval(int g, long i, A& X, typename A::S* out) const {
         using S = typename A::S;
         if (g == 0) {
@@ -258,7 +258,7 @@ struct Poisson : Energy<T> {
     }
     void bind(void** p) override { this->U[0].data = (T*)p[0]; Tg = (const T*)p[1]; M = (const T*)p[2]; }
     int numGroups() const override { return 4; }
-    GroupInfo group(int) const override { return { (long)W * H, 4, true }; }
+    GroupInfo group(int) const override { return { (long)W * H, 4, true, 8 }; }
     bool excluded(int, long e) const override { return !(M[e] == T(0)); }
     template <class A> void eval(int g, long i, A& X, typename A::S* out) const {
         using S = typename A::S;
@@ -286,7 +286,7 @@ struct Laplacian : Energy<T> {
     }
     void bind(void** p) override { this->U[0].data = (T*)p[0]; A_ = (const T*)p[1]; }
     int numGroups() const override { return 3; }
-    GroupInfo group(int) const override { return { (long)W * H, 1, true }; }
+    GroupInfo group(int) const override { return { (long)W * H, 1, true, 2 }; }
     template <class A> void eval(int g, long i, A& X, typename A::S* out) const {
         using S = typename A::S;
         int x = int(i % W), y = int(i / W);
@@ -363,14 +363,17 @@ struct Oracle : OracleBase {
     long nU = 0;
     // sparse Jacobian rows for the current linearisation
     std::vector<long> rowStart;    // per group: first row
-    std::vector<long> colIdx;      // rows * KMAX (unused = -1)
+    std::vector<long> entStart;    // per group: first Jacobian entry; row r of group g owns entries [entStart[g] + (r-rowStart[g])*nd, +nd)
+    std::vector<int> colIdx;       // unused slots = -1
     std::vector<T> colVal;
+    std::vector<int> entRow;       // entry -> row
+    long nEnt = 0;
     std::vector<T> F;              // residual per row
     std::vector<char> rowCost;     // row contributes to cost/model cost (centre not excluded)
     std::vector<char> active;      // per unknown scalar: not excluded
     long nRows = 0;
     // transpose structure
-    std::vector<long> tStart, tEntry;
+    std::vector<long> tStart; std::vector<int> tEntry;
     bool haveT = false;
     // PCG state (solverGPUGaussNewton.t:173-185)
     std::vector<T> delta, r, b, Adelta, z, p, Ap, CtC, pre, SSq, prevX;
@@ -415,16 +418,24 @@ struct Oracle : OracleBase {
     // ---- linearise: residuals + Jacobian rows at the current unknowns
     void linearise(bool withJ) {
         int G = E->numGroups();
-        rowStart.assign(G + 1, 0);
-        for (int g = 0; g < G; ++g) { GroupInfo gi = E->group(g); rowStart[g + 1] = rowStart[g] + gi.count * gi.nres; }
-        bool resized = (nRows != rowStart[G]);
-        nRows = rowStart[G];
+        rowStart.assign(G + 1, 0); entStart.assign(G + 1, 0);
+        for (int g = 0; g < G; ++g) {
+            GroupInfo gi = E->group(g);
+            rowStart[g + 1] = rowStart[g] + gi.count * gi.nres;
+            entStart[g + 1] = entStart[g] + gi.count * gi.nres * gi.ndeps;
+        }
+        bool resized = (nRows != rowStart[G]) || (nEnt != entStart[G]);
+        nRows = rowStart[G]; nEnt = entStart[G];
         F.resize(nRows); rowCost.resize(nRows);
-        if (withJ) { if (resized || colIdx.size() != (size_t)nRows * KMAX) { colIdx.assign(nRows * KMAX, -1); colVal.assign(nRows * KMAX, T(0)); haveT = false; } }
+        if (withJ && (resized || colIdx.size() != (size_t)nEnt)) {
+            colIdx.assign(nEnt, -1); colVal.assign(nEnt, T(0)); entRow.assign(nEnt, 0); haveT = false;
+        }
+        bool structureChanged = false;
         for (int g = 0; g < G; ++g) {
             GroupInfo gi = E->group(g);
             int ca = E->centerArray(g);
-#pragma omp parallel for schedule(static)
+            const int nd = gi.ndeps;
+#pragma omp parallel for schedule(static) reduction(|| : structureChanged)
             for (long i = 0; i < gi.count; ++i) {
                 long row0 = rowStart[g] + i * gi.nres;
                 char rc = 1;
@@ -433,15 +444,16 @@ struct Oracle : OracleBase {
                     DualAcc<T> X; X.U = &E->U;
                     Dual<T> out[RMAX];
                     E->evalD(g, i, X, out);
+                    if (X.n > nd) { fprintf(stderr, "oracle: group %d declares %d deps but touched %d\n", g, nd, X.n); abort(); }
                     for (int k = 0; k < gi.nres; ++k) {
                         long row = row0 + k;
+                        long e0 = entStart[g] + (row - rowStart[g]) * nd;
                         F[row] = out[k].v; rowCost[row] = rc;
-                        for (int s = 0; s < KMAX; ++s) {
-                            if (s < X.n) {
-                                long gidx = X.idx[s];
-                                if (colIdx[row * KMAX + s] != gidx) { colIdx[row * KMAX + s] = gidx; haveT = false; }
-                                colVal[row * KMAX + s] = out[k].d[s];
-                            } else if (colIdx[row * KMAX + s] != -1) { colIdx[row * KMAX + s] = -1; haveT = false; }
+                        for (int s = 0; s < nd; ++s) {
+                            int want = s < X.n ? (int)X.idx[s] : -1;
+                            if (colIdx[e0 + s] != want) { colIdx[e0 + s] = want; structureChanged = true; }
+                            colVal[e0 + s] = s < X.n ? out[k].d[s] : T(0);
+                            entRow[e0 + s] = (int)row;
                         }
                     }
                 } else {
@@ -452,25 +464,30 @@ struct Oracle : OracleBase {
                 }
             }
         }
+        if (structureChanged) haveT = false;
         if (withJ && !haveT) buildTranspose();
     }
     void buildTranspose() {
         tStart.assign(nU + 1, 0);
-        for (long e = 0; e < nRows * KMAX; ++e) if (colIdx[e] >= 0) tStart[colIdx[e] + 1]++;
+        for (long e = 0; e < nEnt; ++e) if (colIdx[e] >= 0) tStart[colIdx[e] + 1]++;
         for (long u = 0; u < nU; ++u) tStart[u + 1] += tStart[u];
         tEntry.resize(tStart[nU]);
         std::vector<long> fill(tStart.begin(), tStart.end() - 1);
-        for (long e = 0; e < nRows * KMAX; ++e) if (colIdx[e] >= 0) tEntry[fill[colIdx[e]]++] = e;
+        for (long e = 0; e < nEnt; ++e) if (colIdx[e] >= 0) tEntry[fill[colIdx[e]]++] = (int)e;
         haveT = true;
     }
     // y = J x (x has zeros at excluded unknowns by construction)
     void mulJ(const std::vector<T>& x, std::vector<double>& y) const {
         y.resize(nRows);
+        for (int g = 0; g < E->numGroups(); ++g) {
+            const int nd = E->group(g).ndeps;
 #pragma omp parallel for schedule(static)
-        for (long row = 0; row < nRows; ++row) {
-            double s = 0;
-            for (int k = 0; k < KMAX; ++k) { long c = colIdx[row * KMAX + k]; if (c >= 0 && active[c]) s += (double)colVal[row * KMAX + k] * (double)x[c]; }
-            y[row] = s;
+            for (long row = rowStart[g]; row < rowStart[g + 1]; ++row) {
+                long e0 = entStart[g] + (row - rowStart[g]) * nd;
+                double s = 0;
+                for (int k = 0; k < nd; ++k) { int c = colIdx[e0 + k]; if (c >= 0 && active[c]) s += (double)colVal[e0 + k] * (double)x[c]; }
+                y[row] = s;
+            }
         }
     }
     // out = J^T y restricted to active unknowns
@@ -478,7 +495,7 @@ struct Oracle : OracleBase {
 #pragma omp parallel for schedule(static)
         for (long u = 0; u < nU; ++u) {
             double s = 0;
-            if (active[u]) for (long t = tStart[u]; t < tStart[u + 1]; ++t) { long e = tEntry[t]; s += (double)colVal[e] * (double)y[e / KMAX]; }
+            if (active[u]) for (long t = tStart[u]; t < tStart[u + 1]; ++t) { long e = tEntry[t]; s += (double)colVal[e] * (double)y[entRow[e]]; }
             out[u] = T(s);
         }
     }

@@ -182,25 +182,29 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJ(IWData<T> D, ReduceWorksp
 }
 
 // ------------------------------------------------------------------------------------ PCGStep1, TMA-tiled (fp32)
-// Same arithmetic as k_iwApplyJTJ, different data movement: a persistent CTA walks 64x8-pixel tiles; one
-// elected thread streams each tile (+1 halo) of z, p and geom into shared memory with
-// cp.async.bulk.tensor (TMA) under an mbarrier, kStages tiles ahead of the math, so HBM latency is
-// hidden by the copy engine instead of by warp occupancy (the direct-load version stalls on
-// long_scoreboard, profiles/r1_*).  Out-of-image halo cells are zero-filled by the TMA unit.  With
-// FUSE3 the new direction p = z + beta*pOld is formed once per staged cell in shared memory.
-constexpr int kTW = 64, kTH = 8, kStages = 3;
+// Same operator as k_iwApplyJTJ, different data movement and schedule.  A persistent CTA walks
+// 64x16-pixel tiles; one elected thread streams each tile (+halo) of z, p, geom and the flag bytes into
+// shared memory with cp.async.bulk.tensor (TMA) under an mbarrier, one tile ahead of the math, so HBM
+// latency is hidden by the copy engine rather than by warp occupancy (the direct-load kernel stalls on
+// long_scoreboard, profiles/r1_ncu_iw.md).  Out-of-image halo cells are zero-filled by the TMA unit.
+// With FUSE3 the new direction p = z + beta*pOld is formed once per staged cell in shared memory.
+// Each thread marches down a 4-pixel column strip: the vertical pair term is evaluated once and
+// credited to both of its pixels (the J^T J pair block is antisymmetric in the offset rows), the
+// horizontal pairs are evaluated one-sided from both ends so no cross-lane exchange is needed.
+constexpr int kTW = 64, kTH = 16, kStages = 2, kStrip = 4;
 // TMA rule (measured, tools/scratch/tma_probe.cu): the innermost box coordinate must start on a 16-byte
 // boundary, so 2-channel rows are staged from pixel x0-2 and 1-channel rows from pixel x0-4.
 constexpr int kRowO = 2 * (kTW + 4);      // floats per staged row of a 2-channel image (pixels x0-2 .. x0+TW+1)
 constexpr int kRowA = kTW + 8;            // floats per staged row of a 1-channel image (pixels x0-4 .. x0+TW+3)
 constexpr int kRows = kTH + 2;
-constexpr int kBytesO = kRows * kRowO * 4, kBytesA = kRows * kRowA * 4, kBytesG = kRows * (kTW + 2) * 16;
+constexpr int kBytesO = kRows * kRowO * 4, kBytesA = kRows * kRowA * 4, kBytesG = kRows * (kTW + 2) * 16, kBytesF = kTH * kTW;
 constexpr int align128(int v) { return (v + 127) / 128 * 128; }
-constexpr int kOffPO = 0, kOffPA = kOffPO + align128(kBytesO), kOffG = kOffPA + align128(kBytesA);
-constexpr int kOffZO = kOffG + align128(kBytesG), kOffZA = kOffZO + align128(kBytesO);
+constexpr int kOffPO = 0, kOffPA = kOffPO + align128(kBytesO), kOffG = kOffPA + align128(kBytesA), kOffF = kOffG + align128(kBytesG);
+constexpr int kOffZO = kOffF + align128(kBytesF), kOffZA = kOffZO + align128(kBytesO);
 constexpr int kStageBytesPlain = kOffZO, kStageBytesFused = kOffZA + align128(kBytesA);
+static_assert(kBlock == kTW * (kTH / kStrip), "thread mapping: one thread per column strip");
 
-struct IWMaps { CUtensorMap pO, pA, zO, zA, geom; };
+struct IWMaps { CUtensorMap pO, pA, zO, zA, geom, flags; };
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count)); }
@@ -225,6 +229,32 @@ __device__ __forceinline__ void tmaLoad3D(void* dst, const CUtensorMap* map, uin
                  ::"r"(smemAddr(dst)), "l"(map), "r"(smemAddr(bar)), "r"(c), "r"(x), "r"(y) : "memory");
 }
 
+struct IWPoint { float c, s, ux, uy, px, py, pa; };   // one staged cell: geom + direction
+__device__ __forceinline__ IWPoint iwLoadPoint(const float4* sG, const float* sPO, const float* sPA, int r, int lx) {
+    const float4 g = sG[r * (kTW + 2) + lx + 1];
+    const float2 p = *reinterpret_cast<const float2*>(&sPO[r * kRowO + 2 * (lx + 2)]);
+    const float a = sPA[r * kRowA + lx + 4];
+    return IWPoint{ g.x, g.y, g.z, g.w, p.x, p.y, a };
+}
+// pair term for the pair (i, j):  t is credited +t to Ap_O(i) and -t to Ap_O(j); Ai / Aj go to Ap_a(i) / Ap_a(j)
+__device__ __forceinline__ void iwPairBoth(const IWPoint& i, const IWPoint& j, float& tx, float& ty, float& Ai, float& Aj) {
+    const float dx = i.ux - j.ux, dy = i.uy - j.uy;
+    const float eix = -i.s * dx - i.c * dy, eiy = i.c * dx - i.s * dy;
+    const float ejx = -j.s * dx - j.c * dy, ejy = j.c * dx - j.s * dy;
+    const float px = i.px - j.px, py = i.py - j.py;
+    tx = 2.f * px - eix * i.pa - ejx * j.pa; ty = 2.f * py - eiy * i.pa - ejy * j.pa;
+    Ai = (eix * eix + eiy * eiy) * i.pa - (eix * px + eiy * py);
+    Aj = (ejx * ejx + ejy * ejy) * j.pa - (ejx * px + ejy * py);
+}
+__device__ __forceinline__ void iwPairOne(const IWPoint& i, const IWPoint& j, float& tx, float& ty, float& Ai) {
+    const float dx = i.ux - j.ux, dy = i.uy - j.uy;
+    const float eix = -i.s * dx - i.c * dy, eiy = i.c * dx - i.s * dy;
+    const float ejx = -j.s * dx - j.c * dy, ejy = j.c * dx - j.s * dy;
+    const float px = i.px - j.px, py = i.py - j.py;
+    tx = 2.f * px - eix * i.pa - ejx * j.pa; ty = 2.f * py - eiy * i.pa - ejy * j.pa;
+    Ai = (eix * eix + eiy * eiy) * i.pa - (eix * px + eiy * py);
+}
+
 template <bool FUSE3, bool LM>
 __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const __grid_constant__ IWMaps M, ReduceWorkspace ws, int dotSlot, int rzNew,
                                                           int rzOld, float* __restrict__ pOut, float* __restrict__ out, const float* __restrict__ CtC,
@@ -246,10 +276,11 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
     auto issue = [&](int tile, int stage) {   // one thread
         unsigned char* base = smem + (size_t)stage * stageBytes;
         const int x0 = (tile % tilesX) * kTW, y0 = (tile / tilesX) * kTH;
-        mbarExpectTx(&bars[stage], (unsigned)(kBytesO + kBytesA + kBytesG + (FUSE3 ? kBytesO + kBytesA : 0)));
+        mbarExpectTx(&bars[stage], (unsigned)(kBytesO + kBytesA + kBytesG + kBytesF + (FUSE3 ? kBytesO + kBytesA : 0)));
         tmaLoad2D(base + kOffPO, &M.pO, &bars[stage], 2 * (x0 - 2), y0 - 1);
         tmaLoad2D(base + kOffPA, &M.pA, &bars[stage], x0 - 4, y0 - 1);
         tmaLoad3D(base + kOffG, &M.geom, &bars[stage], 0, x0 - 1, y0 - 1);
+        tmaLoad2D(base + kOffF, &M.flags, &bars[stage], x0, y0);
         if (FUSE3) {
             tmaLoad2D(base + kOffZO, &M.zO, &bars[stage], 2 * (x0 - 2), y0 - 1);
             tmaLoad2D(base + kOffZA, &M.zA, &bars[stage], x0 - 4, y0 - 1);
@@ -259,7 +290,7 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
         for (int s = 0; s < kStages; ++s) { const int t = blockIdx.x + s * gridDim.x; if (t < numTiles) issue(t, s); }
     }
     const float w2 = D.w * D.w, wf2 = D.wf * D.wf;
-    const int lx = tid & (kTW - 1), lyBase = (tid >> 6) * 2;   // 256 threads = 64 columns x 4 row pairs
+    const int lx = tid & (kTW - 1), ly0 = (tid >> 6) * kStrip;   // 256 threads = 64 columns x 4 strips of 4 rows
     float acc = 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
@@ -267,61 +298,63 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
         const unsigned parity = (unsigned)((it / kStages) & 1);
         unsigned char* base = smem + (size_t)stage * stageBytes;
         const int x0 = (tile % tilesX) * kTW, y0 = (tile / tilesX) * kTH;
-        const int gx = x0 + lx;
-        unsigned fl[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) { const int gy = y0 + lyBase + q; fl[q] = (gx < D.W && gy < D.H) ? D.flags[(long)gy * D.W + gx] : 0u; }
         mbarWait(&bars[stage], parity);
         float* sPO = reinterpret_cast<float*>(base + kOffPO);
         float* sPA = reinterpret_cast<float*>(base + kOffPA);
         const float4* sG = reinterpret_cast<const float4*>(base + kOffG);
+        const unsigned char* sF = base + kOffF;
         if (FUSE3) {   // p = z + beta * pOld for every staged cell (halo included), in place
             const float4* zO4 = reinterpret_cast<const float4*>(base + kOffZO); float4* pO4 = reinterpret_cast<float4*>(sPO);
-            for (int i = tid; i < kRows * kRowO / 4; i += kBlock) { float4 zv = zO4[i], pv = pO4[i]; pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y; pv.z = zv.z + beta * pv.z; pv.w = zv.w + beta * pv.w; pO4[i] = pv; }
+#pragma unroll 2
+            for (int i = tid; i < kRows * kRowO / 4; i += kBlock) { const float4 zv = zO4[i]; float4 pv = pO4[i]; pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y; pv.z = zv.z + beta * pv.z; pv.w = zv.w + beta * pv.w; pO4[i] = pv; }
             const float4* zA4 = reinterpret_cast<const float4*>(base + kOffZA); float4* pA4 = reinterpret_cast<float4*>(sPA);
-            for (int i = tid; i < kRows * kRowA / 4; i += kBlock) { float4 zv = zA4[i], pv = pA4[i]; pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y; pv.z = zv.z + beta * pv.z; pv.w = zv.w + beta * pv.w; pA4[i] = pv; }
+            for (int i = tid; i < kRows * kRowA / 4; i += kBlock) { const float4 zv = zA4[i]; float4 pv = pA4[i]; pv.x = zv.x + beta * pv.x; pv.y = zv.y + beta * pv.y; pv.z = zv.z + beta * pv.z; pv.w = zv.w + beta * pv.w; pA4[i] = pv; }
             __syncthreads();
         }
+        const int gx = x0 + lx;
+        // staged row r holds image row y0 - 1 + r; pixel (lx, ly) is the cell (r = ly + 1)
+        IWPoint up = iwLoadPoint(sG, sPO, sPA, ly0, lx);
+        IWPoint cur = iwLoadPoint(sG, sPO, sPA, ly0 + 1, lx);
+        float cx = 0.f, cy = 0.f, ca = 0.f;   // contribution of the pair with the pixel above, carried down the strip
+        {
+            const unsigned f0 = sF[ly0 * kTW + lx];
+            float tx, ty, Ai, Aj; iwPairBoth(up, cur, tx, ty, Ai, Aj);
+            const float v = (f0 & 8u) ? 1.f : 0.f;   // bit 3: neighbour (0,-1)
+            cx = -v * tx; cy = -v * ty; ca = v * Aj;
+        }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int ly = lyBase + q, gy = y0 + ly;
+        for (int q = 0; q < kStrip; ++q) {
+            const int ly = ly0 + q, r = ly + 1, gy = y0 + ly;
+            const unsigned fl = sF[ly * kTW + lx];
+            const IWPoint dn = iwLoadPoint(sG, sPO, sPA, r + 1, lx);
+            const IWPoint lf = iwLoadPoint(sG, sPO, sPA, r, lx - 1);
+            const IWPoint rt = iwLoadPoint(sG, sPO, sPA, r, lx + 1);
+            float ax = cx, ay = cy, aa = ca;
+            float tx, ty, Ai, Aj;
+            iwPairBoth(cur, dn, tx, ty, Ai, Aj);
+            const float vd = (fl & 4u) ? 1.f : 0.f;     // bit 2: neighbour (0,+1)
+            ax += vd * tx; ay += vd * ty; aa += vd * Ai;
+            cx = -vd * tx; cy = -vd * ty; ca = vd * Aj;
+            iwPairOne(cur, rt, tx, ty, Ai);
+            const float vr = (fl & 1u) ? 1.f : 0.f;     // bit 0: neighbour (+1,0)
+            ax += vr * tx; ay += vr * ty; aa += vr * Ai;
+            iwPairOne(cur, lf, tx, ty, Ai);
+            const float vl = (fl & 2u) ? 1.f : 0.f;     // bit 1: neighbour (-1,0)
+            ax += vl * tx; ay += vl * ty; aa += vl * Ai;
+            const float vf = (fl & 16u) ? wf2 : 0.f;
+            float2 oO = make_float2(w2 * ax + vf * cur.px, w2 * ay + vf * cur.py);
+            float oA = w2 * aa;
             if (gx < D.W && gy < D.H) {
                 const long i = (long)gy * D.W + gx;
-                float2 oO = make_float2(0.f, 0.f); float oA = 0.f;
-                float2 pi = make_float2(0.f, 0.f); float pai = 0.f;
-                if (fl[q] & 32u) {
-                    const int r = ly + 1, c = lx + 1;             // staged coordinates of the centre
-                    const float4 gi = sG[r * (kTW + 2) + c];
-                    pi = *reinterpret_cast<const float2*>(&sPO[r * kRowO + 2 * (c + 1)]);
-                    pai = sPA[r * kRowA + c + 3];
-                    float ax = 0.f, ay = 0.f, aa = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (fl[q] & (1u << k)) {
-                            const int rr = r + (k == 2 ? 1 : (k == 3 ? -1 : 0)), cc = c + (k == 0 ? 1 : (k == 1 ? -1 : 0));
-                            const float4 gj = sG[rr * (kTW + 2) + cc];
-                            const float2 pj = *reinterpret_cast<const float2*>(&sPO[rr * kRowO + 2 * (cc + 1)]);
-                            const float paj = sPA[rr * kRowA + cc + 3];
-                            const float dx = gi.z - gj.z, dy = gi.w - gj.w;
-                            const float eix = -gi.y * dx - gi.x * dy, eiy = gi.x * dx - gi.y * dy;
-                            const float ejx = -gj.y * dx - gj.x * dy, ejy = gj.x * dx - gj.y * dy;
-                            const float px = pi.x - pj.x, py = pi.y - pj.y;
-                            ax += 2.f * px - eix * pai - ejx * paj;
-                            ay += 2.f * py - eiy * pai - ejy * paj;
-                            aa += (eix * eix + eiy * eiy) * pai - (eix * px + eiy * py);
-                        }
-                    }
-                    oO.x = w2 * ax; oO.y = w2 * ay; oA = w2 * aa;
-                    if (fl[q] & 16u) { oO.x += wf2 * pi.x; oO.y += wf2 * pi.y; }
-                    if (LM) {
-                        const float2 cO = reinterpret_cast<const float2*>(CtC)[i];
-                        oO.x += cO.x * pi.x; oO.y += cO.y * pi.y; oA += CtC[D.offA + i] * pai;
-                    }
-                    acc += pi.x * oO.x + pi.y * oO.y + pai * oA;
+                if (LM) {
+                    const float2 cO = reinterpret_cast<const float2*>(CtC)[i];
+                    oO.x += cO.x * cur.px; oO.y += cO.y * cur.py; oA += CtC[D.offA + i] * cur.pa;
                 }
+                acc += cur.px * oO.x + cur.py * oO.y + cur.pa * oA;
                 reinterpret_cast<float2*>(out)[i] = oO; out[D.offA + i] = oA;
-                if (FUSE3) { reinterpret_cast<float2*>(pOut)[i] = pi; pOut[D.offA + i] = pai; }
+                if (FUSE3) { reinterpret_cast<float2*>(pOut)[i] = make_float2(cur.px, cur.py); pOut[D.offA + i] = cur.pa; }
             }
+            cur = dn;
         }
         __syncthreads();   // every thread is done with this stage
         if (tid == 0) {
@@ -431,6 +464,14 @@ struct ImageWarpingOps : EnergyOps<T> {
         if (rc != CUDA_SUCCESS) { fprintf(stderr, "opt_b200: cuTensorMapEncodeTiled(3D) failed: %d\n", (int)rc); exit(3); }
         return m;
     }
+    CUtensorMap mapFlags() {
+        CUtensorMap m; cuuint64_t dims[2] = { (cuuint64_t)D.W, (cuuint64_t)D.H }; cuuint64_t strides[1] = { (cuuint64_t)D.W };
+        cuuint32_t box[2] = { (cuuint32_t)kTW, (cuuint32_t)kTH }, es[2] = { 1, 1 };
+        CUresult rc = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)D.flags, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) { fprintf(stderr, "opt_b200: cuTensorMapEncodeTiled(flags) failed: %d\n", (int)rc); exit(3); }
+        return m;
+    }
     const IWMaps& mapsFor(const float* pIn, const float* z) {
         auto key = std::make_pair((const void*)pIn, (const void*)z);
         auto it = mapCache.find(key);
@@ -442,10 +483,11 @@ struct ImageWarpingOps : EnergyOps<T> {
         m.zO = map2D(zz, 2L * D.W, D.H, 2L * D.W, kRowO, kRows);
         m.zA = map2D(zz + D.offA, D.W, D.H, D.W, kRowA, kRows);
         m.geom = mapGeom();
+        m.flags = mapFlags();
         return mapCache.emplace(key, m).first->second;
     }
     void setupTma(int sms) {
-        if (!std::is_same<T, float>::value || D.W % 4 != 0 || getenv("OPTB_NO_TMA")) return;
+        if (!std::is_same<T, float>::value || D.W % 16 != 0 || getenv("OPTB_NO_TMA")) return;   // 16-byte row pitch rule of the flag-byte map
         void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) return;
         encode = (EncodeFn)fn;

@@ -191,7 +191,12 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJ(IWData<T> D, ReduceWorksp
 // Each thread marches down a 4-pixel column strip: the vertical pair term is evaluated once and
 // credited to both of its pixels (the J^T J pair block is antisymmetric in the offset rows), the
 // horizontal pairs are evaluated one-sided from both ends so no cross-lane exchange is needed.
-constexpr int kTW = 64, kTH = 16, kStages = 2, kStrip = 4;
+#ifndef IW_TH
+#define IW_TH 16
+#define IW_STAGES 2
+#define IW_STRIP 4
+#endif
+constexpr int kTW = 64, kTH = IW_TH, kStages = IW_STAGES, kStrip = IW_STRIP;
 // TMA rule (measured, tools/scratch/tma_probe.cu): the innermost box coordinate must start on a 16-byte
 // boundary, so 2-channel rows are staged from pixel x0-2 and 1-channel rows from pixel x0-4.
 constexpr int kRowO = 2 * (kTW + 4);      // floats per staged row of a 2-channel image (pixels x0-2 .. x0+TW+1)

@@ -1,0 +1,14 @@
+#!/bin/bash
+# Builds oracle/_ref/*.so from the reference's own sources WHERE THEY LIE (/root/reference), for pinning
+# the oracle.  Outputs only under oracle/_ref/ (git-ignored, travels with gpurun).  No reference build
+# system is run: each library is the shim in oracle/ plus the reference headers it includes.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF=/root/reference
+[ -d "$REF" ] || { echo "ref_build: $REF not mounted, keeping prebuilt oracle/_ref"; exit 0; }
+mkdir -p "$HERE/_ref"
+CXX=/usr/bin/g++
+FLAGS="-O2 -fPIC -shared -std=c++14 -w -I/usr/local/cuda/include"
+if [ ! -f "$HERE/_ref/libref_iw.so" ] || [ "$HERE/ref_iw_shim.cpp" -nt "$HERE/_ref/libref_iw.so" ]; then
+  $CXX $FLAGS -I"$REF/examples/image_warping/src" -o "$HERE/_ref/libref_iw.so" "$HERE/ref_iw_shim.cpp"
+fi

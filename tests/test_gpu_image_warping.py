@@ -153,3 +153,24 @@ def test_full_size_properties(built):
     assert all(b <= a * (1 + 1e-6) for a, b in zip(costs, costs[1:])), costs
     assert costs[-1] < costs[0]
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("name,kind", [("image_warping_gn", "gaussNewtonGPU"), ("image_warping_lm", "LMGPU")])
+def test_golden(built, name, kind):
+    """fp64 GPU solve vs the committed golden vectors (tests/golden, no oracle involved at run time)"""
+    import os
+    from opt_b200 import OptSolver, spec_path
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = np.load(os.path.join(root, "tests", "golden", name + ".npz"))
+    host = workloads.image_warping(32, 24, dtype=np.float64, mask="blob" if name.endswith("gn") else "random", seed=9)
+    dev = workloads.to_device(host)
+    s = OptSolver([32, 24], spec_path("image_warping"), kind, double_precision=True)
+    s.set_solver_parameters({"nIterations": int(ref["nIterations"]), "lIterations": int(ref["lIterations"])})
+    s.init(dev)
+    costs = [s.current_cost()]
+    while s.step(dev):
+        costs.append(s.current_cost())
+    assert len(costs) == len(ref["costs"])
+    assert np.allclose(costs, ref["costs"], rtol=1e-8)
+    assert np.allclose(dev[0].cpu().numpy(), ref["unknown0"], rtol=1e-7, atol=1e-8)
+    assert np.allclose(dev[1].cpu().numpy(), ref["unknown1"], rtol=1e-6, atol=1e-8)

@@ -46,6 +46,16 @@ float OptB200_PcgLoopMsLastStep(Opt_Plan* plan);
  * returns the average duration per launch (ms).  names[i] point at static strings.  The PCG state
  * is scratch afterwards -- call Opt_ProblemInit before solving again.  Returns the entry count. */
 int OptB200_ProfileKernels(Opt_Plan* plan, void** problemparams, int reps, int maxOut, const char** names, float* avgMs);
+/* ---- multi-GPU slab decomposition (one process per GPU) --------------------------
+ * Each rank plans its LOCAL domain = owned slab + 1 halo row towards every neighbour and binds local
+ * buffers.  OptB200_PlanCommHandles writes 3 CUDA IPC handles (192 bytes: scalar mailbox, z, p); the host
+ * all-gathers them (any transport, e.g. torch.distributed) and passes the rank-ordered concatenation to
+ * OptB200_PlanConnect together with this rank's owned local rows [ownedBegin, ownedEnd) and the LOCAL row
+ * counts of the upper / lower neighbour (0 = none).  Afterwards Opt_ProblemInit/Step must be called
+ * collectively by all ranks: the PCG scalars are summed through peer-memory mailboxes and the halo rows of
+ * z / p travel by direct NVLink stores, all issued from inside the solver's kernels.  Returns 0 on success. */
+int OptB200_PlanCommHandles(Opt_Plan* plan, void* out, int outBytes);
+int OptB200_PlanConnect(Opt_Plan* plan, int rank, int world, const void* allHandles, int ownedBegin, int ownedEnd, int upperRows, int lowerRows);
 /* Front-end probe (no GPU needed): writes the registry name of the energy in `filename` to `out` and
  * returns 0, or writes the rejection message and returns 1. */
 int OptB200_SpecEnergyName(const char* filename, char* out, int outLen);

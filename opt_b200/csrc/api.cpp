@@ -111,6 +111,10 @@ void OptB200_PlanSetStream(Opt_Plan* plan, void* stream) { plan->impl->setStream
 int OptB200_LaunchesLastStep(Opt_Plan* plan) { return plan->impl->launchesLastStep(); }
 float OptB200_PcgLoopMsLastStep(Opt_Plan* plan) { return plan->impl->pcgLoopMsLastStep(); }
 int OptB200_ProfileKernels(Opt_Plan* plan, void** pp, int reps, int maxOut, const char** names, float* avgMs) { return plan->impl->profileKernels(pp, reps, maxOut, names, avgMs); }
+int OptB200_PlanCommHandles(Opt_Plan* plan, void* out, int outBytes) { return plan->impl->commHandles(out, outBytes); }
+int OptB200_PlanConnect(Opt_Plan* plan, int rank, int world, const void* allHandles, int ownedBegin, int ownedEnd, int upperRows, int lowerRows) {
+    return plan->impl->connect(rank, world, allHandles, ownedBegin, ownedEnd, upperRows, lowerRows);
+}
 int OptB200_SpecEnergyName(const char* filename, char* out, int outLen) {
     optb::SpecMatch m = optb::matchSpecFile(filename);
     snprintf(out, outLen, "%s", m.ok ? m.energy.c_str() : m.message.c_str());

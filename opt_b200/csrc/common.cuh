@@ -40,11 +40,62 @@ enum Scalar : int {
     kNumScalars = 16
 };
 
+constexpr int kMaxRanks = 8;
+
+// Cross-GPU view of the scalar mailboxes ("a single allreduce of the PCG scalars").
+// Every rank owns one mailbox block (cudaMalloc + CUDA IPC); peerPartials[r] / peerFlags[r] are rank r's
+// block mapped into this process.  A reduction's last CTA stores its local sum into slot
+// [scalar][epoch&1][myRank] of EVERY rank's block over NVLink and then releases flag [scalar][myRank] =
+// epoch; consumers spin on their OWN block until all `world` flags reach the epoch and add the `world`
+// partials in rank order, so every rank obtains the bitwise-identical sum with no host involvement and
+// no NCCL launch.  Two parities suffice: a rank cannot produce epoch e+2 of a scalar before every rank
+// has consumed epoch e (it needs every rank's epoch e+1 contribution first).
+struct CommView {
+    int world, rank;
+    double* peerPartials[kMaxRanks];                // [kNumScalars][2][kMaxRanks]
+    unsigned long long* peerFlags[kMaxRanks];       // [kNumScalars][kMaxRanks]
+    unsigned long long* epoch;                      // local [kNumScalars]: epochs produced so far
+};
+
 struct ReduceWorkspace {
     double* partials;        // [kNumScalars][kMaxPartials]
     unsigned int* counters;  // [kNumScalars]  arrival counters, self-resetting
-    double* scalars;         // [kNumScalars]
+    double* scalars;         // [kNumScalars]   (single GPU: the reduced values)
+    CommView comm;           // world == 1: unused
 };
+
+__device__ __forceinline__ unsigned long long ldAcquireSys(const unsigned long long* p) {
+    unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void stReleaseSys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ldRelaxedSysF64(const double* p) {
+    double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v;
+}
+
+// Value of reduction `slot` as seen by every rank (single thread; callers broadcast through shared memory).
+__device__ __forceinline__ double loadScalarGlobal(const ReduceWorkspace& ws, int slot) {
+    if (ws.comm.world <= 1) return ws.scalars[slot];
+    const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(ws.comm.epoch + slot);
+    const unsigned long long* flags = ws.comm.peerFlags[ws.comm.rank] + slot * kMaxRanks;
+    const double* part = ws.comm.peerPartials[ws.comm.rank] + (slot * 2 + (int)(e & 1ull)) * kMaxRanks;
+    double sum = 0.0;
+    for (int r = 0; r < ws.comm.world; ++r) {
+        while (ldAcquireSys(flags + r) < e) {}
+        sum += ldRelaxedSysF64(part + r);
+    }
+    return sum;
+}
+// Block-wide: returns the globally reduced values of two slots to every thread.
+__device__ __forceinline__ void loadScalars2(const ReduceWorkspace& ws, int slotA, int slotB, double& a, double& b) {
+    if (ws.comm.world <= 1) { a = ws.scalars[slotA]; b = ws.scalars[slotB]; return; }
+    __shared__ double s_ab[2];
+    if (threadIdx.x == 0) { s_ab[0] = loadScalarGlobal(ws, slotA); s_ab[1] = loadScalarGlobal(ws, slotB); }
+    __syncthreads();
+    a = s_ab[0]; b = s_ab[1];
+    __syncthreads();
+}
 
 __device__ __forceinline__ double warpSum(double v) {
 #pragma unroll
@@ -87,7 +138,19 @@ __device__ __forceinline__ void gridReduceTo(double v, const ReduceWorkspace& ws
         if (wid == 0) {
             double u = lane < NT / 32 ? s_warp[lane] : 0.0;
             u = warpSum(u);
-            if (lane == 0) { ws.scalars[slot] = u; ws.counters[slot] = 0u; }
+            if (lane == 0) {
+                ws.counters[slot] = 0u;
+                if (ws.comm.world <= 1) {
+                    ws.scalars[slot] = u;
+                } else {   // publish the local sum to every rank's mailbox, then release the flags
+                    const unsigned long long e = ws.comm.epoch[slot] + 1ull;
+                    ws.comm.epoch[slot] = e;
+                    for (int r = 0; r < ws.comm.world; ++r)
+                        ws.comm.peerPartials[r][(slot * 2 + (int)(e & 1ull)) * kMaxRanks + ws.comm.rank] = u;
+                    __threadfence_system();
+                    for (int r = 0; r < ws.comm.world; ++r) stReleaseSys(ws.comm.peerFlags[r] + slot * kMaxRanks + ws.comm.rank, e);
+                }
+            }
         }
     }
     __syncthreads();   // s_warp / s_last reusable by a second call in the same kernel

@@ -40,6 +40,8 @@ struct IWData {
     T w, wf;                 // w_regSqrt, w_fitSqrt (float Params cast to opt_float on use, o.t:1699)
     long offA;               // offset of the Angle block inside the flat PCG vectors
     Vec4<T>* geom; uint8_t* flags;
+    int y0, y1;              // owned local rows (multi-GPU slab; [0,H) on a single GPU).  Rows outside are halo:
+                             // read as neighbours, never written as results, flags = 0
 };
 
 constexpr int kTileW = 32, kTileH = 8;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(kBlock) k_iwInit(IWData<T> D, ReduceWorkspace 
         uint8_t fl = 0;
         Vec2<T> rO{ T(0), T(0) }, pO{ T(0), T(0) }, preO{ T(0), T(0) };
         T rA = T(0), pA = T(0), preA = T(0);
-        if (D.Mask[i] == T(0)) {
+        if (y >= D.y0 && y < D.y1 && D.Mask[i] == T(0)) {
             const Vec2<T> Oi = D.Offset[i];
             T gx = T(0), gy = T(0), gA = T(0), dO = T(0), dA = T(0);
             const T w = D.w, w2 = D.w * D.w;
@@ -132,7 +134,8 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJ(IWData<T> D, ReduceWorksp
                                                        T* __restrict__ out, const T* __restrict__ CtC) {
     T beta = T(0);
     if (FUSE3) {
-        const T rn = (T)ws.scalars[rzNew], ro = (T)ws.scalars[rzOld];
+        double drn, dro; loadScalars2(ws, rzNew, rzOld, drn, dro);
+        const T rn = (T)drn, ro = (T)dro;
         if (ro > T(0)) beta = rn / ro;
     }
     const Vec2<T>* pInO = reinterpret_cast<const Vec2<T>*>(pIn);
@@ -146,10 +149,13 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJ(IWData<T> D, ReduceWorksp
         const unsigned fl = D.flags[i];
         Vec2<T> oO{ T(0), T(0) }; T oA = T(0);
         Vec2<T> pi{ T(0), T(0) }; T pai = T(0);
+        if (FUSE3) {   // every pixel (halo rows included) gets its new direction; only active owned pixels get an Ap
+            pi = pInO[i]; pai = pInA[i];
+            const Vec2<T> zi = zO[i]; pi.x = zi.x + beta * pi.x; pi.y = zi.y + beta * pi.y; pai = zA[i] + beta * pai;
+        }
         if (fl & 32u) {
             const Vec4<T> gi = D.geom[i];
-            pi = pInO[i]; pai = pInA[i];
-            if (FUSE3) { const Vec2<T> zi = zO[i]; pi.x = zi.x + beta * pi.x; pi.y = zi.y + beta * pi.y; pai = zA[i] + beta * pai; }
+            if (!FUSE3) { pi = pInO[i]; pai = pInA[i]; }
             T ax = T(0), ay = T(0), aa = T(0);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -270,7 +276,8 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
     const int tid = threadIdx.x;
     float beta = 0.f;
     if (FUSE3) {
-        const float rn = (float)ws.scalars[rzNew], ro = (float)ws.scalars[rzOld];
+        double drn, dro; loadScalars2(ws, rzNew, rzOld, drn, dro);
+        const float rn = (float)drn, ro = (float)dro;
         if (ro > 0.f) beta = rn / ro;
     }
     if (tid == 0) {
@@ -380,7 +387,7 @@ __global__ void __launch_bounds__(kBlock) k_iwCost(IWData<T> D, ReduceWorkspace 
     const T* dA = MODEL ? delta + D.offA : nullptr;
     IW_TILE_LOOP(D) {
         const long i = (long)y * D.W + x;
-        if (D.Mask[i] == T(0)) {
+        if (y >= D.y0 && y < D.y1 && D.Mask[i] == T(0)) {
             const Vec2<T> Oi = D.Offset[i], Ui = D.UrShape[i];
             T s, c; sincosT(D.Angle[i], &s, &c);
             Vec2<T> di{ T(0), T(0) }; T dai = T(0);
@@ -509,7 +516,7 @@ struct ImageWarpingOps : EnergyOps<T> {
         tmaOk = true;
     }
     ImageWarpingOps(const unsigned* dims) {
-        D.W = (int)dims[0]; D.H = (int)dims[1];
+        D.W = (int)dims[0]; D.H = (int)dims[1]; D.y0 = 0; D.y1 = D.H;
         D.tilesX = (D.W + kTileW - 1) / kTileW; D.numTiles = D.tilesX * ((D.H + kTileH - 1) / kTileH);
         const long N = (long)D.W * D.H;
         this->unknowns.resize(2);
@@ -536,6 +543,30 @@ struct ImageWarpingOps : EnergyOps<T> {
     }
     ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); }
     const char* name() const override { return "image_warping"; }
+    int upperRows = 0, lowerRows = 0;
+    bool setSlab(int ownedBegin, int ownedEnd, int up, int dn) override {
+        if (ownedBegin < 0 || ownedEnd > D.H || ownedBegin >= ownedEnd || D.W % 4 != 0) return false;
+        D.y0 = ownedBegin; D.y1 = ownedEnd; upperRows = up; lowerRows = dn;
+        return true;
+    }
+    static long alignUp64(long v) { return (v + 63) / 64 * 64; }
+    std::vector<typename EnergyOps<T>::HaloSegment> haloSegments() const override {
+        std::vector<typename EnergyOps<T>::HaloSegment> s;
+        const long W = D.W;
+        if (upperRows > 0) {   // my first owned row -> last local row of the upper neighbour
+            s.push_back({ 2 * W * D.y0, 2 * W * (upperRows - 1), 2 * W, 0 });
+            s.push_back({ D.offA + W * D.y0, alignUp64(2 * W * upperRows) + W * (upperRows - 1), W, 0 });
+        }
+        if (lowerRows > 0) {   // my last owned row -> local row 0 of the lower neighbour
+            s.push_back({ 2 * W * (D.y1 - 1), 0, 2 * W, 1 });
+            s.push_back({ D.offA + W * (D.y1 - 1), alignUp64(2 * W * lowerRows), W, 1 });
+        }
+        return s;
+    }
+    std::vector<std::pair<long, long>> ownedScalarRanges() const override {
+        const long W = D.W;
+        return { { 2 * W * D.y0, 2 * W * D.y1 }, { D.offA + W * D.y0, D.offA + W * D.y1 } };
+    }
     void bind(void** q) override {   // positions: image_warping.t:2-8
         this->unknowns[0].user = q[0]; this->unknowns[1].user = q[1];
         D.Offset = (const Vec2<T>*)q[0]; D.Angle = (const T*)q[1]; D.UrShape = (const Vec2<T>*)q[2];

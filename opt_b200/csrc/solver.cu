@@ -28,21 +28,37 @@ template <class T> __device__ __forceinline__ void unpack(const double2& v, T* a
 __device__ __forceinline__ float4 pack(const float* a) { return make_float4(a[0], a[1], a[2], a[3]); }
 __device__ __forceinline__ double2 pack(const double* a) { return make_double2(a[0], a[1]); }
 
+// Multi-GPU: which entries of the flat vectors this rank owns (in VecOf<T>::N-wide units).  Halo entries
+// are streamed like everything else (so delta/p stay bitwise consistent with their owner) but must not
+// be counted in dot products.  n == 0 means "everything" (single GPU).
+struct OwnedRanges {
+    long lo[4], hi[4]; int n;
+    __device__ __forceinline__ bool owns(long i) const {
+        if (n == 0) return true;
+        bool o = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o = o || (k < n && i >= lo[k] && i < hi[k]);
+        return o;
+    }
+};
+
 // ------------------------------------------------------------------------------------ PCGStep2
 // solverGPUGaussNewton.t:446-489.  alpha = rz_old / pAp (guarded), delta += alpha p, r -= alpha Ap,
 // z = pre*r, rz_new = z.r ; LM: q = 1/2 delta.(r+b).
 template <class T, bool LM, bool USEPRE>
-__global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, ReduceWorkspace ws, int rzOld, int rzNew,
+__global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, ReduceWorkspace ws, OwnedRanges own, int rzOld, int rzNew,
                                                      T* __restrict__ delta, const T* __restrict__ p, T* __restrict__ r,
                                                      const T* __restrict__ Ap, const T* __restrict__ pre,
                                                      const T* __restrict__ b, T* __restrict__ z) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
     if (LM && ws.scalars[kFlags] != 0.0) return;
-    const T num = (T)ws.scalars[rzOld], den = (T)ws.scalars[kPAp];
+    double dnum, dden; loadScalars2(ws, rzOld, kPAp, dnum, dden);
+    const T num = (T)dnum, den = (T)dden;
     T alpha = T(0);
     if (den > T(0)) alpha = num / den;
     T accRz = T(0), accQ = T(0);
     for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
+        const bool mine = own.owns(i);
         T d[N], pp[N], rr[N], ap[N], pr[N], bb[N], zz[N];
         unpack(reinterpret_cast<const V*>(delta)[i], d);
         unpack(reinterpret_cast<const V*>(p)[i], pp);
@@ -55,8 +71,10 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, ReduceWorkspace 
             d[k] = d[k] + alpha * pp[k];
             rr[k] = rr[k] - alpha * ap[k];
             zz[k] = USEPRE ? pr[k] * rr[k] : rr[k];
-            accRz += zz[k] * rr[k];
-            if (LM) accQ += T(0.5) * (d[k] * (rr[k] + bb[k]));
+            if (mine) {
+                accRz += zz[k] * rr[k];
+                if (LM) accQ += T(0.5) * (d[k] * (rr[k] + bb[k]));
+            }
         }
         reinterpret_cast<V*>(delta)[i] = pack(d);
         reinterpret_cast<V*>(r)[i] = pack(rr);
@@ -71,7 +89,8 @@ template <class T>
 __global__ void __launch_bounds__(kBlock) k_pcgStep2FirstHalf(long nVec, ReduceWorkspace ws, int rzOld, T* __restrict__ delta, const T* __restrict__ p) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
     if (ws.scalars[kFlags] != 0.0) return;
-    const T num = (T)ws.scalars[rzOld], den = (T)ws.scalars[kPAp];
+    double dnum, dden; loadScalars2(ws, rzOld, kPAp, dnum, dden);
+    const T num = (T)dnum, den = (T)dden;
     T alpha = T(0);
     if (den > T(0)) alpha = num / den;
     for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
@@ -84,7 +103,7 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2FirstHalf(long nVec, ReduceW
 }
 // PCGStep2_2ndHalf (:505-534): r = b - Adelta, z = pre*r, rz_new, q
 template <class T, bool USEPRE>
-__global__ void __launch_bounds__(kBlock) k_pcgStep2SecondHalf(long nVec, ReduceWorkspace ws, int rzNew, const T* __restrict__ delta,
+__global__ void __launch_bounds__(kBlock) k_pcgStep2SecondHalf(long nVec, ReduceWorkspace ws, OwnedRanges own, int rzNew, const T* __restrict__ delta,
                                                                T* __restrict__ r, const T* __restrict__ Adelta, const T* __restrict__ pre,
                                                                const T* __restrict__ b, T* __restrict__ z) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
@@ -99,8 +118,10 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2SecondHalf(long nVec, Reduce
         for (int k = 0; k < N; ++k) {
             rr[k] = bb[k] - ad[k];
             zz[k] = USEPRE ? pr[k] * rr[k] : rr[k];
-            accRz += zz[k] * rr[k];
-            accQ += T(0.5) * (d[k] * (rr[k] + bb[k]));
+            if (own.owns(i)) {
+                accRz += zz[k] * rr[k];
+                accQ += T(0.5) * (d[k] * (rr[k] + bb[k]));
+            }
         }
         reinterpret_cast<V*>(r)[i] = pack(rr); reinterpret_cast<V*>(z)[i] = pack(zz);
     }
@@ -114,7 +135,8 @@ template <class T, bool LM>
 __global__ void __launch_bounds__(kBlock) k_pcgStep3(long nVec, ReduceWorkspace ws, int rzNew, int rzOld, const T* __restrict__ z, T* __restrict__ p) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
     if (LM && ws.scalars[kFlags] != 0.0) return;
-    const T rn = (T)ws.scalars[rzNew], ro = (T)ws.scalars[rzOld];
+    double drn, dro; loadScalars2(ws, rzNew, rzOld, drn, dro);
+    const T rn = (T)drn, ro = (T)dro;
     T beta = T(0);
     if (ro > T(0)) beta = rn / ro;
     for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
@@ -130,7 +152,7 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep3(long nVec, ReduceWorkspace 
 template <class T>
 __global__ void k_lmZeta(ReduceWorkspace ws, int lIter, T qTol) {
     if (ws.scalars[kFlags] != 0.0) return;
-    T Q1 = (T)ws.scalars[kQ], Q0 = (T)ws.scalars[kQPrev];
+    T Q1 = (T)loadScalarGlobal(ws, kQ), Q0 = (T)ws.scalars[kQPrev];
     T zeta = T(lIter + 1) * (Q1 - Q0) / Q1;
     if (zeta < qTol) ws.scalars[kFlags] = 1.0 + lIter;   // remembers the breaking iteration
     ws.scalars[kQPrev] = (double)Q1;
@@ -146,7 +168,7 @@ template <class T> __global__ void __launch_bounds__(kBlock) k_copy(long n, T* _
 // PCGFinalizeDiagonal (:631-664).  `pre` holds guardedInvert(diag) from PCGInit1 on entry (0 on
 // excluded/padding entries, which stay inert), the true LM preconditioner on exit.
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, ReduceWorkspace ws, int rzSlot, T* __restrict__ CtC, const T* __restrict__ SSq,
+__global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, ReduceWorkspace ws, OwnedRanges own, int rzSlot, T* __restrict__ CtC, const T* __restrict__ SSq,
                                                                T* __restrict__ pre, const T* __restrict__ r, T* __restrict__ b, T* __restrict__ p,
                                                                const T* __restrict__ delta, T radius, T minDiag, T maxDiag) {
     T accD = T(0), accQ = T(0);
@@ -165,8 +187,10 @@ __global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, ReduceWor
             b[i] = res;
             T pp = pr * res;
             p[i] = pp;
-            accD += res * pp;
-            accQ += T(0.5) * (delta[i] * (res + res));
+            if (own.owns(i)) {
+                accD += res * pp;
+                accQ += T(0.5) * (delta[i] * (res + res));
+            }
         } else {
             CtC[i] = T(0); pre[i] = T(0); b[i] = T(0); p[i] = T(0);
         }
@@ -175,7 +199,39 @@ __global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, ReduceWor
     gridReduceTo<kBlock>((double)accD, ws, rzSlot);
 }
 __global__ void k_setScalar(ReduceWorkspace ws, int slot, double v) { ws.scalars[slot] = v; }
-__global__ void k_copyScalar(ReduceWorkspace ws, int dst, int src) { ws.scalars[dst] = ws.scalars[src]; }
+__global__ void k_copyScalar(ReduceWorkspace ws, int dst, int src) { ws.scalars[dst] = loadScalarGlobal(ws, src); }
+// multi-GPU: materialise the globally reduced values into the local scalar block before a host read-back
+__global__ void k_finalizeScalars(ReduceWorkspace ws, unsigned mask) {
+    const int s = threadIdx.x;
+    if (s < kNumScalars && (mask >> s) & 1u) ws.scalars[s] = loadScalarGlobal(ws, s);
+}
+// Halo exchange of one flat vector: a single CTA stores this rank's boundary segments
+// into the neighbours' halo segments over NVLink (peer pointers from CUDA IPC), releases a flag at each
+// neighbour and then waits for the neighbours' flags, so the next kernel on the stream sees fresh halos.
+struct HaloPlan {
+    int nSeg;
+    long srcOff[4], dstOff[4], len[4];   // in scalars
+    int dir[4];                          // 0 = to the upper neighbour, 1 = to the lower neighbour
+    void* peerVec[2];                    // neighbour's copy of the vector being exchanged (nullptr: no neighbour)
+    unsigned long long* peerFlag[2];     // neighbour's "halo arrived from me" flag
+    unsigned long long* myFlag[2];       // my flags, written by the upper / lower neighbour
+    unsigned long long* epoch;           // local counter
+};
+template <class T>
+__global__ void __launch_bounds__(1024) k_haloExchange(HaloPlan hp, const T* __restrict__ vec) {
+    for (int s = 0; s < hp.nSeg; ++s) {
+        T* dst = reinterpret_cast<T*>(hp.peerVec[hp.dir[s]]);
+        if (!dst) continue;
+        for (long i = threadIdx.x; i < hp.len[s]; i += blockDim.x) dst[hp.dstOff[s] + i] = vec[hp.srcOff[s] + i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long e = *hp.epoch + 1ull; *hp.epoch = e;
+        for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) stReleaseSys(hp.peerFlag[d], e);
+        for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) { while (ldAcquireSys(hp.myFlag[d]) < e) {} }
+    }
+}
 
 // ====================================================================================== Plan<T>
 template <class T>
@@ -189,6 +245,13 @@ struct Plan : PlanBase {
     T *p2 = nullptr, *pFinal = nullptr;   // second direction buffer for the fused Step3+Step1 path; where p lives after the loop
     T *b = nullptr, *Adelta = nullptr, *CtC = nullptr, *SSq = nullptr, *prevX = nullptr;   // LM only
     ReduceWorkspace ws{};
+    OwnedRanges ownVec{}, ownScalar{};       // n == 0: single GPU, everything owned
+    // multi-GPU mailbox block (cudaMalloc'ed so it can be exported through CUDA IPC), see common.cuh CommView
+    struct CommBlock { double partials[kNumScalars][2][kMaxRanks]; unsigned long long flags[kNumScalars][kMaxRanks]; unsigned long long haloFlags[2]; unsigned long long epoch[kNumScalars]; unsigned long long haloEpoch; };
+    CommBlock* commBlock = nullptr;
+    int world = 1, rank = 0;
+    HaloPlan haloP{}, haloZ{};
+    std::vector<void*> ipcOpened;
     double* hScalars = nullptr;  // pinned mirror
     cudaStream_t stream = nullptr, userStream = nullptr;
     bool ownStream = true;
@@ -217,6 +280,9 @@ struct Plan : PlanBase {
         OPT_CUDA_CHECK(cudaMalloc((void**)&ws.scalars, sizeof(double) * kNumScalars));
         OPT_CUDA_CHECK(cudaMemset(ws.counters, 0, sizeof(unsigned) * kNumScalars));
         OPT_CUDA_CHECK(cudaMemset(ws.scalars, 0, sizeof(double) * kNumScalars));
+        OPT_CUDA_CHECK(cudaMalloc((void**)&commBlock, sizeof(CommBlock)));
+        OPT_CUDA_CHECK(cudaMemset(commBlock, 0, sizeof(CommBlock)));
+        ws.comm.world = 1; ws.comm.rank = 0;
         OPT_CUDA_CHECK(cudaMallocHost((void**)&hScalars, sizeof(double) * kNumScalars));
         OPT_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         OPT_CUDA_CHECK(cudaEventCreateWithFlags(&evEntry, cudaEventDisableTiming));
@@ -233,6 +299,8 @@ struct Plan : PlanBase {
         cudaStreamSynchronize(stream);
         if (loopExec) cudaGraphExecDestroy(loopExec);
         for (T* v : { delta, r, z, p, p2, Ap, pre, b, Adelta, CtC, SSq, prevX }) if (v) cudaFree(v);
+        for (void* q : ipcOpened) cudaIpcCloseMemHandle(q);
+        cudaFree(commBlock);
         cudaFree(ws.partials); cudaFree(ws.counters); cudaFree(ws.scalars); cudaFreeHost(hScalars);
         cudaEventDestroy(evEntry); cudaEventDestroy(evLoop0); cudaEventDestroy(evLoop1);
         if (ownStream) cudaStreamDestroy(stream);
@@ -269,7 +337,63 @@ struct Plan : PlanBase {
         OPT_CUDA_CHECK(cudaEventRecord(evEntry, userStream));
         OPT_CUDA_CHECK(cudaStreamWaitEvent(stream, evEntry, 0));
     }
+    // ---- multi-GPU wiring (include/OptB200.h: OptB200_PlanCommHandles / OptB200_PlanConnect)
+    int commHandles(void* out, int outBytes) override {
+        if (outBytes < 3 * (int)sizeof(cudaIpcMemHandle_t)) return -1;
+        cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)out;
+        OPT_CUDA_CHECK(cudaIpcGetMemHandle(&h[0], commBlock));
+        OPT_CUDA_CHECK(cudaIpcGetMemHandle(&h[1], z));
+        OPT_CUDA_CHECK(cudaIpcGetMemHandle(&h[2], p));
+        return 3 * (int)sizeof(cudaIpcMemHandle_t);
+    }
+    int connect(int rank_, int world_, const void* allHandles, int ownedBegin, int ownedEnd, int upperRows, int lowerRows) override {
+        if (world_ < 1 || world_ > kMaxRanks || rank_ < 0 || rank_ >= world_) return -1;
+        if (!E->setSlab(ownedBegin, ownedEnd, upperRows, lowerRows)) { fprintf(stderr, "opt_b200: energy %s has no slab decomposition\n", E->name()); return -2; }
+        OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
+        world = world_; rank = rank_;
+        const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)allHandles;
+        auto open = [&](const cudaIpcMemHandle_t& hh) { void* q = nullptr; OPT_CUDA_CHECK(cudaIpcOpenMemHandle(&q, hh, cudaIpcMemLazyEnablePeerAccess)); ipcOpened.push_back(q); return q; };
+        ws.comm.world = world; ws.comm.rank = rank; ws.comm.epoch = commBlock->epoch;
+        for (int r = 0; r < world; ++r) {
+            CommBlock* cb = (r == rank) ? commBlock : (CommBlock*)open(h[3 * r + 0]);
+            ws.comm.peerPartials[r] = &cb->partials[0][0][0];
+            ws.comm.peerFlags[r] = &cb->flags[0][0];
+            peerBlocks[r] = cb;
+        }
+        void* upZ = nullptr; void* upP = nullptr; void* dnZ = nullptr; void* dnP = nullptr;
+        if (rank > 0 && upperRows > 0) { upZ = open(h[3 * (rank - 1) + 1]); upP = open(h[3 * (rank - 1) + 2]); }
+        if (rank + 1 < world && lowerRows > 0) { dnZ = open(h[3 * (rank + 1) + 1]); dnP = open(h[3 * (rank + 1) + 2]); }
+        auto segs = E->haloSegments();
+        auto fill = [&](HaloPlan& hp, void* up, void* dn) {
+            hp = HaloPlan{};
+            hp.nSeg = (int)segs.size();
+            for (int i = 0; i < hp.nSeg && i < 4; ++i) { hp.srcOff[i] = segs[i].srcOff; hp.dstOff[i] = segs[i].dstOff; hp.len[i] = segs[i].len; hp.dir[i] = segs[i].dir; }
+            hp.peerVec[0] = up; hp.peerVec[1] = dn;
+            // my data lands in the upper neighbour as "from below" (its haloFlags[1]) and in the lower neighbour as "from above" (its haloFlags[0])
+            hp.peerFlag[0] = up ? &peerBlocks[rank - 1]->haloFlags[1] : nullptr;
+            hp.peerFlag[1] = dn ? &peerBlocks[rank + 1]->haloFlags[0] : nullptr;
+            hp.myFlag[0] = &commBlock->haloFlags[0]; hp.myFlag[1] = &commBlock->haloFlags[1];
+            hp.epoch = &commBlock->haloEpoch;
+        };
+        fill(haloP, upP, dnP); fill(haloZ, upZ, dnZ);
+        auto ranges = E->ownedScalarRanges();
+        ownVec = OwnedRanges{}; ownScalar = OwnedRanges{};
+        for (size_t i = 0; i < ranges.size() && i < 4; ++i) {
+            ownScalar.lo[i] = ranges[i].first; ownScalar.hi[i] = ranges[i].second;
+            if (ranges[i].first % VecOf<T>::N || ranges[i].second % VecOf<T>::N) { fprintf(stderr, "opt_b200: slab boundary not vector aligned\n"); return -3; }
+            ownVec.lo[i] = ranges[i].first / VecOf<T>::N; ownVec.hi[i] = ranges[i].second / VecOf<T>::N;
+        }
+        ownVec.n = ownScalar.n = (int)ranges.size();
+        if (loopExec) { cudaGraphExecDestroy(loopExec); loopExec = nullptr; }
+        return 0;
+    }
+    CommBlock* peerBlocks[kMaxRanks] = {};
+    void exchangeHalo(HaloPlan& hp, const T* vec) {
+        if (world <= 1 || hp.nSeg == 0 || (!hp.peerVec[0] && !hp.peerVec[1])) return;
+        k_haloExchange<T><<<1, 1024, 0, stream>>>(hp, vec); ++launches;
+    }
     void readScalars() {
+        if (world > 1) { k_finalizeScalars<<<1, 32, 0, stream>>>(ws, (1u << kRz0) | (1u << kRz1) | (1u << kPAp) | (1u << kCost) | (1u << kModelCost) | (1u << kQ)); ++launches; }
         OPT_CUDA_CHECK(cudaMemcpyAsync(hScalars, ws.scalars, sizeof(double) * kNumScalars, cudaMemcpyDeviceToHost, stream));
         OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
@@ -294,11 +418,11 @@ struct Plan : PlanBase {
     void launchStep2(int rzOld, int rzNew, T* p) {
         long nVec = n / VecOf<T>::N;
         if (lm) {
-            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
-            else k_pcgStep2<T, true, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            else k_pcgStep2<T, true, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
         } else {
-            if (E->usePreconditioner) k_pcgStep2<T, false, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
-            else k_pcgStep2<T, false, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            if (E->usePreconditioner) k_pcgStep2<T, false, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            else k_pcgStep2<T, false, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
         }
         ++launches;
     }
@@ -330,12 +454,13 @@ struct Plan : PlanBase {
                 long nVec = n / VecOf<T>::N;
                 k_pcgStep2FirstHalf<T><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, delta, cur); ++launches;
                 E->applyJTJ(c, delta, Adelta, ctc, -1); ++launches;
-                if (E->usePreconditioner) k_pcgStep2SecondHalf<T, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzNew, delta, r, Adelta, pre, b, z);
-                else k_pcgStep2SecondHalf<T, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzNew, delta, r, Adelta, pre, b, z);
+                if (E->usePreconditioner) k_pcgStep2SecondHalf<T, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzNew, delta, r, Adelta, pre, b, z);
+                else k_pcgStep2SecondHalf<T, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzNew, delta, r, Adelta, pre, b, z);
                 ++launches;
             } else {
                 launchStep2(rzOld, rzNew, cur);
             }
+            exchangeHalo(haloZ, z);                            // neighbours need z on my boundary rows for their p = z + beta p
             if (fuse && !lm && l + 1 < L) pending = true;   // defer Step3 into the next Step1
             else launchStep3(rzNew, rzOld, cur);
             if (lm) { k_lmZeta<T><<<1, 1, 0, stream>>>(ws, l, (T)sp.q_tolerance); ++launches; }
@@ -381,10 +506,11 @@ struct Plan : PlanBase {
         if (lm) {   // :1038-1053
             if (nIter == 0) { k_copy<T><<<gridStream, kBlock, 0, stream>>>(n, SSq, pre); ++launches; }   // PCGSaveSSq
             E->computeCtC(c, CtC, T(1) / trust_region_radius); ++launches;
-            k_lmFinalizeDiagonal<T><<<gridStream, kBlock, 0, stream>>>(n, ws, kRz0, CtC, SSq, pre, r, b, p, delta, trust_region_radius, min_lm_diagonal, max_lm_diagonal); ++launches;
+            k_lmFinalizeDiagonal<T><<<gridStream, kBlock, 0, stream>>>(n, ws, ownScalar, kRz0, CtC, SSq, pre, r, b, p, delta, trust_region_radius, min_lm_diagonal, max_lm_diagonal); ++launches;
             k_copyScalar<<<1, 1, 0, stream>>>(ws, kQPrev, kQ);          // Q0 = fetchQ
             k_setScalar<<<1, 1, 0, stream>>>(ws, kFlags, 0.0); launches += 2;
         }
+        exchangeHalo(haloP, p);                                // initial direction on the halo rows
         int L = sp.lIterations; if (maxLinIters >= 0 && maxLinIters < L) L = maxLinIters;
         runLoop(L);
         if (maxLinIters >= 0) { OPT_CUDA_CHECK(cudaStreamSynchronize(stream)); return 1; }   // debug hook: PCG state left for inspection

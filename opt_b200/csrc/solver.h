@@ -72,6 +72,13 @@ struct EnergyOps {
     virtual void modelCost(const LaunchCtx&, const T* /*delta*/) { unsupported("modelCost (LM)"); }
     // ComputedArray refresh (kernels.precompute, solverGPUGaussNewton.t:607-614)
     virtual void precompute(const LaunchCtx&) {}
+    // ---- multi-GPU slab decomposition.  The plan's dimensions describe the LOCAL domain =
+    // owned slab rows + halo rows; [ownedBegin, ownedEnd) are the owned local rows, upperRows/lowerRows the
+    // local row counts of the neighbouring ranks (0 = no neighbour).  Returns false if unsupported.
+    virtual bool setSlab(int /*ownedBegin*/, int /*ownedEnd*/, int /*upperRows*/, int /*lowerRows*/) { return false; }
+    struct HaloSegment { long srcOff, dstOff, len; int dir; };          // scalars in the flat layout; dir 0 = up, 1 = down
+    virtual std::vector<HaloSegment> haloSegments() const { return {}; }
+    virtual std::vector<std::pair<long, long>> ownedScalarRanges() const { return {}; }
     virtual const char* name() const = 0;
     static void unsupported(const char* what) {
         fprintf(stderr, "opt_b200: %s is not implemented for this energy\n", what);
@@ -105,6 +112,8 @@ struct PlanBase {
     virtual int launchesLastStep() const = 0;
     virtual float pcgLoopMsLastStep() const = 0;
     virtual int profileKernels(void** params, int reps, int maxOut, const char** names, float* avgMs) = 0;
+    virtual int commHandles(void* out, int outBytes) = 0;
+    virtual int connect(int rank, int world, const void* allHandles, int ownedBegin, int ownedEnd, int upperRows, int lowerRows) = 0;
 };
 
 // factory implemented in solver.cu

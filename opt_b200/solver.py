@@ -151,6 +151,19 @@ class OptSolver:
     def pcg_loop_ms_last_step(self):
         return self.L.OptB200_PcgLoopMsLastStep(self.plan)
 
+    def comm_handles(self):
+        """192 bytes: CUDA IPC handles of this plan's scalar mailbox, z and p (OptB200_PlanCommHandles)"""
+        buf = ctypes.create_string_buffer(192)
+        n = self.L.OptB200_PlanCommHandles(self.plan, buf, 192)
+        if n != 192:
+            raise capi.OptError("OptB200_PlanCommHandles failed")
+        return buf.raw
+
+    def connect(self, rank, world, all_handles, owned_begin, owned_end, upper_rows, lower_rows):
+        rc = self.L.OptB200_PlanConnect(self.plan, int(rank), int(world), all_handles, int(owned_begin), int(owned_end), int(upper_rows), int(lower_rows))
+        if rc != 0:
+            raise capi.OptError(f"OptB200_PlanConnect failed ({rc})")
+
     def profile_kernels(self, problem_params, reps=20):
         """{kernel name: average ms per launch}, CUDA events on the plan's stream (OptB200_ProfileKernels)"""
         t = ParamTable(problem_params)

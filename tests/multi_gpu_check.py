@@ -1,0 +1,61 @@
+"""Run under torchrun (one rank per GPU): slab-decomposed image_warping solve vs the single-GPU solve of the
+same problem (and vs the CPU oracle at this size).  Used by tests/test_gpu_multi.py and by hand:
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from opt_b200 import OptSolver, spec_path, workloads
+    from opt_b200.distributed import Slab, scatter_image_params, connect_plan, gather_owned_rows
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (128, 96)
+    kind = sys.argv[3] if len(sys.argv) > 3 else "gaussNewtonGPU"
+    sp = {"nIterations": 3, "lIterations": 40}
+    full = workloads.image_warping(W, H, mask="blob", seed=21)
+    slab = Slab(H, world, rank)
+    local_host = scatter_image_params(full, (0, 1, 2, 3, 4), W, slab)
+    dev = workloads.to_device(local_host)
+    s = OptSolver([W, slab.local_rows], spec_path("image_warping"), kind)
+    connect_plan(s, slab)
+    s.set_solver_parameters(sp)
+    s.init(dev)
+    costs = [s.current_cost()]
+    while s.step(dev):
+        costs.append(s.current_cost())
+    torch.cuda.synchronize()
+    off = gather_owned_rows(dev[0].cpu().numpy().reshape(-1, 2), W, slab).reshape(-1, 2)
+    ang = gather_owned_rows(dev[1].cpu().numpy(), W, slab).reshape(-1)
+    all_costs = [None] * world
+    dist.all_gather_object(all_costs, costs)
+    ok = True
+    if rank == 0:
+        assert all(c == all_costs[0] for c in all_costs), "ranks disagree on the cost history (must be bitwise equal)"
+        ref = workloads.to_device(workloads.clone_params(full))
+        s1 = OptSolver([W, H], spec_path("image_warping"), kind)
+        s1.set_solver_parameters(sp)
+        s1.init(ref); c1 = [s1.current_cost()]
+        while s1.step(ref):
+            c1.append(s1.current_cost())
+        o1, a1 = ref[0].cpu().numpy(), ref[1].cpu().numpy()
+        rel_c = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(costs, c1))
+        e_off = np.linalg.norm(off - o1) / np.linalg.norm(o1); e_ang = np.linalg.norm(ang - a1) / max(np.linalg.norm(a1), 1e-12)
+        print(f"multi_gpu_check world={world} {W}x{H} {kind}: costs {costs[0]:.6f} -> {costs[-1]:.6f}; vs 1 GPU: cost rel {rel_c:.2e}, Offset {e_off:.2e}, Angle {e_ang:.2e}")
+        ok = rel_c < 1e-4 and e_off < 1e-5 and e_ang < 2e-3 and len(costs) == len(c1)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,10 +12,11 @@ value = PCG steps per second of the whole job (K * lIterations / time, all ranks
 GN iteration.  Timing: CUDA events, barrier + synchronize on both sides, max over ranks.  The working
 set (~0.6 GB of live vectors) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
 
-Multi-GPU (N > 1): the image is cut into N row slabs.  Until the halo-exchange path
-lands every rank solves its own slab-sized problem with pinned slab borders ("independent slabs",
-weak in the sense that the slab height per rank is fixed at 2048/1 ... no: at H rows per rank); see
-`config.parallelism`.
+Multi-GPU (N > 1): STRONG scaling of the same 2048^2 problem.  The image is cut into N row slabs
+(SURVEY.md 8e), one rank per GPU; each rank plans slab + 1 halo row per neighbour, the plans are wired
+together with OptB200_PlanConnect (CUDA IPC over NVLink): halo rows of z/p move by direct peer stores and
+the two PCG scalars are summed through peer-memory mailboxes from inside the solver kernels -- no NCCL
+call in the timed region (torch.distributed/NCCL is used only for setup and for the timing max-reduce).
 
 --impl reference times the CPU oracle (oracle/, a C++/OpenMP port of the reference solver: the
 reference's own Terra/CUDA path cannot be built without Terra) on the box's host cores on a
@@ -151,13 +152,18 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from opt_b200.distributed import Slab, scatter_image_params, connect_plan
     W = H = args.size
-    Hr = H // world                       # rows of this rank's slab
-    host = workloads.image_warping(W, Hr, seed=rank, mask="none")
+    full = workloads.image_warping(W, H, seed=0, mask="none")          # every rank builds the same global problem ...
+    slab = Slab(H, world, rank)
+    host = scatter_image_params(full, (0, 1, 2, 3, 4), W, slab) if world > 1 else full   # ... and keeps its slab (+halo rows)
+    del full
+    Hr = slab.local_rows
     dev = workloads.to_device(host)
-    pristine = [t.clone() if hasattr(t, "clone") else t for t in dev]
     pinned = [torch.from_numpy(p).pin_memory() if isinstance(p, np.ndarray) else p for p in host]
     solver = OptSolver([W, Hr], spec_path("image_warping"), "gaussNewtonGPU")
+    if world > 1:
+        connect_plan(solver, slab)
     total = args.warmup + args.steps
     solver.set_solver_parameters({"nIterations": total + 1, "lIterations": args.liters})
 
@@ -211,7 +217,7 @@ def main():
     e2e_ms = e0.elapsed_time(e1)
 
     # ------------------------------------------------------------------ per-kernel replay (roofline)
-    prof = solver.profile_kernels(dev, reps=20)
+    prof = solver.profile_kernels(dev, reps=20) if world == 1 else {}
 
     t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -220,21 +226,23 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        pixels = W * Hr
-        value = world * args.steps * args.liters / (ms / 1e3)
-        e2e_value = world * ksteps * args.liters / (e2e_ms / 1e3)
+        pixels = W * H                      # whole job (all ranks)
+        value = args.steps * args.liters / (ms / 1e3)          # PCG steps/s of the one shared problem
+        e2e_value = ksteps * args.liters / (e2e_ms / 1e3)
+        loop_step_us = 1e3 * statistics.mean(loop_ms) / args.liters
         fused = "PCGStep3+PCGStep1(fused)" in prof
         dom_name = "PCGStep3+PCGStep1(fused)" if fused else "PCGStep1"
         dom_bytes = (BYTES_STEP1 + BYTES_STEP3 if fused else BYTES_STEP1) * pixels
-        dom_ms = prof[dom_name]
+        dom_ms = prof.get(dom_name)
+        if dom_ms is None:                  # multi-GPU: no per-kernel replay; report the PCG step as the unit
+            dom_name, dom_bytes, dom_ms = "PCG step (all kernels, rank 0 slab)", BYTES_PCG_STEP * W * (slab.g1 - slab.g0), loop_step_us * 1e-3
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-        loop_step_us = 1e3 * statistics.mean(loop_ms) / args.liters
         line = {
             "metric": "pcg_steps_per_s", "value": value, "unit": "PCG steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"image_warping {W}x{H} fp32 GN (BASELINE.json headline), lIterations={args.liters}, step = 1 GN iteration",
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent row slabs of {W}x{Hr} (halo exchange not in this round)",
-                       "l2": "inputs larger than L2 (live PCG vectors ~%.0f MB per rank)" % (pixels * 4 * 3 * 7 / 1e6),
+                       "parallelism": "single GPU" if world == 1 else f"{world} row slabs of {W}x{slab.g1 - slab.g0} (+1 halo row per neighbour), NVLink peer-memory halo exchange + scalar mailboxes",
+                       "l2": "inputs larger than L2 (live PCG vectors ~%.0f MB per rank)" % (W * Hr * 4 * 3 * 7 / 1e6) if W * Hr * 84 > 126e6 else "per-rank working set %.0f MB fits the 126 MB L2 (no flush between steps: the solver itself streams >= 7 vectors per PCG step)" % (W * Hr * 4 * 3 * 7 / 1e6),
                        "final_cost": final_cost},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "PCG steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -243,9 +251,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
-                         "pcg_step": {"algorithmic_bytes": BYTES_PCG_STEP * pixels, "us_in_timed_region": loop_step_us,
-                                      "achieved": BYTES_PCG_STEP * pixels / (loop_step_us * 1e-6) / 1e9,
-                                      "frac": BYTES_PCG_STEP * pixels / (loop_step_us * 1e-6) / 1e9 / peak},
+                         "pcg_step": {"algorithmic_bytes_per_gpu": BYTES_PCG_STEP * W * (slab.g1 - slab.g0), "us_in_timed_region": loop_step_us,
+                                      "achieved": BYTES_PCG_STEP * W * (slab.g1 - slab.g0) / (loop_step_us * 1e-6) / 1e9,
+                                      "frac": BYTES_PCG_STEP * W * (slab.g1 - slab.g0) / (loop_step_us * 1e-6) / 1e9 / peak},
                          "kernels_ms": prof},
         }
         if not args.no_cpu_baseline and world == 1:

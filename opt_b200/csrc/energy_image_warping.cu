@@ -115,11 +115,17 @@ __global__ void __launch_bounds__(kBlock) k_iwInit(IWData<T> D, ReduceWorkspace 
             pO = Vec2<T>{ io * rO.x, io * rO.y }; pA = ia * rA;
             acc += rO.x * pO.x + rO.y * pO.y + rA * pA;
         }
+        else if (D.Mask[i] == T(0)) {
+            // halo row (multi-GPU): no unknowns of ours here, but the pair-validity bits are still needed by the
+            // owned row next to it (the tiled kernel reads the validity of a vertical pair from its upper pixel)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { long j; if (neighbour(k, x, y, D.W, D.H, &j) && D.Mask[j] == T(0)) fl |= (uint8_t)(1u << k); }
+        }
         D.flags[i] = fl;
         reinterpret_cast<Vec2<T>*>(delta)[i] = Vec2<T>{ T(0), T(0) }; delta[D.offA + i] = T(0);
         reinterpret_cast<Vec2<T>*>(r)[i] = rO; r[D.offA + i] = rA;
         reinterpret_cast<Vec2<T>*>(pre)[i] = preO; pre[D.offA + i] = preA;
-        reinterpret_cast<Vec2<T>*>(p)[i] = pO; p[D.offA + i] = pA;
+        if (y >= D.y0 && y < D.y1) { reinterpret_cast<Vec2<T>*>(p)[i] = pO; p[D.offA + i] = pA; }   // halo rows of p arrive from the neighbour
     }
     gridReduceTo<kBlock>((double)acc, ws, rzSlot);
 }
@@ -356,6 +362,7 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
             const float vf = (fl & 16u) ? wf2 : 0.f;
             float2 oO = make_float2(w2 * ax + vf * cur.px, w2 * ay + vf * cur.py);
             float oA = w2 * aa;
+            if (gy < D.y0 || gy >= D.y1) { oO = make_float2(0.f, 0.f); oA = 0.f; }   // halo row: direction only, no Ap
             if (gx < D.W && gy < D.H) {
                 const long i = (long)gy * D.W + gx;
                 if (LM) {

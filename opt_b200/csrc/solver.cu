@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, ReduceWorkspace 
         }
         reinterpret_cast<V*>(delta)[i] = pack(d);
         reinterpret_cast<V*>(r)[i] = pack(rr);
-        reinterpret_cast<V*>(z)[i] = pack(zz);
+        if (mine) reinterpret_cast<V*>(z)[i] = pack(zz);   // halo entries of z belong to the neighbour's NVLink store (k_haloExchange)
     }
     gridReduceTo<kBlock>((double)accRz, ws, rzNew);
     if (LM) gridReduceTo<kBlock>((double)accQ, ws, kQ);
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2SecondHalf(long nVec, Reduce
                 accQ += T(0.5) * (d[k] * (rr[k] + bb[k]));
             }
         }
-        reinterpret_cast<V*>(r)[i] = pack(rr); reinterpret_cast<V*>(z)[i] = pack(zz);
+        reinterpret_cast<V*>(r)[i] = pack(rr); if (own.owns(i)) reinterpret_cast<V*>(z)[i] = pack(zz);
     }
     gridReduceTo<kBlock>((double)accRz, ws, rzNew);
     gridReduceTo<kBlock>((double)accQ, ws, kQ);
@@ -186,13 +186,13 @@ __global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, ReduceWor
             T res = r[i];
             b[i] = res;
             T pp = pr * res;
-            p[i] = pp;
+            if (own.owns(i)) p[i] = pp;   // halo entries of p arrive from the neighbour
             if (own.owns(i)) {
                 accD += res * pp;
                 accQ += T(0.5) * (delta[i] * (res + res));
             }
         } else {
-            CtC[i] = T(0); pre[i] = T(0); b[i] = T(0); p[i] = T(0);
+            CtC[i] = T(0); pre[i] = T(0); b[i] = T(0); if (own.owns(i)) p[i] = T(0);
         }
     }
     gridReduceTo<kBlock>((double)accQ, ws, kQ);

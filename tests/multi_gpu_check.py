@@ -50,6 +50,7 @@ def main():
         rel_c = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(costs, c1))
         e_off = np.linalg.norm(off - o1) / np.linalg.norm(o1); e_ang = np.linalg.norm(ang - a1) / max(np.linalg.norm(a1), 1e-12)
         print(f"multi_gpu_check world={world} {W}x{H} {kind}: costs {costs[0]:.6f} -> {costs[-1]:.6f}; vs 1 GPU: cost rel {rel_c:.2e}, Offset {e_off:.2e}, Angle {e_ang:.2e}")
+        print("  multi :", [f"{c:.6g}" for c in costs]); print("  single:", [f"{c:.6g}" for c in c1])
         ok = rel_c < 1e-4 and e_off < 1e-5 and e_ang < 2e-3 and len(costs) == len(c1)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

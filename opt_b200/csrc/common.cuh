@@ -43,17 +43,20 @@ enum Scalar : int {
 constexpr int kMaxRanks = 8;
 
 // Cross-GPU view of the scalar mailboxes ("a single allreduce of the PCG scalars").
-// Every rank owns one mailbox block (cudaMalloc + CUDA IPC); peerPartials[r] / peerFlags[r] are rank r's
-// block mapped into this process.  A reduction's last CTA stores its local sum into slot
-// [scalar][epoch&1][myRank] of EVERY rank's block over NVLink and then releases flag [scalar][myRank] =
-// epoch; consumers spin on their OWN block until all `world` flags reach the epoch and add the `world`
-// partials in rank order, so every rank obtains the bitwise-identical sum with no host involvement and
-// no NCCL launch.  Two parities suffice: a rank cannot produce epoch e+2 of a scalar before every rank
+// Every rank owns one mailbox block (cudaMalloc + CUDA IPC); peerWords[r] is rank r's block mapped into
+// this process.  A reduction's last CTA stores its local sum into slot [scalar][epoch&1][myRank] of EVERY
+// rank's block over NVLink; consumers spin on their OWN block until all `world` entries carry the epoch
+// and add them in rank order, so every rank obtains the bitwise-identical sum with no host involvement
+// and no NCCL launch.  Two parities suffice: a rank cannot produce epoch e+2 of a scalar before every rank
 // has consumed epoch e (it needs every rank's epoch e+1 contribution first).
+// Wire format ("LL", as in NCCL's low-latency protocol): a double travels as two 8-byte words, each
+// carrying 32 payload bits and the 32-bit epoch, so an 8-byte store is self-validating -- no fence and no
+// separate flag write, one NVLink one-way latency per reduction.
 struct CommView {
     int world, rank;
-    double* peerPartials[kMaxRanks];                // [kNumScalars][2][kMaxRanks]
-    unsigned long long* peerFlags[kMaxRanks];       // [kNumScalars][kMaxRanks]
+    unsigned long long* const* peerWords;           // device table [world]: rank r's mailbox [kNumScalars][2 parities][kMaxRanks senders][2 words]
+                                                    // (a table in global memory, not an array in the kernel parameters: run-time indexing of a
+                                                    // by-value parameter array forces a per-thread local-memory copy of the whole struct)
     unsigned long long* epoch;                      // local [kNumScalars]: epochs produced so far
 };
 
@@ -74,18 +77,44 @@ __device__ __forceinline__ double ldRelaxedSysF64(const double* p) {
     double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v;
 }
 
+__device__ __forceinline__ unsigned long long ldVolatileU64(const unsigned long long* p) {
+    unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void stVolatileU64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ size_t mailboxWord(int slot, unsigned long long e, int sender) {
+    return (((size_t)slot * 2 + (size_t)(e & 1ull)) * kMaxRanks + sender) * 2;
+}
+// last CTA of a reduction: publish the local sum `u` of `slot` to every rank (including this one)
+__device__ __forceinline__ void publishScalar(const ReduceWorkspace& ws, int slot, double u) {
+    const unsigned long long e = ws.comm.epoch[slot] + 1ull;
+    ws.comm.epoch[slot] = e;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(u);
+    const unsigned long long w0 = ((bits & 0xffffffffull) << 32) | (e & 0xffffffffull);
+    const unsigned long long w1 = ((bits >> 32) << 32) | (e & 0xffffffffull);
+    const size_t at = mailboxWord(slot, e, ws.comm.rank);
+    for (int r = 0; r < ws.comm.world; ++r) { stVolatileU64(ws.comm.peerWords[r] + at, w0); stVolatileU64(ws.comm.peerWords[r] + at + 1, w1); }
+}
 // Value of reduction `slot` as seen by every rank (single thread; callers broadcast through shared memory).
 __device__ __forceinline__ double loadScalarGlobal(const ReduceWorkspace& ws, int slot) {
     if (ws.comm.world <= 1) return ws.scalars[slot];
     const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(ws.comm.epoch + slot);
-    const unsigned long long* flags = ws.comm.peerFlags[ws.comm.rank] + slot * kMaxRanks;
-    const double* part = ws.comm.peerPartials[ws.comm.rank] + (slot * 2 + (int)(e & 1ull)) * kMaxRanks;
+    if (e == 0ull) return 0.0;     // never produced
+    const unsigned long long want = e & 0xffffffffull;
     double sum = 0.0;
-    for (int r = 0; r < ws.comm.world; ++r) {
-        while (ldAcquireSys(flags + r) < e) {}
-        sum += ldRelaxedSysF64(part + r);
+    for (int r = 0; r < ws.comm.world; ++r) {   // fixed rank order => bitwise identical on every rank
+        const unsigned long long* w = ws.comm.peerWords[ws.comm.rank] + mailboxWord(slot, e, r);
+        unsigned long long w0, w1;
+        do { w0 = ldVolatileU64(w); w1 = ldVolatileU64(w + 1); } while ((w0 & 0xffffffffull) != want || (w1 & 0xffffffffull) != want);
+        sum += __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
     }
     return sum;
+}
+// Sequence number of the halo exchange that follows the most recent r.z production (PCGInit1 / PCGStep2):
+// identical on all ranks, strictly increasing from one exchange to the next, stable while a kernel runs.
+__device__ __forceinline__ unsigned long long haloEpochNow(const ReduceWorkspace& ws) {
+    return *reinterpret_cast<volatile unsigned long long*>(ws.comm.epoch + kRz0) + *reinterpret_cast<volatile unsigned long long*>(ws.comm.epoch + kRz1);
 }
 // Block-wide: returns the globally reduced values of two slots to every thread.
 __device__ __forceinline__ void loadScalars2(const ReduceWorkspace& ws, int slotA, int slotB, double& a, double& b) {
@@ -142,13 +171,8 @@ __device__ __forceinline__ void gridReduceTo(double v, const ReduceWorkspace& ws
                 ws.counters[slot] = 0u;
                 if (ws.comm.world <= 1) {
                     ws.scalars[slot] = u;
-                } else {   // publish the local sum to every rank's mailbox, then release the flags
-                    const unsigned long long e = ws.comm.epoch[slot] + 1ull;
-                    ws.comm.epoch[slot] = e;
-                    for (int r = 0; r < ws.comm.world; ++r)
-                        ws.comm.peerPartials[r][(slot * 2 + (int)(e & 1ull)) * kMaxRanks + ws.comm.rank] = u;
-                    __threadfence_system();
-                    for (int r = 0; r < ws.comm.world; ++r) stReleaseSys(ws.comm.peerFlags[r] + slot * kMaxRanks + ws.comm.rank, e);
+                } else {
+                    publishScalar(ws, slot, u);
                 }
             }
         }

@@ -275,7 +275,7 @@ __device__ __forceinline__ void iwPairOne(const IWPoint& i, const IWPoint& j, fl
 template <bool FUSE3, bool LM>
 __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const __grid_constant__ IWMaps M, ReduceWorkspace ws, int dotSlot, int rzNew,
                                                           int rzOld, float* __restrict__ pOut, float* __restrict__ out, const float* __restrict__ CtC,
-                                                          int tilesX, int numTiles) {
+                                                          int tilesX, int numTiles, const float* __restrict__ haloSrc, const HaloPlan* __restrict__ hpp) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[kStages];
     constexpr int stageBytes = FUSE3 ? kStageBytesFused : kStageBytesPlain;
@@ -291,9 +291,25 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int tile, int stage) {   // one thread
+    // Multi-GPU (hp.nSeg > 0): this kernel is also the halo exchange.  The last CTA first stores this rank's
+    // boundary rows of haloSrc (z when FUSE3, else p) into the neighbours' halo rows over NVLink and releases
+    // their flags; every CTA waits for the incoming flag only before staging a tile that touches a halo row,
+    // and the tile order is rotated so those tiles come mid-kernel, when the flags have long arrived.
+    const bool halo = hpp != nullptr;
+    const unsigned long long haloE = halo ? haloEpochNow(ws) : 0ull;
+    unsigned long long* myFlagUp = nullptr; unsigned long long* myFlagDn = nullptr;   // non-null: a neighbour exists on that side
+    if (halo) { if (hpp->peerVec[0]) myFlagUp = hpp->myFlag[0]; if (hpp->peerVec[1]) myFlagDn = hpp->myFlag[1]; }
+    const int tileRot = halo ? ((numTiles / tilesX) / 2) * tilesX : 0;
+    auto issue = [&](int seq, int stage) {   // one thread
+        int tile = seq + tileRot; if (tile >= numTiles) tile -= numTiles;
         unsigned char* base = smem + (size_t)stage * stageBytes;
         const int x0 = (tile % tilesX) * kTW, y0 = (tile / tilesX) * kTH;
+        if (halo) {
+            bool waited = false;
+            if (myFlagUp && y0 - 1 <= D.y0 - 1) { while (ldAcquireSys(myFlagUp) < haloE) {} waited = true; }
+            if (myFlagDn && y0 + kTH >= D.y1) { while (ldAcquireSys(myFlagDn) < haloE) {} waited = true; }
+            if (waited) asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
         mbarExpectTx(&bars[stage], (unsigned)(kBytesO + kBytesA + kBytesG + kBytesF + (FUSE3 ? kBytesO + kBytesA : 0)));
         tmaLoad2D(base + kOffPO, &M.pO, &bars[stage], 2 * (x0 - 2), y0 - 1);
         tmaLoad2D(base + kOffPA, &M.pA, &bars[stage], x0 - 4, y0 - 1);
@@ -304,6 +320,18 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
             tmaLoad2D(base + kOffZA, &M.zA, &bars[stage], x0 - 4, y0 - 1);
         }
     };
+    if (halo && blockIdx.x == gridDim.x - 1) {
+        const HaloPlan& hp = *hpp;
+        for (int s = 0; s < hp.nSeg; ++s) {
+            float* dst = reinterpret_cast<float*>(hp.peerVec[hp.dir[s]]);
+            if (!dst) continue;
+            const float4* src4 = reinterpret_cast<const float4*>(haloSrc + hp.srcOff[s]); float4* dst4 = reinterpret_cast<float4*>(dst + hp.dstOff[s]);
+            for (long i = tid; i < hp.len[s] / 4; i += kBlock) dst4[i] = src4[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) stReleaseSys(hp.peerFlag[d], haloE);
+    }
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) { const int t = blockIdx.x + s * gridDim.x; if (t < numTiles) issue(t, s); }
     }
@@ -311,7 +339,8 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
     const int lx = tid & (kTW - 1), ly0 = (tid >> 6) * kStrip;   // 256 threads = 64 columns x 4 strips of 4 rows
     float acc = 0.f;
     int it = 0;
-    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++it) {
+    for (int seq = blockIdx.x; seq < numTiles; seq += gridDim.x, ++it) {
+        int tile = seq + tileRot; if (tile >= numTiles) tile -= numTiles;
         const int stage = it % kStages;
         const unsigned parity = (unsigned)((it / kStages) & 1);
         unsigned char* base = smem + (size_t)stage * stageBytes;
@@ -377,7 +406,7 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
         }
         __syncthreads();   // every thread is done with this stage
         if (tid == 0) {
-            const int next = tile + kStages * gridDim.x;
+            const int next = seq + kStages * gridDim.x;
             if (next < numTiles) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(next, stage); }
         }
     }
@@ -584,25 +613,28 @@ struct ImageWarpingOps : EnergyOps<T> {
     void pcgInit(const LaunchCtx& c, T* delta, T* r, T* pre, T* p, int rzSlot) override {
         k_iwInit<T><<<gridInit, kBlock, 0, c.stream>>>(D, c.ws, rzSlot, delta, r, pre, p);
     }
-    void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot) override {
+    bool inKernelHalo() const override { return tmaOk; }
+    void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot, const HaloPlan* halo) override {
         if constexpr (std::is_same<T, float>::value) {
             if (tmaOk) {
                 const IWMaps& m = mapsFor(x, nullptr);
-                if (CtC) k_iwApplyJTJTma<false, true><<<gridTma, kBlock, kStages * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, CtC, tmaTilesX, tmaTiles);
-                else k_iwApplyJTJTma<false, false><<<gridTma, kBlock, kStages * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, nullptr, tmaTilesX, tmaTiles);
+                const HaloPlan* hp = halo;
+                if (CtC) k_iwApplyJTJTma<false, true><<<gridTma, kBlock, kStages * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, CtC, tmaTilesX, tmaTiles, x, hp);
+                else k_iwApplyJTJTma<false, false><<<gridTma, kBlock, kStages * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, nullptr, tmaTilesX, tmaTiles, x, hp);
                 return;
             }
         }
         if (CtC) k_iwApplyJTJ<T, false, true><<<gridJTJ, kBlock, 0, c.stream>>>(D, c.ws, dotSlot, 0, 0, x, nullptr, nullptr, out, CtC);
         else k_iwApplyJTJ<T, false, false><<<gridJTJ, kBlock, 0, c.stream>>>(D, c.ws, dotSlot, 0, 0, x, nullptr, nullptr, out, nullptr);
     }
-    bool step3ApplyJTJ(const LaunchCtx& c, const T* z, const T* pOld, T* pNew, T* out, const T* CtC, int rzNew, int rzOld, int dotSlot) override {
+    bool step3ApplyJTJ(const LaunchCtx& c, const T* z, const T* pOld, T* pNew, T* out, const T* CtC, int rzNew, int rzOld, int dotSlot, const HaloPlan* halo) override {
         if (dotSlot == -2) return true;
         if constexpr (std::is_same<T, float>::value) {
             if (tmaOk) {
                 const IWMaps& m = mapsFor(pOld, z);
-                if (CtC) k_iwApplyJTJTma<true, true><<<gridTmaF, kBlock, kStages * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, CtC, tmaTilesX, tmaTiles);
-                else k_iwApplyJTJTma<true, false><<<gridTmaF, kBlock, kStages * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, nullptr, tmaTilesX, tmaTiles);
+                const HaloPlan* hp = halo;
+                if (CtC) k_iwApplyJTJTma<true, true><<<gridTmaF, kBlock, kStages * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, CtC, tmaTilesX, tmaTiles, z, hp);
+                else k_iwApplyJTJTma<true, false><<<gridTmaF, kBlock, kStages * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, nullptr, tmaTilesX, tmaTiles, z, hp);
                 return true;
             }
         }

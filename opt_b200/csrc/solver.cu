@@ -208,17 +208,9 @@ __global__ void k_finalizeScalars(ReduceWorkspace ws, unsigned mask) {
 // Halo exchange of one flat vector: a single CTA stores this rank's boundary segments
 // into the neighbours' halo segments over NVLink (peer pointers from CUDA IPC), releases a flag at each
 // neighbour and then waits for the neighbours' flags, so the next kernel on the stream sees fresh halos.
-struct HaloPlan {
-    int nSeg;
-    long srcOff[4], dstOff[4], len[4];   // in scalars
-    int dir[4];                          // 0 = to the upper neighbour, 1 = to the lower neighbour
-    void* peerVec[2];                    // neighbour's copy of the vector being exchanged (nullptr: no neighbour)
-    unsigned long long* peerFlag[2];     // neighbour's "halo arrived from me" flag
-    unsigned long long* myFlag[2];       // my flags, written by the upper / lower neighbour
-    unsigned long long* epoch;           // local counter
-};
 template <class T>
-__global__ void __launch_bounds__(1024) k_haloExchange(HaloPlan hp, const T* __restrict__ vec) {
+__global__ void __launch_bounds__(1024) k_haloExchange(const HaloPlan* __restrict__ hpp, ReduceWorkspace ws, const T* __restrict__ vec) {
+    const HaloPlan& hp = *hpp;
     for (int s = 0; s < hp.nSeg; ++s) {
         T* dst = reinterpret_cast<T*>(hp.peerVec[hp.dir[s]]);
         if (!dst) continue;
@@ -227,7 +219,7 @@ __global__ void __launch_bounds__(1024) k_haloExchange(HaloPlan hp, const T* __r
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned long long e = *hp.epoch + 1ull; *hp.epoch = e;
+        const unsigned long long e = haloEpochNow(ws);
         for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) stReleaseSys(hp.peerFlag[d], e);
         for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) { while (ldAcquireSys(hp.myFlag[d]) < e) {} }
     }
@@ -247,10 +239,12 @@ struct Plan : PlanBase {
     ReduceWorkspace ws{};
     OwnedRanges ownVec{}, ownScalar{};       // n == 0: single GPU, everything owned
     // multi-GPU mailbox block (cudaMalloc'ed so it can be exported through CUDA IPC), see common.cuh CommView
-    struct CommBlock { double partials[kNumScalars][2][kMaxRanks]; unsigned long long flags[kNumScalars][kMaxRanks]; unsigned long long haloFlags[2]; unsigned long long epoch[kNumScalars]; unsigned long long haloEpoch; };
+    struct CommBlock { unsigned long long words[kNumScalars][2][kMaxRanks][2]; unsigned long long haloFlags[2]; unsigned long long epoch[kNumScalars]; unsigned long long haloEpoch; };
     CommBlock* commBlock = nullptr;
     int world = 1, rank = 0;
     HaloPlan haloP{}, haloZ{};
+    HaloPlan* dHaloP = nullptr; HaloPlan* dHaloZ = nullptr;       // device copies (kernels take them by pointer)
+    unsigned long long** dPeerTable = nullptr;
     std::vector<void*> ipcOpened;
     double* hScalars = nullptr;  // pinned mirror
     cudaStream_t stream = nullptr, userStream = nullptr;
@@ -300,7 +294,7 @@ struct Plan : PlanBase {
         if (loopExec) cudaGraphExecDestroy(loopExec);
         for (T* v : { delta, r, z, p, p2, Ap, pre, b, Adelta, CtC, SSq, prevX }) if (v) cudaFree(v);
         for (void* q : ipcOpened) cudaIpcCloseMemHandle(q);
-        cudaFree(commBlock);
+        cudaFree(commBlock); cudaFree(dHaloP); cudaFree(dHaloZ); cudaFree(dPeerTable);
         cudaFree(ws.partials); cudaFree(ws.counters); cudaFree(ws.scalars); cudaFreeHost(hScalars);
         cudaEventDestroy(evEntry); cudaEventDestroy(evLoop0); cudaEventDestroy(evLoop1);
         if (ownStream) cudaStreamDestroy(stream);
@@ -356,10 +350,12 @@ struct Plan : PlanBase {
         ws.comm.world = world; ws.comm.rank = rank; ws.comm.epoch = commBlock->epoch;
         for (int r = 0; r < world; ++r) {
             CommBlock* cb = (r == rank) ? commBlock : (CommBlock*)open(h[3 * r + 0]);
-            ws.comm.peerPartials[r] = &cb->partials[0][0][0];
-            ws.comm.peerFlags[r] = &cb->flags[0][0];
+            hostPeerTable[r] = &cb->words[0][0][0][0];
             peerBlocks[r] = cb;
         }
+        if (!dPeerTable) OPT_CUDA_CHECK(cudaMalloc((void**)&dPeerTable, sizeof(void*) * kMaxRanks));
+        OPT_CUDA_CHECK(cudaMemcpy(dPeerTable, hostPeerTable, sizeof(void*) * kMaxRanks, cudaMemcpyHostToDevice));
+        ws.comm.peerWords = dPeerTable;
         void* upZ = nullptr; void* upP = nullptr; void* dnZ = nullptr; void* dnP = nullptr;
         if (rank > 0 && upperRows > 0) { upZ = open(h[3 * (rank - 1) + 1]); upP = open(h[3 * (rank - 1) + 2]); }
         if (rank + 1 < world && lowerRows > 0) { dnZ = open(h[3 * (rank + 1) + 1]); dnP = open(h[3 * (rank + 1) + 2]); }
@@ -376,6 +372,9 @@ struct Plan : PlanBase {
             hp.epoch = &commBlock->haloEpoch;
         };
         fill(haloP, upP, dnP); fill(haloZ, upZ, dnZ);
+        if (!dHaloP) { OPT_CUDA_CHECK(cudaMalloc((void**)&dHaloP, sizeof(HaloPlan))); OPT_CUDA_CHECK(cudaMalloc((void**)&dHaloZ, sizeof(HaloPlan))); }
+        OPT_CUDA_CHECK(cudaMemcpy(dHaloP, &haloP, sizeof(HaloPlan), cudaMemcpyHostToDevice));
+        OPT_CUDA_CHECK(cudaMemcpy(dHaloZ, &haloZ, sizeof(HaloPlan), cudaMemcpyHostToDevice));
         auto ranges = E->ownedScalarRanges();
         ownVec = OwnedRanges{}; ownScalar = OwnedRanges{};
         for (size_t i = 0; i < ranges.size() && i < 4; ++i) {
@@ -388,9 +387,11 @@ struct Plan : PlanBase {
         return 0;
     }
     CommBlock* peerBlocks[kMaxRanks] = {};
-    void exchangeHalo(HaloPlan& hp, const T* vec) {
+    unsigned long long* hostPeerTable[kMaxRanks] = {};
+    void exchangeHalo(const HaloPlan& hp, const T* vec) {
         if (world <= 1 || hp.nSeg == 0 || (!hp.peerVec[0] && !hp.peerVec[1])) return;
-        k_haloExchange<T><<<1, 1024, 0, stream>>>(hp, vec); ++launches;
+        if (getenv("OPTB_SKIP_HALO")) return;   // timing experiment only (results are wrong)
+        k_haloExchange<T><<<1, 1024, 0, stream>>>(&hp == &haloP ? dHaloP : dHaloZ, ws, vec); ++launches;
     }
     void readScalars() {
         if (world > 1) { k_finalizeScalars<<<1, 32, 0, stream>>>(ws, (1u << kRz0) | (1u << kRz1) | (1u << kPAp) | (1u << kCost) | (1u << kModelCost) | (1u << kQ)); ++launches; }
@@ -439,15 +440,16 @@ struct Plan : PlanBase {
         const T* ctc = lm ? CtC : nullptr;
         bool pending = false;
         T *cur = p, *alt = p2;
+        const bool kernelHalo = world > 1 && fuse && E->inKernelHalo();   // z / p0 halos move inside the J^T J kernels
         for (int l = 0; l < L; ++l) {
             int rzOld = l & 1, rzNew = (l + 1) & 1;
             if (pending) {
                 // Step3 of iteration l-1 (beta = rz[rzOld_now]/rz[rzNew_now^...]) fused into this Step1
-                E->step3ApplyJTJ(c, z, cur, alt, Ap, ctc, /*rzNew of l-1*/ rzOld, /*rzOld of l-1*/ rzNew, kPAp);
+                E->step3ApplyJTJ(c, z, cur, alt, Ap, ctc, /*rzNew of l-1*/ rzOld, /*rzOld of l-1*/ rzNew, kPAp, kernelHalo ? dHaloZ : nullptr);
                 std::swap(cur, alt);
                 ++launches; pending = false;
             } else {
-                E->applyJTJ(c, cur, Ap, ctc, kPAp); ++launches;   // PCGStep1 (+_Graph)
+                E->applyJTJ(c, cur, Ap, ctc, kPAp, (kernelHalo && l == 0) ? dHaloP : nullptr); ++launches;   // PCGStep1 (+_Graph)
             }
             bool reset = lm && ((l + 1) % sp.residual_reset_period) == 0;
             if (reset) {   // :1077-1083
@@ -460,18 +462,20 @@ struct Plan : PlanBase {
             } else {
                 launchStep2(rzOld, rzNew, cur);
             }
-            exchangeHalo(haloZ, z);                            // neighbours need z on my boundary rows for their p = z + beta p
+            if (!(kernelHalo && fuse && l + 1 < L)) exchangeHalo(haloZ, z);   // neighbours need z on my boundary rows for their p = z + beta p
             if (fuse && !lm && l + 1 < L) pending = true;   // defer Step3 into the next Step1
             else launchStep3(rzNew, rzOld, cur);
             if (lm) { k_lmZeta<T><<<1, 1, 0, stream>>>(ws, l, (T)sp.q_tolerance); ++launches; }
         }
         pFinal = cur;
     }
-    void runLoop(int L) {
+    bool loopFuses() {
         bool fuse = useFusion && !lm;
-        if (fuse) {   // probe support once (no launch): energies that do not implement it return false
-            fuse = E->step3ApplyJTJ(ctx(), nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, -2);
-        }
+        if (fuse) fuse = E->step3ApplyJTJ(ctx(), nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, -2);   // capability probe, no launch
+        return fuse;
+    }
+    void runLoop(int L) {
+        bool fuse = loopFuses();
         OPT_CUDA_CHECK(cudaEventRecord(evLoop0, stream));
         if (useGraph && L > 0) {
             if (!loopExec || loopExecIters != L || loopExecFused != fuse) {
@@ -510,8 +514,8 @@ struct Plan : PlanBase {
             k_copyScalar<<<1, 1, 0, stream>>>(ws, kQPrev, kQ);          // Q0 = fetchQ
             k_setScalar<<<1, 1, 0, stream>>>(ws, kFlags, 0.0); launches += 2;
         }
-        exchangeHalo(haloP, p);                                // initial direction on the halo rows
         int L = sp.lIterations; if (maxLinIters >= 0 && maxLinIters < L) L = maxLinIters;
+        if (!(world > 1 && loopFuses() && E->inKernelHalo() && L > 0)) exchangeHalo(haloP, p);   // initial direction on the halo rows
         runLoop(L);
         if (maxLinIters >= 0) { OPT_CUDA_CHECK(cudaStreamSynchronize(stream)); return 1; }   // debug hook: PCG state left for inspection
         T model_cost_change = 0;

@@ -38,6 +38,20 @@ struct UnknownArray {
     long offset = 0;        // start inside every PCG vector, in scalars; 64-scalar aligned
 };
 
+// Halo exchange of one flat vector between slab neighbours.  Segments are this rank's
+// boundary rows; peerVec are the neighbours' copies of the same vector (CUDA IPC), flags live in the
+// ranks' mailbox blocks.  Used either by the stand-alone k_haloExchange or from inside an energy's
+// J^T J kernel (push at kernel start, wait only before tiles that touch halo rows).
+struct HaloPlan {
+    int nSeg;
+    long srcOff[4], dstOff[4], len[4];   // in scalars
+    int dir[4];                          // 0 = to the upper neighbour, 1 = to the lower neighbour
+    void* peerVec[2];                    // neighbour's copy of the vector being exchanged (nullptr: no neighbour)
+    unsigned long long* peerFlag[2];     // neighbour's "halo arrived from me" flag
+    unsigned long long* myFlag[2];       // my flags, written by the upper / lower neighbour
+    unsigned long long* epoch;           // local counter (stand-alone exchange kernel only)
+};
+
 struct LaunchCtx {
     cudaStream_t stream;
     ReduceWorkspace ws;
@@ -58,13 +72,16 @@ struct EnergyOps {
     // scalars[rzSlot] = r.p ; also refreshes whatever per-linearisation data applyJTJ needs.
     virtual void pcgInit(const LaunchCtx& c, T* delta, T* r, T* pre, T* p, int rzSlot) = 0;
     // PCGStep1 (+_Graph): out = (J^T J [+ diag(CtC)]) x, scalars[dotSlot] = x.out  (dotSlot<0: no reduction)
-    virtual void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot) = 0;
+    // halo != nullptr (only when inKernelHalo()): the kernel itself pushes x's boundary rows to the neighbours and
+    // waits for theirs before touching halo rows.
+    virtual void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot, const HaloPlan* halo = nullptr) = 0;
+    virtual bool inKernelHalo() const { return false; }
     // optional fusion of PCGStep3 into PCGStep1:  p <- z + beta*p  (beta = rz[new]/rz[old], guarded),
     // then out = (J^T J [+CtC]) p and scalars[dotSlot] = p.out.  Return false if not implemented.
     // p is double-buffered by the caller (pOld read incl. neighbours, pNew written) so the stencil never
     // sees a half-updated direction.  Called with dotSlot == -2 it only reports support (no launch).
     virtual bool step3ApplyJTJ(const LaunchCtx&, const T* /*z*/, const T* /*pOld*/, T* /*pNew*/, T* /*out*/, const T* /*CtC*/,
-                               int /*rzNew*/, int /*rzOld*/, int /*dotSlot*/) { return false; }
+                               int /*rzNew*/, int /*rzOld*/, int /*dotSlot*/, const HaloPlan* /*haloZ*/ = nullptr) { return false; }
     // computeCost (+_Graph): scalars[kCost] = 1/2 sum r^2
     virtual void cost(const LaunchCtx& c) = 0;
     // LM: CtC <- diag(J^T J)/radius (PCGComputeCtC), scalars[kModelCost] = 1/2 sum (r + J delta)^2

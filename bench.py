@@ -230,11 +230,18 @@ def main():
         value = args.steps * args.liters / (ms / 1e3)          # PCG steps/s of the one shared problem
         e2e_value = ksteps * args.liters / (e2e_ms / 1e3)
         loop_step_us = 1e3 * statistics.mean(loop_ms) / args.liters
-        fused = "PCGStep3+PCGStep1(fused)" in prof
-        dom_name = "PCGStep3+PCGStep1(fused)" if fused else "PCGStep1"
-        dom_bytes = (BYTES_STEP1 + BYTES_STEP3 if fused else BYTES_STEP1) * pixels
-        dom_ms = prof.get(dom_name)
-        if dom_ms is None:                  # multi-GPU: no per-kernel replay; report the PCG step as the unit
+        # dominant kernel of the inner loop = the larger of the two per-iteration kernels in the CUDA-event replay
+        # (same ordering as the ncu launch list, profiles/r1_ncu_iw2048.md); algorithmic bytes per SURVEY 8(d)
+        loop_kernels = {"PCGStep2": BYTES_STEP2, "PCGStep3+PCGStep1(fused)": BYTES_STEP1 + BYTES_STEP3, "PCGStep1": BYTES_STEP1}
+        cands = [k for k in ("PCGStep2", "PCGStep3+PCGStep1(fused)") if k in prof] or [k for k in ("PCGStep1",) if k in prof]
+        traffic = None
+        if cands:
+            dom_name = max(cands, key=lambda k: prof[k])
+            dom_bytes, dom_ms = loop_kernels[dom_name] * pixels, prof[dom_name]
+            tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+            if os.path.exists(tp) and W == W_FULL and H == H_FULL:
+                traffic = json.load(open(tp)).get(dom_name)
+        else:                               # multi-GPU: no per-kernel replay; report the PCG step as the unit
             dom_name, dom_bytes, dom_ms = "PCG step (all kernels, rank 0 slab)", BYTES_PCG_STEP * W * (slab.g1 - slab.g0), loop_step_us * 1e-3
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         line = {
@@ -249,7 +256,7 @@ def main():
                     "ms_per_step": e2e_ms / ksteps, "what": "pinned host inputs -> H2D, Opt_ProblemInit + one Opt_ProblemStep via the C ABI, unknowns -> D2H"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src, "traffic": traffic,
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
                          "pcg_step": {"algorithmic_bytes_per_gpu": BYTES_PCG_STEP * W * (slab.g1 - slab.g0), "us_in_timed_region": loop_step_us,
                                       "achieved": BYTES_PCG_STEP * W * (slab.g1 - slab.g0) / (loop_step_us * 1e-6) / 1e9,

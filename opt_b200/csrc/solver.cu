@@ -406,6 +406,7 @@ struct Plan : PlanBase {
 
     void init(void** params) override {   // :956-1007
         E->bind(params);
+        E->newSolve();
         enter();
         nIter = 0; finished = false; launches = 0;
         trust_region_radius = (T)sp.trust_region_radius; radius_decrease_factor = (T)sp.radius_decrease_factor;
@@ -656,8 +657,9 @@ struct Plan : PlanBase {
 
 template <class T>
 static EnergyOps<T>* makeEnergy(const std::string& energy, const unsigned* dims) {
-    if (energy == "image_warping") return makeImageWarping<T>(dims);
-    return nullptr;
+    // OPTB_GENERIC=1 routes every energy (image_warping included) through the generic cached-Jacobian engine
+    if (energy == "image_warping" && !getenv("OPTB_GENERIC")) return makeImageWarping<T>(dims);
+    return makeGenericEnergy<T>(energy, dims);
 }
 
 PlanBase* makePlan(const std::string& energy, bool lm, bool doublePrecision, const unsigned* dims, int verbosity, int collectTiming) {

@@ -96,6 +96,8 @@ struct EnergyOps {
     struct HaloSegment { long srcOff, dstOff, len; int dir; };          // scalars in the flat layout; dir 0 = up, 1 = down
     virtual std::vector<HaloSegment> haloSegments() const { return {}; }
     virtual std::vector<std::pair<long, long>> ownedScalarRanges() const { return {}; }
+    // called at every Opt_ProblemInit: graph indices / masks may have changed since the last solve
+    virtual void newSolve() {}
     virtual const char* name() const = 0;
     static void unsupported(const char* what) {
         fprintf(stderr, "opt_b200: %s is not implemented for this energy\n", what);
@@ -139,6 +141,6 @@ PlanBase* makePlan(const std::string& energy, bool lm, bool doublePrecision, con
 
 // per-energy factories (energy_*.cu); return nullptr when the energy/precision is not built
 template <class T> EnergyOps<T>* makeImageWarping(const unsigned* dims);
-template <class T> EnergyOps<T>* makeArapMesh(const unsigned* dims);
+template <class T> EnergyOps<T>* makeGenericEnergy(const std::string& energy, const unsigned* dims);
 
 }  // namespace optb

@@ -659,6 +659,7 @@ template <class T>
 static EnergyOps<T>* makeEnergy(const std::string& energy, const unsigned* dims) {
     // OPTB_GENERIC=1 routes every energy (image_warping included) through the generic cached-Jacobian engine
     if (energy == "image_warping" && !getenv("OPTB_GENERIC")) return makeImageWarping<T>(dims);
+    if (energy == "arap_mesh_deformation" && !getenv("OPTB_GENERIC")) return makeArapMesh<T>(dims);
     return makeGenericEnergy<T>(energy, dims);
 }
 

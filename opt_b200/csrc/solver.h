@@ -141,6 +141,7 @@ PlanBase* makePlan(const std::string& energy, bool lm, bool doublePrecision, con
 
 // per-energy factories (energy_*.cu); return nullptr when the energy/precision is not built
 template <class T> EnergyOps<T>* makeImageWarping(const unsigned* dims);
+template <class T> EnergyOps<T>* makeArapMesh(const unsigned* dims);
 template <class T> EnergyOps<T>* makeGenericEnergy(const std::string& energy, const unsigned* dims);
 
 }  // namespace optb

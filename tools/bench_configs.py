@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Secondary measurements for the other BASELINE.json configs (single GPU): PCG steps/s and ms per nonlinear
+iteration through Opt_ProblemStep, CUDA events, inputs resident.  Not the driver's bench line (that is bench.py,
+image_warping 2048^2); results are recorded in profiles/ and DESIGN.md."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def run(name, dims, spec, kind, host, dp, liters, steps=6, warmup=3, bytes_per_step=None):
+    import torch
+    from opt_b200 import OptSolver, spec_path, workloads
+    dev = workloads.to_device(host)
+    s = OptSolver(dims, spec_path(spec), kind, double_precision=dp)
+    s.set_solver_parameters({"nIterations": steps + warmup + 1, "lIterations": liters})
+    s.init(dev)
+    c0 = s.current_cost()
+    for _ in range(warmup):
+        s.step(dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    loop = []
+    e0.record()
+    done = 0
+    for _ in range(steps):
+        if not s.step(dev):
+            break
+        done += 1; loop.append(s.pcg_loop_ms_last_step())
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = {"config": name, "kind": kind, "dtype": "f64" if dp else "f32", "lIterations": liters, "gn_iterations_timed": done,
+           "ms_per_nonlinear_iter": ms / max(done, 1), "pcg_steps_per_s": (done * liters) / (ms / 1e3) if done else None,
+           "pcg_loop_us_per_step": 1e3 * float(np.mean(loop)) / liters if loop else None, "launches_per_nonlinear_iter": s.launches_last_step(),
+           "cost0": c0, "cost": s.current_cost()}
+    if bytes_per_step and out["pcg_loop_us_per_step"]:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        out["algorithmic_bytes_per_pcg_step"] = bytes_per_step
+        out["achieved_gbs"] = bytes_per_step / (out["pcg_loop_us_per_step"] * 1e-6) / 1e9
+        out["frac_of_hbm_peak"] = out["achieved_gbs"] / peak
+    print(json.dumps(out), flush=True)
+    s.close()
+
+
+def main():
+    from opt_b200 import workloads
+    which = sys.argv[1:] or ["iw512", "sfs", "arap500k", "arap500k_generic", "rna"]
+    if "iw512" in which:
+        run("image_warping 512x512 fp32 GN", [512, 512], "image_warping", "gaussNewtonGPU", workloads.image_warping(512, 512), False, 400, bytes_per_step=188 * 512 * 512)
+    if "sfs" in which:
+        run("shape_from_shading 640x480 fp32 LM (synthetic depth)", [640, 480], "shape_from_shading", "LMGPU", workloads.shape_from_shading(640, 480), False, 10, steps=10,
+            bytes_per_step=90 * 640 * 480)
+    nx = 708
+    nv = nx * nx
+    if "arap500k" in which or "arap500k_generic" in which:
+        host = workloads.arap_mesh(nx, nx, n_handles=32)
+        ne = host[6]
+        for tag in ("arap500k", "arap500k_generic"):
+            if tag not in which:
+                continue
+            if tag.endswith("generic"):
+                os.environ["OPTB_GENERIC"] = "1"
+            run(f"arap_mesh_deformation {nv} vertices / {ne} directed edges fp32 GN" + (" [generic engine]" if tag.endswith("generic") else ""), [nv], "arap_mesh_deformation",
+                "gaussNewtonGPU", workloads.clone_params(host), False, 100, bytes_per_step=396 * nv + 8 * ne)
+            os.environ.pop("OPTB_GENERIC", None)
+    if "rna" in which:
+        n2 = 316
+        host = workloads.robust_nonrigid(n2, n2, dtype=np.float64)
+        run(f"robust_nonrigid_alignment {n2 * n2} vertices fp64 LM [generic engine]", [n2 * n2], "robust_nonrigid_alignment", "LMGPU", host, True, 250, steps=4,
+            bytes_per_step=1136 * n2 * n2 + 8 * host[8])
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,9 @@ int OptB200_PlanConnect(Opt_Plan* plan, int rank, int world, const void* allHand
 /* Front-end probe (no GPU needed): writes the registry name of the energy in `filename` to `out` and
  * returns 0, or writes the rejection message and returns 1. */
 int OptB200_SpecEnergyName(const char* filename, char* out, int outLen);
+/* General front end, host only (no GPU needed): runs the .t file (Lua subset + Opt DSL), generates the residual code
+ * and compiles it with NVRTC for sm_100a.  Returns 0 and a summary in msg, or nonzero and the error text. */
+int OptB200_FrontendCompile(const char* filename, int doublePrecision, char* msg, int msgLen);
 
 #ifdef __cplusplus
 }

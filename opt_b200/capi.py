@@ -41,6 +41,7 @@ SYMBOLS = [
     ("OptB200_PcgLoopMsLastStep", ctypes.c_float, [_VP]),
     ("OptB200_ProfileKernels", ctypes.c_int, [_VP, _VPP, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]),
     ("OptB200_SpecEnergyName", ctypes.c_int, [_CP, ctypes.c_char_p, ctypes.c_int]),
+    ("OptB200_FrontendCompile", ctypes.c_int, [_CP, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
     ("OptB200_PlanCommHandles", ctypes.c_int, [_VP, _VP, ctypes.c_int]),
     ("OptB200_PlanConnect", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
 ]

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include "solver.h"
 #include "spec.h"
+#include "frontend.h"
 
 extern "C" {
 #include "../../include/OptB200.h"
@@ -74,14 +75,23 @@ Opt_Plan* Opt_ProblemPlan(Opt_State* state, Opt_Problem* problem, unsigned int* 
         fprintf(stderr, "opt_b200: unknown solver kind '%s' (expected gaussNewtonGPU or LMGPU)\n", d.solverkind.c_str());
         return nullptr;
     }
-    optb::SpecMatch m = optb::matchSpecFile(d.filename);
-    if (!m.ok) { fprintf(stderr, "opt_b200: %s\n", m.message.c_str()); return nullptr; }
     bool lm = d.solverkind.find("LM") != std::string::npos;
-    optb::PlanBase* impl = optb::makePlan(m.energy, lm, state->params.doublePrecision != 0, dimensions,
-                                          state->params.verbosityLevel, state->params.collectPerKernelTimingInfo);
-    if (!impl) {
-        fprintf(stderr, "opt_b200: energy '%s' is registered but has no kernel set in this build\n", m.energy.c_str());
-        return nullptr;
+    // Two tiers.  (a) the spec's canonical token stream is in the registry: its hand-written / statically compiled
+    // kernel set is used.  (b) anything else (or everything, with OPTB_FRONTEND=1): the .t file is executed by the
+    // front end, its residual code is generated, compiled with NVRTC and run on the generic engine -- the
+    // counterpart of the reference's Lua/Terra JIT at this point (o.t:861-882).
+    optb::SpecMatch m = optb::matchSpecFile(d.filename);
+    optb::PlanBase* impl = nullptr;
+    if (m.ok && !getenv("OPTB_FRONTEND")) {
+        impl = optb::makePlan(m.energy, lm, state->params.doublePrecision != 0, dimensions, state->params.verbosityLevel, state->params.collectPerKernelTimingInfo);
+        if (!impl) { fprintf(stderr, "opt_b200: energy '%s' is registered but has no kernel set in this build\n", m.energy.c_str()); return nullptr; }
+    } else {
+        optb::fe::CompiledSpec cs = optb::fe::compileSpecFile(d.filename);
+        if (!cs.ok) { fprintf(stderr, "opt_b200: %s\n", cs.error.c_str()); return nullptr; }   // like the reference: message + NULL plan (o.t:862-880)
+        std::string err;
+        impl = optb::makePlanDynamic(cs, d.filename, lm, state->params.doublePrecision != 0, dimensions, state->params.verbosityLevel, state->params.collectPerKernelTimingInfo, err);
+        if (!impl) { fprintf(stderr, "opt_b200: %s: %s\n", d.filename.c_str(), err.c_str()); return nullptr; }
+        if (state->params.verbosityLevel > 0) printf("compiled '%s' through the front end: %zu scalar residual groups\n", d.filename.c_str(), cs.groups.size());
     }
     if (state->params.verbosityLevel > 0) printf("problem plan complete\n");
     return new Opt_Plan{ impl };
@@ -114,6 +124,14 @@ int OptB200_ProfileKernels(Opt_Plan* plan, void** pp, int reps, int maxOut, cons
 int OptB200_PlanCommHandles(Opt_Plan* plan, void* out, int outBytes) { return plan->impl->commHandles(out, outBytes); }
 int OptB200_PlanConnect(Opt_Plan* plan, int rank, int world, const void* allHandles, int ownedBegin, int ownedEnd, int upperRows, int lowerRows) {
     return plan->impl->connect(rank, world, allHandles, ownedBegin, ownedEnd, upperRows, lowerRows);
+}
+int OptB200_FrontendCompile(const char* filename, int doublePrecision, char* msg, int msgLen) {
+    optb::fe::CompiledSpec cs = optb::fe::compileSpecFile(filename);
+    if (!cs.ok) { snprintf(msg, msgLen, "%s", cs.error.c_str()); return 1; }
+    std::vector<char> cubin; std::string log;
+    if (!optb::compileSpecToCubin(cs, doublePrecision != 0, cubin, log)) { snprintf(msg, msgLen, "NVRTC: %s", log.c_str()); return 2; }
+    snprintf(msg, msgLen, "ok: %zu residual groups, %zu bytes of generated CUDA, %zu bytes of sm_100a cubin", cs.groups.size(), cs.cudaSource.size(), cubin.size());
+    return 0;
 }
 int OptB200_SpecEnergyName(const char* filename, char* out, int outLen) {
     optb::SpecMatch m = optb::matchSpecFile(filename);

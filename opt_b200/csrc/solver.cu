@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include "solver.h"
+#include "frontend.h"
 
 namespace optb {
 
@@ -669,6 +670,16 @@ PlanBase* makePlan(const std::string& energy, bool lm, bool doublePrecision, con
         return e ? new Plan<double>(e, lm, verbosity, collectTiming) : nullptr;
     }
     EnergyOps<float>* e = makeEnergy<float>(energy, dims);
+    return e ? new Plan<float>(e, lm, verbosity, collectTiming) : nullptr;
+}
+
+PlanBase* makePlanDynamic(const fe::CompiledSpec& cs, const std::string& name, bool lm, bool doublePrecision, const unsigned* dims, int verbosity,
+                          int collectTiming, std::string& error) {
+    if (doublePrecision) {
+        EnergyOps<double>* e = makeDynamicEnergy<double>(cs, dims, name, error);
+        return e ? new Plan<double>(e, lm, verbosity, collectTiming) : nullptr;
+    }
+    EnergyOps<float>* e = makeDynamicEnergy<float>(cs, dims, name, error);
     return e ? new Plan<float>(e, lm, verbosity, collectTiming) : nullptr;
 }
 

@@ -135,9 +135,16 @@ struct PlanBase {
     virtual int connect(int rank, int world, const void* allHandles, int ownedBegin, int ownedEnd, int upperRows, int lowerRows) = 0;
 };
 
+namespace fe { struct CompiledSpec; }
 // factory implemented in solver.cu
 PlanBase* makePlan(const std::string& energy, bool lm, bool doublePrecision, const unsigned* dims,
                    int verbosity, int collectTiming);
+
+// plan over a spec produced by the .t front end (frontend.cpp) and compiled with NVRTC (dynamic_ops.cu)
+PlanBase* makePlanDynamic(const fe::CompiledSpec& cs, const std::string& name, bool lm, bool doublePrecision, const unsigned* dims,
+                          int verbosity, int collectTiming, std::string& error);
+template <class T> EnergyOps<T>* makeDynamicEnergy(const fe::CompiledSpec& cs, const unsigned* dims, const std::string& name, std::string& error);
+bool compileSpecToCubin(const fe::CompiledSpec& cs, bool doublePrecision, std::vector<char>& cubin, std::string& log);
 
 // per-energy factories (energy_*.cu); return nullptr when the energy/precision is not built
 template <class T> EnergyOps<T>* makeImageWarping(const unsigned* dims);

@@ -178,3 +178,11 @@ def spec_energy_name(filename):
     buf = ctypes.create_string_buffer(512)
     rc = L.OptB200_SpecEnergyName(os.fsencode(filename), buf, 512)
     return rc == 0, buf.value.decode()
+
+
+def frontend_compile(filename, double_precision=False):
+    """general front end, host only: (ok, message) of interpreting the .t file and NVRTC-compiling its residual code"""
+    L = capi.lib()
+    buf = ctypes.create_string_buffer(16384)
+    rc = L.OptB200_FrontendCompile(os.fsencode(filename), int(bool(double_precision)), buf, 16384)
+    return rc == 0, buf.value.decode(errors="replace")

@@ -103,3 +103,38 @@ def test_no_cpu_fallback(built):
     from opt_b200.capi import OptError
     with pytest.raises(OptError):
         OptSolver([8, 8], spec_path("image_warping"))
+
+
+@pytest.mark.parametrize("name", ["image_warping", "arap_mesh_deformation", "poisson_image_editing", "laplacian", "curveFitting", "shape_from_shading", "robust_nonrigid_alignment"])
+def test_front_end_compiles_every_shipped_spec(built, name):
+    """general front end (no GPU needed): the .t file is executed by the Lua-subset interpreter, its residual code is
+    generated and NVRTC compiles it for sm_100a"""
+    from opt_b200 import spec_path
+    from opt_b200.solver import frontend_compile
+    ok, msg = frontend_compile(spec_path(name), double_precision=(name == "curveFitting"))
+    assert ok, msg
+    assert "residual groups" in msg
+
+
+def test_front_end_accepts_a_new_energy_and_reports_errors(built, tmp_path):
+    from opt_b200.solver import frontend_compile
+    new = tmp_path / "tv_denoise.t"     # an energy that is in no registry: Huber-like smoothing with a data term and a graph-free 3-channel unknown
+    new.write_text("""
+        local W, H = Dim("W", 0), Dim("H", 1)
+        local X = Unknown("X", opt_float3, { W, H }, 0)
+        local Y = Array("Y", opt_float3, { W, H }, 1)
+        local lambda = Param("lambda", float, 2)
+        UsePreconditioner(true)
+        Energy(X(0, 0) - Y(0, 0))
+        for dx, dy in Stencil { { 1, 0 }, { 0, 1 } } do
+            local g = X(0, 0) - X(dx, dy)
+            local w = 1.0 / sqrt(sqrt(g:dot(g) + 0.0001))
+            Energy(Select(InBounds(dx, dy), lambda * w * g, 0))
+        end
+    """)
+    ok, msg = frontend_compile(str(new))
+    assert ok and "9 residual groups" in msg, msg
+    bad = tmp_path / "bad.t"
+    bad.write_text("local W = Dim('W', 0)\nlocal X = Unknown('X', opt_float, {W}, 0)\nEnergy(X(0) - undefined_name(1))\n")
+    ok, msg = frontend_compile(str(bad))
+    assert not ok and "line 3" in msg

@@ -180,6 +180,21 @@ __device__ __forceinline__ void gridReduceTo(double v, const ReduceWorkspace& ws
     __syncthreads();   // s_warp / s_last reusable by a second call in the same kernel
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with launchPdl may begin while its predecessor on the stream
+// is still draining; it must call pdlWait() before touching anything the predecessor wrote.  Kernels call
+// pdlTrigger() first so that THEIR successor can be scheduled early.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdlTrigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdlWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <class... KArgs, class... Args>
+inline void launchPdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    OPT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 inline int divUp(long a, long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace optb

@@ -29,6 +29,7 @@ struct ArapData {
     long offA;                                         // Angle block inside the flat PCG vectors
     ArapPack<T>* pack;
     const int *outStart, *outNbr, *inStart, *inNbr;    // vertex-CSR neighbour lists (out: edges v->b, in: edges c->v)
+    int lo, hi, wlo, whi;                              // multi-GPU: owned vertices [lo,hi) and the window incl. halo [wlo,whi); single GPU: [0,N)
 };
 
 __device__ __forceinline__ void sincosV(float a, float* s, float* c) { sincosf(a, s, c); }
@@ -61,7 +62,7 @@ template <class T> __device__ __forceinline__ T dot3(const V3<T>& a, const V3<T>
 // pass 1: per-vertex pack.  pass 2: gather J^T F and diag(J^T J), then r, pre, p, r.p  (:361-419, :687-692)
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_arapPack(ArapData<T> D) {
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < D.N; v += gridDim.x * kBlock) {
+    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
         ArapPack<T> s;
         sincosV(D.Angle[3 * v], &s.sa, &s.ca); sincosV(D.Angle[3 * v + 1], &s.sb, &s.cb); sincosV(D.Angle[3 * v + 2], &s.sg, &s.cg);
         s.ux = D.UrShape[3 * v]; s.uy = D.UrShape[3 * v + 1]; s.uz = D.UrShape[3 * v + 2];
@@ -74,7 +75,14 @@ __global__ void __launch_bounds__(kBlock) k_arapInit(ArapData<T> D, ReduceWorksp
                                                      T* __restrict__ pre, T* __restrict__ p) {
     T acc = T(0);
     const T w = D.w, w2 = D.w * D.w;
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < D.N; v += gridDim.x * kBlock) {
+    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
+        if (v < D.lo || v >= D.hi) {   // halo vertex: no unknowns of ours; its p arrives from the owner (k_haloExchange)
+            const long o = 3L * v, a = D.offA + 3L * v;
+            delta[o] = delta[o + 1] = delta[o + 2] = T(0); delta[a] = delta[a + 1] = delta[a + 2] = T(0);
+            r[o] = r[o + 1] = r[o + 2] = T(0); r[a] = r[a + 1] = r[a + 2] = T(0);
+            pre[o] = pre[o + 1] = pre[o + 2] = T(0); pre[a] = pre[a + 1] = pre[a + 2] = T(0);
+            continue;
+        }
         const ArapPack<T> sv = D.pack[v];
         const ArapRot<T> Rv(sv);
         const V3<T> Ov = ld3(D.Offset, v);
@@ -139,10 +147,16 @@ __global__ void __launch_bounds__(kBlock) k_arapApplyJTJ(ArapData<T> D, ReduceWo
     auto dirA = [&](int v) -> V3<T> { V3<T> q = ld3(pIn + D.offA, v); if (FUSE3) { const V3<T> zz = ld3(z + D.offA, v); q.x = zz.x + beta * q.x; q.y = zz.y + beta * q.y; q.z = zz.z + beta * q.z; } return q; };
     const T w2 = D.w * D.w, wf2 = D.wf * D.wf;
     T acc = T(0);
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < D.N; v += gridDim.x * kBlock) {
+    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
+        const V3<T> pOv = dirO(v), pAv = dirA(v);
+        if (v < D.lo || v >= D.hi) {   // halo vertex: only its new direction is needed here
+            const long o = 3L * v, a = D.offA + 3L * v;
+            out[o] = out[o + 1] = out[o + 2] = T(0); out[a] = out[a + 1] = out[a + 2] = T(0);
+            if (FUSE3) { pOut[o] = pOv.x; pOut[o + 1] = pOv.y; pOut[o + 2] = pOv.z; pOut[a] = pAv.x; pOut[a + 1] = pAv.y; pOut[a + 2] = pAv.z; }
+            continue;
+        }
         const ArapPack<T> sv = D.pack[v];
         const ArapRot<T> Rv(sv);
-        const V3<T> pOv = dirO(v), pAv = dirA(v);
         V3<T> aO{ T(0), T(0), T(0) }, aA{ T(0), T(0), T(0) };
         for (int k = D.outStart[v]; k < D.outStart[v + 1]; ++k) {
             const int b = D.outNbr[k];
@@ -188,7 +202,8 @@ __global__ void __launch_bounds__(kBlock) k_arapApplyJTJ(ArapData<T> D, ReduceWo
 template <class T, bool MODEL>
 __global__ void __launch_bounds__(kBlock) k_arapCost(ArapData<T> D, ReduceWorkspace ws, int slot, const T* __restrict__ delta) {
     T acc = T(0);
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < D.N; v += gridDim.x * kBlock) {
+    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
+        if (v < D.lo || v >= D.hi) continue;
         const V3<T> Ov = ld3(D.Offset, v), Uv = ld3(D.UrShape, v);
         ArapPack<T> sv; sincosV(D.Angle[3 * v], &sv.sa, &sv.ca); sincosV(D.Angle[3 * v + 1], &sv.sb, &sv.cb); sincosV(D.Angle[3 * v + 2], &sv.sg, &sv.cg);
         const ArapRot<T> Rv(sv);
@@ -224,7 +239,7 @@ __global__ void __launch_bounds__(kBlock) k_arapCost(ArapData<T> D, ReduceWorksp
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_arapCtC(ArapData<T> D, T* __restrict__ CtC, T invRadius) {
     const T w2 = D.w * D.w;
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < D.N; v += gridDim.x * kBlock) {
+    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
         const ArapPack<T> sv = D.pack[v];
         const ArapRot<T> Rv(sv);
         T dO = T(0); V3<T> dA{ T(0), T(0), T(0) };
@@ -258,7 +273,7 @@ struct ArapOps : EnergyOps<T> {
     bool csrValid = false;
     int sms = 148;
     ArapOps(const unsigned* dims) {
-        D.N = (int)dims[0];
+        D.N = (int)dims[0]; D.lo = D.wlo = 0; D.hi = D.whi = D.N;
         this->unknowns.resize(2);
         this->unknowns[0].elements = D.N; this->unknowns[0].channels = 3;   // Offset
         this->unknowns[1].elements = D.N; this->unknowns[1].channels = 3;   // Angle
@@ -271,7 +286,7 @@ struct ArapOps : EnergyOps<T> {
     }
     ~ArapOps() override { for (void* q : { (void*)D.pack, (void*)outStart, (void*)outNbr, (void*)inStart, (void*)inNbr, (void*)keysTmp, cubTemp }) if (q) cudaFree(q); }
     const char* name() const override { return "arap_mesh_deformation"; }
-    int grid() const { long g = ((long)D.N + kBlock - 1) / kBlock; long cap = (long)sms * 8; if (g > cap) g = cap; if (g > kMaxPartials) g = kMaxPartials; return g < 1 ? 1 : (int)g; }
+    int grid() const { long g = ((long)(D.whi - D.wlo) + kBlock - 1) / kBlock; long cap = (long)sms * 8; if (g > cap) g = cap; if (g > kMaxPartials) g = kMaxPartials; return g < 1 ? 1 : (int)g; }
     void bind(void** q) override {   // positions: arap_mesh_deformation.t:2-8
         D.wf = (T) * (const float*)q[0]; D.w = (T) * (const float*)q[1];
         this->unknowns[0].user = q[2]; this->unknowns[1].user = q[3];
@@ -280,7 +295,27 @@ struct ArapOps : EnergyOps<T> {
         if (n != nEdges || v0 != (const int*)q[7] || v1 != (const int*)q[8]) csrValid = false;
         nEdges = n; v0 = (const int*)q[7]; v1 = (const int*)q[8];
     }
-    void newSolve() override { csrValid = false; }   // the caller may have rewritten the index arrays in place
+    void newSolve() override { csrValid = false; }
+    // ---- multi-GPU: 1-D decomposition of the (locality-ordered) vertex index.  Every rank binds the GLOBAL arrays; it owns the
+    // vertices [ownedBegin, ownedEnd) and keeps `up` / `dn` halo vertices beyond them (the graph's index bandwidth, uniform).
+    int haloUp = 0, haloDn = 0;
+    bool setSlab(int ownedBegin, int ownedEnd, int up, int dn) override {
+        if (ownedBegin < 0 || ownedEnd > D.N || ownedBegin >= ownedEnd || ownedBegin % 4 || (ownedEnd % 4 && ownedEnd != D.N) || up % 4 || dn % 4) return false;
+        if (ownedBegin - up < 0 || ownedEnd + dn > D.N || up > ownedEnd - ownedBegin || dn > ownedEnd - ownedBegin) return false;
+        D.lo = ownedBegin; D.hi = ownedEnd; D.wlo = ownedBegin - up; D.whi = ownedEnd + dn; haloUp = up; haloDn = dn;
+        return true;
+    }
+    std::vector<typename EnergyOps<T>::HaloSegment> haloSegments() const override {
+        std::vector<typename EnergyOps<T>::HaloSegment> s;   // vectors are global-size on every rank: destination offsets equal source offsets
+        if (haloUp > 0) { s.push_back({ 3L * D.lo, 3L * D.lo, 3L * haloUp, 0 }); s.push_back({ D.offA + 3L * D.lo, D.offA + 3L * D.lo, 3L * haloUp, 0 }); }
+        if (haloDn > 0) { s.push_back({ 3L * (D.hi - haloDn), 3L * (D.hi - haloDn), 3L * haloDn, 1 }); s.push_back({ D.offA + 3L * (D.hi - haloDn), D.offA + 3L * (D.hi - haloDn), 3L * haloDn, 1 }); }
+        return s;
+    }
+    std::vector<std::pair<long, long>> ownedScalarRanges() const override { return { { 3L * D.lo, 3L * D.hi }, { D.offA + 3L * D.lo, D.offA + 3L * D.hi } }; }
+    std::vector<std::pair<long, long>> processScalarRanges() const override {
+        if (D.wlo == 0 && D.whi == D.N) return {};
+        return { { 3L * D.wlo, 3L * D.whi }, { D.offA + 3L * D.wlo, D.offA + 3L * D.whi } };
+    }   // the caller may have rewritten the index arrays in place
     void buildCsr(cudaStream_t st) {
         if (csrValid) return;
         if (nEdges > capE) {

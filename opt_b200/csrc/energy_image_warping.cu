@@ -280,15 +280,17 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
     __shared__ __align__(8) uint64_t bars[kStages];
     constexpr int stageBytes = FUSE3 ? kStageBytesFused : kStageBytesPlain;
     const int tid = threadIdx.x;
+    pdlTrigger();
+    if (tid == 0) {   // prologue that does not depend on the previous kernel overlaps its tail (PDL)
+        for (int s = 0; s < kStages; ++s) mbarInit(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdlWait();
     float beta = 0.f;
     if (FUSE3) {
         double drn, dro; loadScalars2(ws, rzNew, rzOld, drn, dro);
         const float rn = (float)drn, ro = (float)dro;
         if (ro > 0.f) beta = rn / ro;
-    }
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbarInit(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     // Multi-GPU (hp.nSeg > 0): this kernel is also the halo exchange.  The last CTA first stores this rank's
@@ -620,7 +622,7 @@ struct ImageWarpingOps : EnergyOps<T> {
                 const IWMaps& m = mapsFor(x, nullptr);
                 const HaloPlan* hp = halo;
                 if (CtC) k_iwApplyJTJTma<false, true><<<gridTma, kBlock, kStages * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, CtC, tmaTilesX, tmaTiles, x, hp);
-                else k_iwApplyJTJTma<false, false><<<gridTma, kBlock, kStages * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, nullptr, tmaTilesX, tmaTiles, x, hp);
+                else launchPdl(k_iwApplyJTJTma<false, false>, gridTma, kBlock, (size_t)(kStages * kStageBytesPlain), c.stream, c.pdl, D, m, c.ws, dotSlot, 0, 0, (float*)nullptr, out, (const float*)nullptr, tmaTilesX, tmaTiles, (const float*)x, hp);
                 return;
             }
         }
@@ -634,7 +636,7 @@ struct ImageWarpingOps : EnergyOps<T> {
                 const IWMaps& m = mapsFor(pOld, z);
                 const HaloPlan* hp = halo;
                 if (CtC) k_iwApplyJTJTma<true, true><<<gridTmaF, kBlock, kStages * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, CtC, tmaTilesX, tmaTiles, z, hp);
-                else k_iwApplyJTJTma<true, false><<<gridTmaF, kBlock, kStages * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, nullptr, tmaTilesX, tmaTiles, z, hp);
+                else launchPdl(k_iwApplyJTJTma<true, false>, gridTmaF, kBlock, (size_t)(kStages * kStageBytesFused), c.stream, c.pdl, D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, (const float*)nullptr, tmaTilesX, tmaTiles, (const float*)z, hp);
                 return true;
             }
         }

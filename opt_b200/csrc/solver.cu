@@ -43,22 +43,31 @@ struct OwnedRanges {
     }
 };
 
+// Multi-GPU with replicated (global-size) vectors (graph energies): the part of the flat vectors this rank has to
+// stream at all = owned entries + halo entries, as up to two contiguous windows.  n == 0: everything.
+struct WindowRanges {
+    long lo[2], len[2]; long total; int n;
+    __device__ __forceinline__ long map(long j) const { return n == 0 ? j : (j < len[0] ? lo[0] + j : lo[1] + (j - len[0])); }
+};
+
 // ------------------------------------------------------------------------------------ PCGStep2
 // solverGPUGaussNewton.t:446-489.  alpha = rz_old / pAp (guarded), delta += alpha p, r -= alpha Ap,
 // z = pre*r, rz_new = z.r ; LM: q = 1/2 delta.(r+b).
 template <class T, bool LM, bool USEPRE>
-__global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, ReduceWorkspace ws, OwnedRanges own, int rzOld, int rzNew,
+__global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, WindowRanges win, ReduceWorkspace ws, OwnedRanges own, int rzOld, int rzNew,
                                                      T* __restrict__ delta, const T* __restrict__ p, T* __restrict__ r,
                                                      const T* __restrict__ Ap, const T* __restrict__ pre,
                                                      const T* __restrict__ b, T* __restrict__ z) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
+    pdlTrigger(); pdlWait();
     if (LM && ws.scalars[kFlags] != 0.0) return;
     double dnum, dden; loadScalars2(ws, rzOld, kPAp, dnum, dden);
     const T num = (T)dnum, den = (T)dden;
     T alpha = T(0);
     if (den > T(0)) alpha = num / den;
     T accRz = T(0), accQ = T(0);
-    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
+    for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < nVec; j += (long)gridDim.x * kBlock) {
+        const long i = win.map(j);
         const bool mine = own.owns(i);
         T d[N], pp[N], rr[N], ap[N], pr[N], bb[N], zz[N];
         unpack(reinterpret_cast<const V*>(delta)[i], d);
@@ -87,14 +96,15 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, ReduceWorkspace 
 
 // PCGStep2_1stHalf (:491-503): delta += alpha p
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_pcgStep2FirstHalf(long nVec, ReduceWorkspace ws, int rzOld, T* __restrict__ delta, const T* __restrict__ p) {
+__global__ void __launch_bounds__(kBlock) k_pcgStep2FirstHalf(long nVec, WindowRanges win, ReduceWorkspace ws, int rzOld, T* __restrict__ delta, const T* __restrict__ p) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
     if (ws.scalars[kFlags] != 0.0) return;
     double dnum, dden; loadScalars2(ws, rzOld, kPAp, dnum, dden);
     const T num = (T)dnum, den = (T)dden;
     T alpha = T(0);
     if (den > T(0)) alpha = num / den;
-    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
+    for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < nVec; j += (long)gridDim.x * kBlock) {
+        const long i = win.map(j);
         T d[N], pp[N];
         unpack(reinterpret_cast<const V*>(delta)[i], d); unpack(reinterpret_cast<const V*>(p)[i], pp);
 #pragma unroll
@@ -104,13 +114,14 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2FirstHalf(long nVec, ReduceW
 }
 // PCGStep2_2ndHalf (:505-534): r = b - Adelta, z = pre*r, rz_new, q
 template <class T, bool USEPRE>
-__global__ void __launch_bounds__(kBlock) k_pcgStep2SecondHalf(long nVec, ReduceWorkspace ws, OwnedRanges own, int rzNew, const T* __restrict__ delta,
+__global__ void __launch_bounds__(kBlock) k_pcgStep2SecondHalf(long nVec, WindowRanges win, ReduceWorkspace ws, OwnedRanges own, int rzNew, const T* __restrict__ delta,
                                                                T* __restrict__ r, const T* __restrict__ Adelta, const T* __restrict__ pre,
                                                                const T* __restrict__ b, T* __restrict__ z) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
     if (ws.scalars[kFlags] != 0.0) return;
     T accRz = T(0), accQ = T(0);
-    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
+    for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < nVec; j += (long)gridDim.x * kBlock) {
+        const long i = win.map(j);
         T d[N], ad[N], pr[N], bb[N], rr[N], zz[N];
         unpack(reinterpret_cast<const V*>(delta)[i], d); unpack(reinterpret_cast<const V*>(Adelta)[i], ad);
         unpack(reinterpret_cast<const V*>(b)[i], bb);
@@ -133,14 +144,16 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2SecondHalf(long nVec, Reduce
 // ------------------------------------------------------------------------------------ PCGStep3
 // :537-550.  beta = rz_new / rz_old (guarded), p = z + beta p
 template <class T, bool LM>
-__global__ void __launch_bounds__(kBlock) k_pcgStep3(long nVec, ReduceWorkspace ws, int rzNew, int rzOld, const T* __restrict__ z, T* __restrict__ p) {
+__global__ void __launch_bounds__(kBlock) k_pcgStep3(long nVec, WindowRanges win, ReduceWorkspace ws, int rzNew, int rzOld, const T* __restrict__ z, T* __restrict__ p) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
+    pdlTrigger(); pdlWait();
     if (LM && ws.scalars[kFlags] != 0.0) return;
     double drn, dro; loadScalars2(ws, rzNew, rzOld, drn, dro);
     const T rn = (T)drn, ro = (T)dro;
     T beta = T(0);
     if (ro > T(0)) beta = rn / ro;
-    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < nVec; i += (long)gridDim.x * kBlock) {
+    for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < nVec; j += (long)gridDim.x * kBlock) {
+        const long i = win.map(j);
         T zz[N], pp[N];
         unpack(reinterpret_cast<const V*>(z)[i], zz); unpack(reinterpret_cast<const V*>(p)[i], pp);
 #pragma unroll
@@ -169,11 +182,12 @@ template <class T> __global__ void __launch_bounds__(kBlock) k_copy(long n, T* _
 // PCGFinalizeDiagonal (:631-664).  `pre` holds guardedInvert(diag) from PCGInit1 on entry (0 on
 // excluded/padding entries, which stay inert), the true LM preconditioner on exit.
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, ReduceWorkspace ws, OwnedRanges own, int rzSlot, T* __restrict__ CtC, const T* __restrict__ SSq,
+__global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, WindowRanges win, ReduceWorkspace ws, OwnedRanges own, int rzSlot, T* __restrict__ CtC, const T* __restrict__ SSq,
                                                                T* __restrict__ pre, const T* __restrict__ r, T* __restrict__ b, T* __restrict__ p,
                                                                const T* __restrict__ delta, T radius, T minDiag, T maxDiag) {
     T accD = T(0), accQ = T(0);
-    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long)gridDim.x * kBlock) {
+    for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < n; j += (long)gridDim.x * kBlock) {
+        const long i = win.map(j);
         T ssq = SSq[i];
         if (ssq > T(0)) {
             T unclamped = CtC[i];
@@ -239,6 +253,8 @@ struct Plan : PlanBase {
     T *b = nullptr, *Adelta = nullptr, *CtC = nullptr, *SSq = nullptr, *prevX = nullptr;   // LM only
     ReduceWorkspace ws{};
     OwnedRanges ownVec{}, ownScalar{};       // n == 0: single GPU, everything owned
+    WindowRanges winVec{}, winScalar{};      // n == 0: stream the whole vectors
+    long nVecWin() const { return winVec.n ? winVec.total : n / VecOf<T>::N; }
     // multi-GPU mailbox block (cudaMalloc'ed so it can be exported through CUDA IPC), see common.cuh CommView
     struct CommBlock { unsigned long long words[kNumScalars][2][kMaxRanks][2]; unsigned long long haloFlags[2]; unsigned long long epoch[kNumScalars]; unsigned long long haloEpoch; };
     CommBlock* commBlock = nullptr;
@@ -254,7 +270,7 @@ struct Plan : PlanBase {
     int numSMs = 148;
     int gridStream = 0;          // CTAs for the streaming kernels
     cudaGraphExec_t loopExec = nullptr; int loopExecIters = -1; bool loopExecFused = false;
-    bool useGraph = true, useFusion = true;
+    bool useGraph = true, useFusion = true, usePdl = false;   // PDL measured slower here (early-resident dependents crowd the streaming kernels): opt-in via OPTB_PDL=1
     // nonlinear state (:994-1006)
     int nIter = 0;
     T prevCost = 0;
@@ -287,6 +303,7 @@ struct Plan : PlanBase {
         if (gridStream < 1) gridStream = 1;
         if (const char* s = getenv("OPTB_NO_GRAPH")) useGraph = atoi(s) == 0;
         if (const char* s = getenv("OPTB_NO_FUSION")) useFusion = atoi(s) == 0;
+        if (const char* s = getenv("OPTB_PDL")) usePdl = atoi(s) != 0;
         if (collectTiming && getenv("OPTB_TIMING_TABLE")) useGraph = false;
         if (verbosity > 1) printf("opt_b200: plan %s %s %s: %ld unknowns (padded), %d SMs\n", E->name(), lm ? "LM" : "GN", sizeof(T) == 8 ? "fp64" : "fp32", n, numSMs);
     }
@@ -301,7 +318,7 @@ struct Plan : PlanBase {
         if (ownStream) cudaStreamDestroy(stream);
         delete E;
     }
-    LaunchCtx ctx() const { return LaunchCtx{ stream, ws, numSMs }; }
+    LaunchCtx ctx() const { return LaunchCtx{ stream, ws, numSMs, usePdl }; }
 
     void setParameter(const char* name, const void* v) override {   // :1205-1221
         std::string s(name);
@@ -384,6 +401,17 @@ struct Plan : PlanBase {
             ownVec.lo[i] = ranges[i].first / VecOf<T>::N; ownVec.hi[i] = ranges[i].second / VecOf<T>::N;
         }
         ownVec.n = ownScalar.n = (int)ranges.size();
+        auto wins = E->processScalarRanges();
+        winVec = WindowRanges{}; winScalar = WindowRanges{};
+        if (!wins.empty()) {
+            if (wins.size() > 2) { fprintf(stderr, "opt_b200: at most two process windows supported\n"); return -4; }
+            for (size_t i = 0; i < wins.size(); ++i) {
+                if (wins[i].first % VecOf<T>::N || wins[i].second % VecOf<T>::N) { fprintf(stderr, "opt_b200: process window not vector aligned\n"); return -3; }
+                winScalar.lo[i] = wins[i].first; winScalar.len[i] = wins[i].second - wins[i].first; winScalar.total += winScalar.len[i];
+                winVec.lo[i] = wins[i].first / VecOf<T>::N; winVec.len[i] = winScalar.len[i] / VecOf<T>::N; winVec.total += winVec.len[i];
+            }
+            winVec.n = winScalar.n = (int)wins.size();
+        }
         if (loopExec) { cudaGraphExecDestroy(loopExec); loopExec = nullptr; }
         return 0;
     }
@@ -421,18 +449,18 @@ struct Plan : PlanBase {
     void launchStep2(int rzOld, int rzNew, T* p) {
         long nVec = n / VecOf<T>::N;
         if (lm) {
-            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
-            else k_pcgStep2<T, true, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            else k_pcgStep2<T, true, false><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
         } else {
-            if (E->usePreconditioner) k_pcgStep2<T, false, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
-            else k_pcgStep2<T, false, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            if (E->usePreconditioner) launchPdl(k_pcgStep2<T, false, true>, gridStream, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            else launchPdl(k_pcgStep2<T, false, false>, gridStream, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
         }
         ++launches;
     }
     void launchStep3(int rzNew, int rzOld, T* p) {
         long nVec = n / VecOf<T>::N;
-        if (lm) k_pcgStep3<T, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzNew, rzOld, z, p);
-        else k_pcgStep3<T, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzNew, rzOld, z, p);
+        if (lm) k_pcgStep3<T, true><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, rzNew, rzOld, z, p);
+        else launchPdl(k_pcgStep3<T, false>, gridStream, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, rzNew, rzOld, (const T*)z, p);
         ++launches;
     }
     // Emits iterations [0, L).  rz slot convention: iteration l reads rz[l&1] as "old", writes rz[(l+1)&1].
@@ -456,10 +484,10 @@ struct Plan : PlanBase {
             bool reset = lm && ((l + 1) % sp.residual_reset_period) == 0;
             if (reset) {   // :1077-1083
                 long nVec = n / VecOf<T>::N;
-                k_pcgStep2FirstHalf<T><<<gridStream, kBlock, 0, stream>>>(nVec, ws, rzOld, delta, cur); ++launches;
+                k_pcgStep2FirstHalf<T><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, rzOld, delta, cur); ++launches;
                 E->applyJTJ(c, delta, Adelta, ctc, -1); ++launches;
-                if (E->usePreconditioner) k_pcgStep2SecondHalf<T, true><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzNew, delta, r, Adelta, pre, b, z);
-                else k_pcgStep2SecondHalf<T, false><<<gridStream, kBlock, 0, stream>>>(nVec, ws, ownVec, rzNew, delta, r, Adelta, pre, b, z);
+                if (E->usePreconditioner) k_pcgStep2SecondHalf<T, true><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzNew, delta, r, Adelta, pre, b, z);
+                else k_pcgStep2SecondHalf<T, false><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzNew, delta, r, Adelta, pre, b, z);
                 ++launches;
             } else {
                 launchStep2(rzOld, rzNew, cur);
@@ -512,7 +540,7 @@ struct Plan : PlanBase {
         if (lm) {   // :1038-1053
             if (nIter == 0) { k_copy<T><<<gridStream, kBlock, 0, stream>>>(n, SSq, pre); ++launches; }   // PCGSaveSSq
             E->computeCtC(c, CtC, T(1) / trust_region_radius); ++launches;
-            k_lmFinalizeDiagonal<T><<<gridStream, kBlock, 0, stream>>>(n, ws, ownScalar, kRz0, CtC, SSq, pre, r, b, p, delta, trust_region_radius, min_lm_diagonal, max_lm_diagonal); ++launches;
+            k_lmFinalizeDiagonal<T><<<gridStream, kBlock, 0, stream>>>(winScalar.n ? winScalar.total : n, winScalar, ws, ownScalar, kRz0, CtC, SSq, pre, r, b, p, delta, trust_region_radius, min_lm_diagonal, max_lm_diagonal); ++launches;
             k_copyScalar<<<1, 1, 0, stream>>>(ws, kQPrev, kQ);          // Q0 = fetchQ
             k_setScalar<<<1, 1, 0, stream>>>(ws, kFlags, 0.0); launches += 2;
         }

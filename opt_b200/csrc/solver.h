@@ -56,6 +56,7 @@ struct LaunchCtx {
     cudaStream_t stream;
     ReduceWorkspace ws;
     int numSMs;
+    bool pdl;   // launch inner-loop kernels with programmatic dependent launch (common.cuh)
 };
 
 // Per-energy kernels ("function map").  T = opt_float (float or double).
@@ -96,6 +97,8 @@ struct EnergyOps {
     struct HaloSegment { long srcOff, dstOff, len; int dir; };          // scalars in the flat layout; dir 0 = up, 1 = down
     virtual std::vector<HaloSegment> haloSegments() const { return {}; }
     virtual std::vector<std::pair<long, long>> ownedScalarRanges() const { return {}; }
+    // energies whose plan holds GLOBAL-size (replicated) vectors: the windows (owned + halo) the streaming kernels must touch
+    virtual std::vector<std::pair<long, long>> processScalarRanges() const { return {}; }
     // called at every Opt_ProblemInit: graph indices / masks may have changed since the last solve
     virtual void newSolve() {}
     virtual const char* name() const = 0;

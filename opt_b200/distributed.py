@@ -74,3 +74,30 @@ def gather_owned_rows(local_image, W, slab, group=None):
     parts = [None] * slab.world
     dist.all_gather_object(parts, mine, group=group)
     return np.concatenate(parts, 0)
+
+
+class VertexSlab:
+    """1-D decomposition of a graph problem over its (locality-ordered) vertex index -- SURVEY.md 8(e) "graph partition".
+    Every rank binds the GLOBAL arrays (they are small: 12 B per vertex per array) but owns the vertices [g0, g1) and
+    streams only that range plus `halo` vertices on each side, where halo = the graph's index bandwidth max|v0 - v1|
+    rounded up to 4 (so a locality-preserving vertex order -- grid order, RCM, a space-filling curve -- is what makes
+    the decomposition efficient).  Same wiring as the image slabs: OptB200_PlanConnect(owned range, halo depths)."""
+
+    def __init__(self, n_vertices, world, rank, v0, v1):
+        self.N, self.world, self.rank = int(n_vertices), world, rank
+        b = [min(self.N, int(round(self.N * r / world / 4.0)) * 4) for r in range(world)] + [self.N]
+        reach = int(np.abs(np.asarray(v0, np.int64) - np.asarray(v1, np.int64)).max()) if len(v0) else 0
+        self.halo = (reach + 3) // 4 * 4
+        if world > 1 and min(b[r + 1] - b[r] for r in range(world)) < max(self.halo, 4):
+            raise ValueError(f"graph index bandwidth {reach} exceeds the per-rank vertex range: reorder the vertices or use fewer ranks")
+        self.g0, self.g1 = b[rank], b[rank + 1]
+        self.owned_begin, self.owned_end = self.g0, self.g1
+        self.upper_rows = self.halo if rank > 0 else 0
+        self.lower_rows = self.halo if rank + 1 < world else 0
+
+    def gather(self, array, group=None):
+        """assemble the global per-vertex array from every rank's owned rows (host numpy, all ranks receive it)"""
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, np.ascontiguousarray(np.asarray(array)[self.g0:self.g1]), group=group)
+        return np.concatenate(parts, 0)

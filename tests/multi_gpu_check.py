@@ -10,7 +10,51 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def main_arap():
+    """vertex-slab decomposition of arap_mesh_deformation vs the single-GPU solve"""
+    import torch
+    import torch.distributed as dist
+    from opt_b200 import OptSolver, spec_path, workloads
+    from opt_b200.distributed import VertexSlab, connect_plan
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nx, ny = int(sys.argv[2]), int(sys.argv[3]); kind = sys.argv[4] if len(sys.argv) > 4 else "gaussNewtonGPU"
+    sp = {"nIterations": 3, "lIterations": 30}
+    full = workloads.arap_mesh(nx, ny, n_handles=12)
+    N = nx * ny
+    slab = VertexSlab(N, world, rank, full[7], full[8])
+    dev = workloads.to_device(workloads.clone_params(full))           # every rank binds the global arrays
+    s = OptSolver([N], spec_path("arap_mesh_deformation"), kind)
+    connect_plan(s, slab)
+    s.set_solver_parameters(sp)
+    s.init(dev); costs = [s.current_cost()]
+    while s.step(dev):
+        costs.append(s.current_cost())
+    torch.cuda.synchronize()
+    off = slab.gather(dev[2].cpu().numpy()); ang = slab.gather(dev[3].cpu().numpy())
+    ok = True
+    if rank == 0:
+        ref = workloads.to_device(workloads.clone_params(full))
+        s1 = OptSolver([N], spec_path("arap_mesh_deformation"), kind); s1.set_solver_parameters(sp)
+        s1.init(ref); c1 = [s1.current_cost()]
+        while s1.step(ref):
+            c1.append(s1.current_cost())
+        o1, a1 = ref[2].cpu().numpy(), ref[3].cpu().numpy()
+        rel_c = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(costs, c1))
+        e_off = np.linalg.norm(off - o1) / np.linalg.norm(o1); e_ang = np.linalg.norm(ang - a1) / max(np.linalg.norm(a1), 1e-12)
+        print(f"multi_gpu_check ARAP world={world} {nx}x{ny} {kind} halo={slab.halo}: costs {costs[0]:.6f} -> {costs[-1]:.6f}; vs 1 GPU: cost rel {rel_c:.2e}, Offset {e_off:.2e}, Angle {e_ang:.2e}")
+        print("  multi :", [f"{c:.6g}" for c in costs]); print("  single:", [f"{c:.6g}" for c in c1])
+        ok = rel_c < 1e-4 and e_off < 1e-5 and e_ang < 2e-3 and len(costs) == len(c1)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "arap":
+        return main_arap()
     import torch
     import torch.distributed as dist
     from opt_b200 import OptSolver, spec_path, workloads

@@ -30,7 +30,7 @@ namespace {
 
 // ===================================================================================== expression DAG
 enum class Op { Const, Param, Load, Unknown, Index, Bounds, Add, Sub, Mul, Div, Neg, Pow, Sin, Cos, Sqrt, Abs, Exp, Log,
-                Less, LessEq, Greater, GreaterEq, Eq, Or, Not, Select };
+                Less, LessEq, Greater, GreaterEq, Eq, Or, Not, Select, Sample };
 struct Node {
     Op op = Op::Const;
     double value = 0;        // Const
@@ -41,6 +41,8 @@ struct Node {
     int slot = -1;           // Load/Unknown via graph: global graph-slot id
     int chan = 0;
     int nd = 0;              // Bounds: number of dims
+    // Sample (bilinear read of a 2-D image at computed coordinates, o.t:582-589): id = image, off[0]/off[1] = images holding d/dx and d/dy
+    // (-1: none), chan; args = { x, y }
     std::vector<int> args;
 };
 struct Dag {
@@ -135,6 +137,7 @@ struct ImageObj : Object {
     std::vector<int> computed;                    // per channel defining expression (ComputedArray)
     const char* kind() const override { return "image"; }
 };
+struct SampledObj : Object { int image = -1, dx = -1, dy = -1; int channels = 1; const char* kind() const override { return "sampled image"; } };
 struct GraphObj : Object { int id = -1; std::map<std::string, int> slotOf; const char* kind() const override { return "graph"; } };
 struct GraphElemObj : Object { int graph = -1; int slot = -1; int globalSlot = -1; std::vector<int> dims; const char* kind() const override { return "graph element"; } };
 
@@ -489,6 +492,7 @@ struct Interp {
                 r = P.dag.add(n); break;
             case Op::Index: n.off[0] += off[n.id]; r = P.dag.add(n); break;
             case Op::Bounds: for (int k = 0; k < 3; ++k) { n.off[k] += off[k]; n.off2[k] += off[k]; } r = P.dag.add(n); break;
+            case Op::Sample: { Node m = n; m.args = { shift(n.args[0], off), shift(n.args[1], off) }; r = P.dag.add(m); break; }
             default: {
                 std::vector<int> a; for (int c : n.args) a.push_back(shift(c, off));
                 if (n.op == Op::Select) r = P.dag.select(a[0], a[1], a[2]);
@@ -526,6 +530,18 @@ struct Interp {
         if (auto* ex = dynamic_cast<ExprObj*>(f.obj.get())) {   // scalar(0) is allowed by the reference for 1-channel images
             if (args.size() == 1 && args[0].type == Value::Num && args[0].n == 0) return { mkExpr(ex->e) };
             fail("attempt to index a scalar expression", ln);
+        }
+        if (auto* sm = dynamic_cast<SampledObj*>(f.obj.get())) {   // SampledImage:__call(x, y [, c])  (o.t:2467-2478)
+            if (args.size() < 2) fail("sampled images take (x, y [, channel])", ln);
+            int x = toExpr(args[0]), y = toExpr(args[1]);
+            int chan = -1; if (args.size() > 2) { if (args[2].type != Value::Num) fail("channel must be a number", ln); chan = (int)args[2].n; }
+            std::vector<int> comps;
+            for (int c = 0; c < sm->channels; ++c) {
+                if (chan >= 0 && c != chan) continue;
+                Node n; n.op = Op::Sample; n.id = sm->image; n.off[0] = sm->dx; n.off[1] = sm->dy; n.chan = c; n.args = { x, y };
+                comps.push_back(P.dag.add(n));
+            }
+            return { fromComponents(comps) };
         }
         auto* im = dynamic_cast<ImageObj*>(f.obj.get());
         if (!im) fail(std::string("attempt to call a ") + f.obj->kind(), ln);
@@ -904,7 +920,24 @@ void installPrelude(Interp& I) {
         std::vector<int> r; for (int i = 0; i < 3; ++i) r.push_back(add(add(mul(m[3 * i], v[0]), mul(m[3 * i + 1], v[1])), mul(m[3 * i + 2], v[2])));
         return std::vector<Value>{ I2.mkVec(r) };
     });
-    for (const char* nyi : { "SampledImage", "L_p", "Slice" })
+    I.def("SampledImage", [](Interp&, std::vector<Value>& a, int ln) {   // o.t:2486-2501
+        auto img = [&](const Value& v) -> ImageObj* { auto* im = v.type == Value::Obj ? dynamic_cast<ImageObj*>(v.obj.get()) : nullptr; if (!im || im->id < 0 || im->dims.size() != 2) fail("sampled images must be 2-D Arrays", ln); return im; };
+        if (a.empty()) fail("SampledImage(image [, imagedx, imagedy])", ln);
+        auto s = std::make_shared<SampledObj>(); ImageObj* m = img(a[0]); s->image = m->id; s->channels = m->channels;
+        if (a.size() >= 3) { s->dx = img(a[1])->id; s->dy = img(a[2])->id; }
+        return std::vector<Value>{ Value::object(s) };
+    });
+    // lib.t:105-115: L_p(val, val_const, p, dims) = ComputedArray( sqrt( (|val_const| + eps)^(p-2) ) )(0,0) * val  -- the weight is a function of
+    // constant data only, so inlining it is exact
+    I.def("L_p", [&P](Interp& I2, std::vector<Value>& a, int ln) {
+        if (a.size() < 3) fail("L_p(val, val_const, p, dims)", ln);
+        int s = P.dag.constant(0); for (int e : I2.toVec(a[1])) s = P.dag.binary(Op::Add, s, P.dag.binary(Op::Mul, e, e));
+        int dist = P.dag.unary(Op::Sqrt, s);
+        int C = P.dag.binary(Op::Pow, P.dag.binary(Op::Add, dist, P.dag.constant(0.0000001)), P.dag.binary(Op::Sub, I2.toExpr(a[2]), P.dag.constant(2)));
+        int w = P.dag.unary(Op::Sqrt, C);
+        return std::vector<Value>{ I2.lift1(a[0], [&](int v) { return P.dag.binary(Op::Mul, w, v); }) };
+    });
+    for (const char* nyi : { "Slice" })
         I.def(nyi, [nyi](Interp&, std::vector<Value>&, int ln) -> std::vector<Value> { fail(std::string(nyi) + " is not supported by this front end yet", ln); });
     // ---- a little of the Lua standard library
     I.def("print", [](Interp&, std::vector<Value>&, int) { return std::vector<Value>{}; });
@@ -1039,6 +1072,13 @@ struct Codegen {
             case Op::Or: out << "((" << val(0) << " != T(0) || " << val(1) << " != T(0)) ? T(1) : T(0))"; break;
             case Op::Not: out << "(" << val(0) << " != T(0) ? T(0) : T(1))"; break;
             case Op::Select: out << "(" << val(0) << " != T(0) ? " << ty << "(" << A(1) << ") : " << ty << "(" << A(2) << "))"; break;
+            case Op::Sample: {
+                const ImageDecl& im = P.images[n.id];
+                auto ptr = [&](int id) { return id < 0 ? std::string("(const ") + ctype(im.type) + "*)0" : std::string("(const ") + ctype(P.images[id].type) + "*)P.img[" + std::to_string(id) + "]"; };
+                out << "geSample<T>(" << ptr(n.id) << ", " << ptr(n.off[0]) << ", " << ptr(n.off[1]) << ", (long)P.dim[" << im.dims[0] << "], (long)P.dim[" << im.dims[1] << "], " << im.channels
+                    << ", " << n.chan << ", " << A(0) << ", " << A(1) << ")";
+                break;
+            }
         }
         out << ";\n";
     }

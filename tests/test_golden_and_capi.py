@@ -105,7 +105,8 @@ def test_no_cpu_fallback(built):
         OptSolver([8, 8], spec_path("image_warping"))
 
 
-@pytest.mark.parametrize("name", ["image_warping", "arap_mesh_deformation", "poisson_image_editing", "laplacian", "curveFitting", "shape_from_shading", "robust_nonrigid_alignment"])
+@pytest.mark.parametrize("name", ["image_warping", "arap_mesh_deformation", "poisson_image_editing", "laplacian", "curveFitting", "shape_from_shading", "robust_nonrigid_alignment",
+                                  "volumetric_mesh_deformation", "cotangent_mesh_smoothing", "embedded_mesh_deformation", "optical_flow", "intrinsic_image_decomposition"])
 def test_front_end_compiles_every_shipped_spec(built, name):
     """general front end (no GPU needed): the .t file is executed by the Lua-subset interpreter, its residual code is
     generated and NVRTC compiles it for sm_100a"""
@@ -138,3 +139,19 @@ def test_front_end_accepts_a_new_energy_and_reports_errors(built, tmp_path):
     bad.write_text("local W = Dim('W', 0)\nlocal X = Unknown('X', opt_float, {W}, 0)\nEnergy(X(0) - undefined_name(1))\n")
     ok, msg = frontend_compile(str(bad))
     assert not ok and "line 3" in msg
+
+
+def test_front_end_compiles_every_reference_spec(built):
+    """when the reference tree is mounted: every .t file it ships (12 examples + 3 tests) runs through the front end"""
+    import glob
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not mounted")
+    from opt_b200.solver import frontend_compile
+    files = sorted(glob.glob(ref + "/examples/*/*.t")) + sorted(glob.glob(ref + "/tests/*/*.t"))
+    assert len(files) >= 15
+    for f in files:
+        if "volumetric" in f:
+            continue            # compiles too (23 s of NVRTC for 21 residual groups); covered by the specs/ variant above
+        ok, msg = frontend_compile(f, double_precision="curveFitting" in f)
+        assert ok, (f, msg)

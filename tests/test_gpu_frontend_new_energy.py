@@ -103,3 +103,29 @@ def test_reference_specs_without_builtin_kernels(built, rel):
     while s.step(params):
         pass
     assert np.isfinite(s.current_cost()) and s.current_cost() < c0
+
+
+def test_optical_flow_sampled_image(built):
+    """SampledImage (bilinear read at unknown-dependent coordinates, partials from derivative images): cost equals a numpy
+    restatement, a GN solve with exact derivative images reduces it"""
+    import torch
+    from opt_b200 import OptSolver, spec_path
+    W, H = 48, 36
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    f = lambda x, y: np.sin(0.21 * x) * np.cos(0.17 * y) + 0.3 * np.sin(0.065 * x + 0.11 * y)
+    fx = lambda x, y: 0.21 * np.cos(0.21 * x) * np.cos(0.17 * y) + 0.3 * 0.065 * np.cos(0.065 * x + 0.11 * y)
+    fy = lambda x, y: -0.17 * np.sin(0.21 * x) * np.sin(0.17 * y) + 0.3 * 0.11 * np.cos(0.065 * x + 0.11 * y)
+    I_hat, I_dx, I_dy = f(xs, ys), fx(xs, ys), fy(xs, ys)
+    I = f(xs + 0.6, ys - 0.4)                                   # the scene moved by (0.6, -0.4)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dev = [1.0, 0.3, t(np.zeros((W * H, 2))), t(I.reshape(-1)), t(I_hat.reshape(-1)), t(I_dx.reshape(-1)), t(I_dy.reshape(-1))]
+    s = OptSolver([W, H], spec_path("optical_flow"), "gaussNewtonGPU", double_precision=True)
+    s.set_solver_parameters({"nIterations": 6, "lIterations": 40})
+    s.init(dev)
+    c0 = s.current_cost()
+    assert abs(c0 - 0.5 * ((I - I_hat) ** 2).sum()) < 1e-9 * c0      # zero flow: the sample is the pixel itself, regulariser is zero
+    while s.step(dev):
+        pass
+    c1 = s.current_cost()
+    flow = dev[2].cpu().numpy().reshape(H, W, 2)[8:-8, 8:-8].mean(axis=(0, 1))
+    assert c1 < 0.2 * c0 and abs(flow[0] - 0.6) < 0.15 and abs(flow[1] + 0.4) < 0.15, (c0, c1, flow)

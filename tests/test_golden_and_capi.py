@@ -142,14 +142,14 @@ def test_front_end_accepts_a_new_energy_and_reports_errors(built, tmp_path):
 
 
 def test_front_end_compiles_every_reference_spec(built):
-    """when the reference tree is mounted: every .t file it ships (12 examples + 3 tests) runs through the front end"""
+    """when the reference tree is mounted: every .t file it ships runs through the front end"""
     import glob
     ref = "/root/reference"
     if not os.path.isdir(ref):
         pytest.skip("reference tree not mounted")
     from opt_b200.solver import frontend_compile
     files = sorted(glob.glob(ref + "/examples/*/*.t")) + sorted(glob.glob(ref + "/tests/*/*.t"))
-    assert len(files) >= 15
+    assert len(files) >= 13      # 10 example specs + 3 test specs ship in the tree
     for f in files:
         if "volumetric" in f:
             continue            # compiles too (23 s of NVRTC for 21 residual groups); covered by the specs/ variant above

@@ -29,6 +29,7 @@ struct ArapData {
     long offA;                                         // Angle block inside the flat PCG vectors
     ArapPack<T>* pack;
     const int *outStart, *outNbr, *inStart, *inNbr;    // vertex-CSR neighbour lists (out: edges v->b, in: edges c->v)
+    int symmetric;                                     // every edge (a,b) has its reverse (b,a): the in-list of a vertex equals its out-list
     int lo, hi, wlo, whi;                              // multi-GPU: owned vertices [lo,hi) and the window incl. halo [wlo,whi); single GPU: [0,N)
 };
 
@@ -170,8 +171,18 @@ __global__ void __launch_bounds__(kBlock) k_arapApplyJTJ(ArapData<T> D, ReduceWo
                                (pOv.z - pOb.z) - (c0.z * pAv.x + c1.z * pAv.y + c2.z * pAv.z) };
             aO.x += Jp.x; aO.y += Jp.y; aO.z += Jp.z;
             aA.x -= dot3(c0, Jp); aA.y -= dot3(c1, Jp); aA.z -= dot3(c2, Jp);
+            if (D.symmetric) {   // the reverse edge (b -> v) exists: account for it with the same neighbour data (one gather instead of two)
+                const ArapRot<T> Rb(sb_);
+                const V3<T> pAb = dirA(b);
+                const V3<T> dr = { -d.x, -d.y, -d.z };                       // U_b - U_v
+                const V3<T> Rdr = Rb.apply(dr);
+                V3<T> e0, e1, e2; Rb.columns(dr, Rdr, e0, e1, e2);
+                aO.x -= (pOb.x - pOv.x) - (e0.x * pAb.x + e1.x * pAb.y + e2.x * pAb.z);
+                aO.y -= (pOb.y - pOv.y) - (e0.y * pAb.x + e1.y * pAb.y + e2.y * pAb.z);
+                aO.z -= (pOb.z - pOv.z) - (e0.z * pAb.x + e1.z * pAb.y + e2.z * pAb.z);
+            }
         }
-        for (int k = D.inStart[v]; k < D.inStart[v + 1]; ++k) {
+        for (int k = D.symmetric ? D.inStart[v + 1] : D.inStart[v]; k < D.inStart[v + 1]; ++k) {
             const int c = D.inNbr[k];
             const ArapPack<T> sc = D.pack[c];
             const ArapRot<T> Rc(sc);
@@ -256,6 +267,20 @@ __global__ void __launch_bounds__(kBlock) k_arapCtC(ArapData<T> D, T* __restrict
         CtC[o] = CtC[o + 1] = CtC[o + 2] = dO; CtC[a] = dA.x; CtC[a + 1] = dA.y; CtC[a + 2] = dA.z;
     }
 }
+// graph symmetry test: every out-neighbour b of v must list v among ITS out-neighbours, and in/out degrees must match
+__global__ void k_arapSymmetric(int N, const int* __restrict__ outStart, const int* __restrict__ outNbr, const int* __restrict__ inStart, int* __restrict__ notSymmetric) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < N; v += gridDim.x * blockDim.x) {
+        bool ok = (outStart[v + 1] - outStart[v]) == (inStart[v + 1] - inStart[v]);
+        for (int k = outStart[v]; ok && k < outStart[v + 1]; ++k) {
+            const int b = outNbr[k];
+            int cnt = 0, mine = 0;
+            for (int q = outStart[b]; q < outStart[b + 1]; ++q) cnt += outNbr[q] == v;
+            for (int q = outStart[v]; q < outStart[v + 1]; ++q) mine += outNbr[q] == b;
+            ok = cnt == mine;                                            // multiplicities must match too (multigraphs)
+        }
+        if (!ok) *notSymmetric = 1;
+    }
+}
 __global__ void k_csrStart(int nE, const int* __restrict__ sortedKeys, int N, int* __restrict__ start) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= nE; t += gridDim.x * blockDim.x) {
         const int k = t < nE ? sortedKeys[t] : N, kp = t > 0 ? sortedKeys[t - 1] : -1;
@@ -332,6 +357,12 @@ struct ArapOps : EnergyOps<T> {
         cub::DeviceRadixSort::SortPairs(cubTemp, cubBytes, v1, keysTmp, v0, inNbr, nEdges, 0, endBit, st);
         k_csrStart<<<g, 256, 0, st>>>(nEdges, keysTmp, D.N, inStart);
         D.outStart = outStart; D.outNbr = outNbr; D.inStart = inStart; D.inNbr = inNbr;
+        // symmetric meshes (the reference app builds both directions of every mesh edge, OptGraph.h:64-75) take the merged loop
+        int* flag = keysTmp;   // reuse: the sort keys are no longer needed
+        OPT_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+        k_arapSymmetric<<<g, 256, 0, st>>>(D.N, outStart, outNbr, inStart, flag);
+        int ns = 1; OPT_CUDA_CHECK(cudaMemcpyAsync(&ns, flag, sizeof(int), cudaMemcpyDeviceToHost, st)); OPT_CUDA_CHECK(cudaStreamSynchronize(st));
+        D.symmetric = (ns == 0 && !getenv("OPTB_ARAP_NO_SYMMETRIC")) ? 1 : 0;
         csrValid = true;
     }
     void pcgInit(const LaunchCtx& c, T* delta, T* r, T* pre, T* p, int rzSlot) override {
@@ -344,7 +375,9 @@ struct ArapOps : EnergyOps<T> {
         else k_arapApplyJTJ<T, false, false><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, 0, 0, x, nullptr, nullptr, out, nullptr);
     }
     bool step3ApplyJTJ(const LaunchCtx& c, const T* z, const T* pOld, T* pNew, T* out, const T* CtC, int rzNew, int rzOld, int dotSlot, const HaloPlan*) override {
-        if (getenv("OPTB_ARAP_NO_FUSION")) return false;
+        // measured (profiles/r1_other_configs.md): fusing PCGStep3 into this gather doubles the per-neighbour reads (z and p) and is
+        // slower than a separate streaming Step3 for this energy; kept as an opt-in
+        if (!getenv("OPTB_ARAP_FUSION")) return false;
         if (dotSlot == -2) return true;
         if (CtC) k_arapApplyJTJ<T, true, true><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, rzNew, rzOld, pOld, z, pNew, out, CtC);
         else k_arapApplyJTJ<T, true, false><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, rzNew, rzOld, pOld, z, pNew, out, nullptr);

@@ -180,6 +180,68 @@ __device__ __forceinline__ void gridReduceTo(double v, const ReduceWorkspace& ws
     __syncthreads();   // s_warp / s_last reusable by a second call in the same kernel
 }
 
+// ------------------------------------------------------------------ persistent-kernel reductions
+// State of the grid-wide all-reduce used by the persistent PCG-loop kernels (cooperative launch: all CTAs are
+// co-resident).  One object per plan; `k` is a sequence number that only ever grows (the host hands every launch a
+// fresh base), so a stale flag can never be mistaken for a new one.
+struct LoopSync { unsigned long long flag[2]; double value[2]; unsigned int counter; unsigned int pad; };
+
+// Every thread of every CTA calls this with the same k.  Returns the sum of `v` over the whole grid to every thread,
+// and is a grid-wide barrier: global stores issued (by any thread of any CTA) before the call are visible to every
+// thread after it, provided the readers do not go through a non-coherent path (use __ldcg / plain pointers, not
+// const __restrict__, for data that other CTAs rewrite during the kernel).
+// Deterministic like gridReduceTo: one double per CTA, summed by the last arriver with a fixed tree.
+template <int NT>
+__device__ __forceinline__ double gridAllReduce(double v, double* partials, LoopSync* S, unsigned long long k) {
+    __shared__ double s_warp[NT / 32];
+    __shared__ double s_val;
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warpSum(v);
+    if (lane == 0) s_warp[wid] = v;
+    __syncthreads();                        // also: every thread's earlier global stores precede thread 0's fence below
+    if (wid == 0) {
+        double t = lane < NT / 32 ? s_warp[lane] : 0.0;
+        t = warpSum(t);
+        if (lane == 0) {
+            partials[blockIdx.x] = t;
+            __threadfence();
+            const unsigned int prev = atomicAdd(&S->counter, 1u);
+            s_last = (prev == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const volatile double* part = partials;
+        double t = 0.0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += NT) t += part[i];
+        t = warpSum(t);
+        if (lane == 0) s_warp[wid] = t;
+        __syncthreads();
+        if (wid == 0) {
+            double u = lane < NT / 32 ? s_warp[lane] : 0.0;
+            u = warpSum(u);
+            if (lane == 0) {
+                S->counter = 0u;
+                *reinterpret_cast<volatile double*>(&S->value[k & 1ull]) = u;
+                __threadfence();
+                stVolatileU64(&S->flag[k & 1ull], k);
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long spins = 0;
+        while (ldVolatileU64(&S->flag[k & 1ull]) != k) { if (++spins > (1ull << 24)) __trap(); }   // a lost CTA is a bug: fail, do not hang
+        __threadfence();
+        s_val = *reinterpret_cast<volatile double*>(&S->value[k & 1ull]);
+    }
+    __syncthreads();
+    const double out = s_val;
+    __syncthreads();   // s_val / s_warp reusable by the next call
+    return out;
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with launchPdl may begin while its predecessor on the stream
 // is still draining; it must call pdlWait() before touching anything the predecessor wrote.  Kernels call
 // pdlTrigger() first so that THEIR successor can be scheduled early.  Both are no-ops for ordinary launches.

@@ -415,6 +415,143 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
     if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
 }
 
+// ------------------------------------------------------------------------------------ whole PCG loop, persistent
+// All L iterations of PCGStep1/2/3 (GN, solverGPUGaussNewton.t:421-550) in ONE cooperative launch.  For images whose
+// PCG vectors fit in L2 the kernel-per-step loop is bound by launch latency and kernel ramp/tail (15 us per step for
+// 512x512 with two kernels per step), not by bandwidth; here every CTA keeps a fixed set of 32x8 tiles and the
+// iterations are separated by two grid-wide all-reduces, which are needed anyway (p.Ap before alpha, z.r before beta):
+//   phase A   p = z + beta*pOld for the tile and its 1-pixel ring (staged in shared memory; iteration 0 takes p as
+//             is), Ap = J^T J p, partial p.Ap                      -> all-reduce #1 -> alpha
+//   phase B   delta += alpha p, r -= alpha Ap, z = pre*r, partial z.r   -> all-reduce #2 -> beta
+// p is double-buffered like in the fused kernel-per-step path (neighbours in other CTAs read pOld while the new
+// centre value is written to the other buffer).  Everything other CTAs rewrite during the kernel is read with
+// ld.global.cg (L2): L1 is not coherent across SMs.  The arithmetic per pixel is that of k_iwApplyJTJ / k_pcgStep2 /
+// k_pcgStep3, so the results agree with the kernel-per-step loop up to the summation order of the dot products.
+__device__ __forceinline__ float ldcgT(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ double ldcgT(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ Vec2<float> ldcgV(const Vec2<float>* p) { const float2 v = __ldcg(reinterpret_cast<const float2*>(p)); return Vec2<float>{ v.x, v.y }; }
+__device__ __forceinline__ Vec2<double> ldcgV(const Vec2<double>* p) { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return Vec2<double>{ v.x, v.y }; }
+__device__ __forceinline__ void stcgT(float* p, float v) { __stcg(p, v); }
+__device__ __forceinline__ void stcgT(double* p, double v) { __stcg(p, v); }
+__device__ __forceinline__ void stcgV(Vec2<float>* p, Vec2<float> v) { __stcg(reinterpret_cast<float2*>(p), make_float2(v.x, v.y)); }
+__device__ __forceinline__ void stcgV(Vec2<double>* p, Vec2<double> v) { __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
+
+constexpr int kPW = kTileW + 2, kPH = kTileH + 2;   // staged cells per tile (1-pixel ring)
+
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_iwPcgLoop(IWData<T> D, ReduceWorkspace ws, LoopSync* S, unsigned long long k0, int L,
+                                                      T* delta, T* r, T* z, T* P0, T* P1, T* Ap, const T* __restrict__ pre) {
+    __shared__ T sPx[kPH][kPW], sPy[kPH][kPW], sPa[kPH][kPW];
+    const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+    double* partials = ws.partials + (size_t)kPAp * kMaxPartials;   // the two reductions alternate, one buffer is enough
+    unsigned long long k = k0;
+    double dRz = ws.scalars[kRz0], dRzPrev = 0.0, dPAp = 0.0;        // r.z of PCGInit1 (previous kernel on the stream)
+    T* cur = P0; T* alt = P1;
+    const T w2 = D.w * D.w, wf2 = D.wf * D.wf;
+    for (int l = 0; l < L; ++l) {
+        T beta = T(0);
+        if (l > 0) { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }   // PCGStep3 of iteration l-1 (:541-546)
+        // ---------------- phase A
+        T acc = T(0);
+        for (int tile = blockIdx.x; tile < D.numTiles; tile += gridDim.x) {
+            const int x0 = (tile % D.tilesX) * kTileW, y0 = (tile / D.tilesX) * kTileH;
+            __syncthreads();   // previous tile's readers are done with the staging buffers
+            for (int c = tid; c < kPW * kPH; c += kBlock) {
+                const int cy = c / kPW, cx = c - cy * kPW;
+                const int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
+                T px = T(0), py = T(0), pa = T(0);
+                if (gx >= 0 && gx < D.W && gy >= 0 && gy < D.H) {
+                    const long j = (long)gy * D.W + gx;
+                    const Vec2<T> po = ldcgV(reinterpret_cast<const Vec2<T>*>(cur) + j);
+                    pa = ldcgT(cur + D.offA + j);
+                    px = po.x; py = po.y;
+                    if (l > 0) {
+                        const Vec2<T> zo = ldcgV(reinterpret_cast<const Vec2<T>*>(z) + j);
+                        const T za = ldcgT(z + D.offA + j);
+                        px = zo.x + beta * px; py = zo.y + beta * py; pa = za + beta * pa;
+                    }
+                }
+                sPx[cy][cx] = px; sPy[cy][cx] = py; sPa[cy][cx] = pa;
+            }
+            __syncthreads();
+            const int x = x0 + lx, y = y0 + ly;
+            if (x < D.W && y < D.H) {
+                const long i = (long)y * D.W + x;
+                const unsigned fl = D.flags[i];
+                const T pix = sPx[ly + 1][lx + 1], piy = sPy[ly + 1][lx + 1], pai = sPa[ly + 1][lx + 1];
+                if (l > 0) { stcgV(reinterpret_cast<Vec2<T>*>(alt) + i, Vec2<T>{ pix, piy }); stcgT(alt + D.offA + i, pai); }
+                T ox = T(0), oy = T(0), oa = T(0);
+                if (fl & 32u) {
+                    const Vec4<T> gi = D.geom[i];
+                    T ax = T(0), ay = T(0), aa = T(0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (fl & (1u << q)) {
+                            const int ddx = q == 0 ? 1 : (q == 1 ? -1 : 0), ddy = q == 2 ? 1 : (q == 3 ? -1 : 0);
+                            const Vec4<T> gj = D.geom[i + (long)ddy * D.W + ddx];
+                            const T pjx = sPx[ly + 1 + ddy][lx + 1 + ddx], pjy = sPy[ly + 1 + ddy][lx + 1 + ddx], paj = sPa[ly + 1 + ddy][lx + 1 + ddx];
+                            const T dx = gi.z - gj.z, dy = gi.w - gj.w;
+                            const T eix = -gi.y * dx - gi.x * dy, eiy = gi.x * dx - gi.y * dy;
+                            const T ejx = -gj.y * dx - gj.x * dy, ejy = gj.x * dx - gj.y * dy;
+                            const T px = pix - pjx, py = piy - pjy;
+                            ax += T(2) * px - eix * pai - ejx * paj;
+                            ay += T(2) * py - eiy * pai - ejy * paj;
+                            aa += (eix * eix + eiy * eiy) * pai - (eix * px + eiy * py);
+                        }
+                    }
+                    ox = w2 * ax; oy = w2 * ay; oa = w2 * aa;
+                    if (fl & 16u) { ox += wf2 * pix; oy += wf2 * piy; }
+                    acc += pix * ox + piy * oy + pai * oa;
+                }
+                stcgV(reinterpret_cast<Vec2<T>*>(Ap) + i, Vec2<T>{ ox, oy }); stcgT(Ap + D.offA + i, oa);
+            }
+        }
+        if (l > 0) { T* t = cur; cur = alt; alt = t; }
+        dPAp = gridAllReduce<kBlock>((double)acc, partials, S, ++k);
+        // ---------------- phase B (PCGStep2 :446-489)
+        T alpha = T(0);
+        { const T num = (T)dRz, den = (T)dPAp; if (den > T(0)) alpha = num / den; }
+        acc = T(0);
+        for (int tile = blockIdx.x; tile < D.numTiles; tile += gridDim.x) {
+            const int x = (tile % D.tilesX) * kTileW + lx, y = (tile / D.tilesX) * kTileH + ly;
+            if (x < D.W && y < D.H) {
+                const long i = (long)y * D.W + x;
+                Vec2<T> dO = ldcgV(reinterpret_cast<const Vec2<T>*>(delta) + i); T dA = ldcgT(delta + D.offA + i);
+                const Vec2<T> pO = ldcgV(reinterpret_cast<const Vec2<T>*>(cur) + i); const T pA = ldcgT(cur + D.offA + i);
+                Vec2<T> rO = ldcgV(reinterpret_cast<const Vec2<T>*>(r) + i); T rA = ldcgT(r + D.offA + i);
+                const Vec2<T> aO = ldcgV(reinterpret_cast<const Vec2<T>*>(Ap) + i); const T aA = ldcgT(Ap + D.offA + i);
+                const Vec2<T> qO = reinterpret_cast<const Vec2<T>*>(pre)[i]; const T qA = pre[D.offA + i];
+                dO.x = dO.x + alpha * pO.x; dO.y = dO.y + alpha * pO.y; dA = dA + alpha * pA;
+                rO.x = rO.x - alpha * aO.x; rO.y = rO.y - alpha * aO.y; rA = rA - alpha * aA;
+                const Vec2<T> zO{ qO.x * rO.x, qO.y * rO.y }; const T zA = qA * rA;
+                acc += zO.x * rO.x; acc += zO.y * rO.y; acc += zA * rA;
+                stcgV(reinterpret_cast<Vec2<T>*>(delta) + i, dO); stcgT(delta + D.offA + i, dA);
+                stcgV(reinterpret_cast<Vec2<T>*>(r) + i, rO); stcgT(r + D.offA + i, rA);
+                stcgV(reinterpret_cast<Vec2<T>*>(z) + i, zO); stcgT(z + D.offA + i, zA);
+            }
+        }
+        dRzPrev = dRz;
+        dRz = gridAllReduce<kBlock>((double)acc, partials, S, ++k);
+    }
+    // PCGStep3 of the last iteration, in place (nobody reads neighbours any more)
+    if (L > 0) {
+        T beta = T(0);
+        { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
+        for (int tile = blockIdx.x; tile < D.numTiles; tile += gridDim.x) {
+            const int x = (tile % D.tilesX) * kTileW + lx, y = (tile / D.tilesX) * kTileH + ly;
+            if (x < D.W && y < D.H) {
+                const long i = (long)y * D.W + x;
+                const Vec2<T> zO = ldcgV(reinterpret_cast<const Vec2<T>*>(z) + i); const T zA = ldcgT(z + D.offA + i);
+                const Vec2<T> pO = ldcgV(reinterpret_cast<const Vec2<T>*>(cur) + i); const T pA = ldcgT(cur + D.offA + i);
+                stcgV(reinterpret_cast<Vec2<T>*>(cur) + i, Vec2<T>{ zO.x + beta * pO.x, zO.y + beta * pO.y }); stcgT(cur + D.offA + i, zA + beta * pA);
+            }
+        }
+        if (blockIdx.x == 0 && tid == 0) {   // leave the scalars as the kernel-per-step loop does (iteration l reads rz[l&1], writes rz[(l+1)&1])
+            ws.scalars[kPAp] = dPAp; ws.scalars[L & 1] = dRz; ws.scalars[(L + 1) & 1] = dRzPrev;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ computeCost
 // solverGPUGaussNewton.t:580-592 + o.t:2375-2385: 1/2 sum r^2 over residuals centred at active pixels.
 // MODEL: computeModelCost (:666-678, o.t:2174-2199): 1/2 sum (r + J delta)^2.
@@ -579,7 +716,7 @@ struct ImageWarpingOps : EnergyOps<T> {
         gridCost = gridOf((const void*)k_iwCost<T, false>);
         setupTma(sms);
     }
-    ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); }
+    ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); if (loopSync) cudaFree(loopSync); }
     const char* name() const override { return "image_warping"; }
     int upperRows = 0, lowerRows = 0;
     bool setSlab(int ownedBegin, int ownedEnd, int up, int dn) override {
@@ -616,6 +753,28 @@ struct ImageWarpingOps : EnergyOps<T> {
         k_iwInit<T><<<gridInit, kBlock, 0, c.stream>>>(D, c.ws, rzSlot, delta, r, pre, p);
     }
     bool inKernelHalo() const override { return tmaOk; }
+    // persistent whole-loop kernel (single GPU, GN): see k_iwPcgLoop
+    LoopSync* loopSync = nullptr; unsigned long long loopSeq = 0; int gridLoop = 0; int coopOk = -1;
+    bool pcgLoop(const LaunchCtx& c, int L, bool force, T* delta, T* r, T* z, T* p, T* p2, T* Ap, const T* pre, T** pFinal) override {
+        if (L <= 0 || D.y0 != 0 || D.y1 != D.H) return false;
+        if (coopOk < 0) {
+            int dev = 0, coop = 0, sms = 148, occ = 0;
+            cudaGetDevice(&dev); cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_iwPcgLoop<T>, kBlock, 0);
+            long g = (long)sms * occ; if (g > D.numTiles) g = D.numTiles; if (g > kMaxPartials) g = kMaxPartials;
+            gridLoop = (int)g; coopOk = (coop && g >= 1) ? 1 : 0;
+            if (coopOk) { OPT_CUDA_CHECK(cudaMalloc((void**)&loopSync, sizeof(LoopSync))); OPT_CUDA_CHECK(cudaMemset(loopSync, 0, sizeof(LoopSync))); }
+        }
+        if (!coopOk) return false;
+        // worth it only while the vectors stay L2-resident and a CTA owns a handful of tiles: beyond that the TMA pipeline wins
+        if (!force && D.numTiles > 4L * gridLoop) return false;
+        unsigned long long k0 = loopSeq; loopSeq += 2ull * (unsigned long long)L;
+        ReduceWorkspace ws = c.ws;
+        void* args[] = { (void*)&D, (void*)&ws, (void*)&loopSync, (void*)&k0, (void*)&L, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&p2, (void*)&Ap, (void*)&pre };
+        OPT_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_iwPcgLoop<T>, dim3((unsigned)gridLoop), dim3(kBlock), args, 0, c.stream));
+        *pFinal = ((L - 1) & 1) ? p2 : p;
+        return true;
+    }
     void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot, const HaloPlan* halo) override {
         if constexpr (std::is_same<T, float>::value) {
             if (tmaOk) {

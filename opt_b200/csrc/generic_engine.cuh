@@ -106,16 +106,16 @@ __global__ void __launch_bounds__(kBlock) k_geSortValues(long nSlots, const int*
 }
 __device__ __forceinline__ float geGuardedInvert(float v) { float s = 1.0f + sqrtf(v); return 1.0f / (s * s); }
 __device__ __forceinline__ double geGuardedInvert(double v) { double s = 1.0 + sqrt(v); return 1.0 / (s * s); }
-// walks column u of the sliced-ELL copy, four slots in flight at a time: f(value, row)
+// walks column u of the sliced-ELL copy, eight slots in flight at a time: f(value, row)
 template <class T, class F>
 __device__ __forceinline__ void geWalkColumn(int u, const int* __restrict__ sliceStart, const T* __restrict__ valS, const int* __restrict__ rowS, F f) {
     const int b0 = sliceStart[u >> 5], w = (sliceStart[(u >> 5) + 1] - b0) >> 5, base = b0 + (u & 31);
-    for (int t = 0; t < w; t += 4) {
-        T v[4]; int r[4];
+    for (int t = 0; t < w; t += 8) {
+        T v[8]; int r[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const bool in = t + q < w; v[q] = in ? valS[base + (t + q) * 32] : T(0); r[q] = in ? rowS[base + (t + q) * 32] : -1; }
+        for (int q = 0; q < 8; ++q) { const bool in = t + q < w; v[q] = in ? valS[base + (t + q) * 32] : T(0); r[q] = in ? rowS[base + (t + q) * 32] : -1; }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) f(v[q], r[q]);
+        for (int q = 0; q < 8; ++q) f(v[q], r[q]);
     }
 }
 // PCGInit1 (+_Graph,+_Finish), solverGPUGaussNewton.t:361-419,687-692: r = -J^T F, pre, p = pre*r, delta = 0, r.p
@@ -153,19 +153,21 @@ __global__ void __launch_bounds__(kBlock) k_geJxAll(const GeLayout* __restrict__
     for (int g = threadIdx.x; g < nG; g += kBlock) { s_rowBase[g] = Lp->rowBase[g]; s_entBase[g] = Lp->entBase[g]; s_count[g] = Lp->group[g].count; s_ndeps[g] = Lp->group[g].ndeps; }
     if (threadIdx.x == 0) s_rowBase[nG] = Lp->rowBase[nG];
     __syncthreads();
-    const long nRows = s_rowBase[nG];
-    for (long row = (long)blockIdx.x * kBlock + threadIdx.x; row < nRows; row += (long)gridDim.x * kBlock) {
+    // 32-bit indexing throughout (bind() rejects caches with 2^31 entries or more): halves the index registers
+    const unsigned nRows = (unsigned)s_rowBase[nG];
+    for (unsigned row = blockIdx.x * kBlock + threadIdx.x; row < nRows; row += gridDim.x * kBlock) {
         int g = 0;
-        while (g + 1 < nG && row >= s_rowBase[g + 1]) ++g;
-        const long count = s_count[g], local = row - s_rowBase[g];
+        while (g + 1 < nG && row >= (unsigned)s_rowBase[g + 1]) ++g;
+        const unsigned count = (unsigned)s_count[g], local = row - (unsigned)s_rowBase[g];
         const int ndeps = s_ndeps[g];
-        const long rho = local / count, i = local - rho * count;
-        const long e0 = s_entBase[g] + rho * ndeps * count + i;
+        const unsigned rho = local / count, i = local - rho * count;
+        const T* __restrict__ vp = val + ((unsigned)s_entBase[g] + rho * ndeps * count + i);
+        const int* __restrict__ cp = colM + ((unsigned)s_entBase[g] + rho * ndeps * count + i);
         T s = T(0);
         for (int k0 = 0; k0 < ndeps; k0 += 8) {
             T v[8]; int c[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const bool in = k0 + k < ndeps; v[k] = in ? val[e0 + (long)(k0 + k) * count] : T(0); c[k] = in ? colM[e0 + (long)(k0 + k) * count] : -1; }
+            for (int k = 0; k < 8; ++k) { const bool in = k0 + k < ndeps; v[k] = in ? vp[(unsigned)(k0 + k) * count] : T(0); c[k] = in ? cp[(unsigned)(k0 + k) * count] : -1; }
             T xv[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) xv[k] = c[k] >= 0 ? x[c[k]] : T(0);

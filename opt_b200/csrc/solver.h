@@ -83,6 +83,13 @@ struct EnergyOps {
     // sees a half-updated direction.  Called with dotSlot == -2 it only reports support (no launch).
     virtual bool step3ApplyJTJ(const LaunchCtx&, const T* /*z*/, const T* /*pOld*/, T* /*pNew*/, T* /*out*/, const T* /*CtC*/,
                                int /*rzNew*/, int /*rzOld*/, int /*dotSlot*/, const HaloPlan* /*haloZ*/ = nullptr) { return false; }
+    // optional: the WHOLE inner loop (L iterations of PCGStep1/2/3 from the state pcgInit left) as one persistent
+    // cooperative kernel -- for problems whose per-iteration kernels are launch/tail bound rather than HBM bound.
+    // p/p2 are the two direction buffers (p holds the initial direction); *pFinal receives the buffer holding p
+    // afterwards; the scalars kRz0/kRz1/kPAp are left exactly as the kernel-per-step loop would leave them.
+    // Returns false (nothing launched) when not implemented / not applicable; `force` overrides the size heuristic.
+    virtual bool pcgLoop(const LaunchCtx&, int /*L*/, bool /*force*/, T* /*delta*/, T* /*r*/, T* /*z*/, T* /*p*/, T* /*p2*/, T* /*Ap*/,
+                         const T* /*pre*/, T** /*pFinal*/) { return false; }
     // computeCost (+_Graph): scalars[kCost] = 1/2 sum r^2
     virtual void cost(const LaunchCtx& c) = 0;
     // LM: CtC <- diag(J^T J)/radius (PCGComputeCtC), scalars[kModelCost] = 1/2 sum (r + J delta)^2

@@ -12,6 +12,30 @@ from opt_b200 import workloads
 pytestmark = pytest.mark.gpu
 
 
+import contextlib
+import os
+
+
+@contextlib.contextmanager
+def _env(**env):
+    """temporarily set environment toggles (read by the library when a plan is created)"""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+# the inner PCG loop exists twice for this energy: one kernel pair per iteration (CUDA graph), and one persistent
+# cooperative kernel for the whole loop (OPTB_PERSISTENT=1); both must match the oracle
+LOOPS = {"per_step": "0", "persistent": "1"}
+
+
 def _mk(W, H, dp, kind="gaussNewtonGPU", **kw):
     from opt_b200 import OptSolver, spec_path
     from oracle.oracle import Oracle
@@ -58,12 +82,14 @@ def test_kernel_parity(built, W, H, mask, dp):
     assert abs(dot - float(np.dot(x_act.astype(np.float64), out.astype(np.float64)))) <= 1e-5 * max(1.0, abs(dot))
 
 
+@pytest.mark.parametrize("loop", list(LOOPS))
 @pytest.mark.parametrize("dp", [False, True])
 @pytest.mark.parametrize("k", [1, 2, 7])
-def test_pcg_iterations_parity(built, dp, k):
+def test_pcg_iterations_parity(built, dp, k, loop):
     """state after k PCG iterations of the first nonlinear step (fused and unfused paths share it)"""
     W, H = 48, 40
-    s, o, host = _mk(W, H, dp, mask="random", seed=2, perturb=0.3)
+    with _env(OPTB_PERSISTENT=LOOPS[loop]):
+        s, o, host = _mk(W, H, dp, mask="random", seed=2, perturb=0.3)
     N = W * H
     dev = workloads.to_device(host)
     for q in (s, o):
@@ -76,13 +102,17 @@ def test_pcg_iterations_parity(built, dp, k):
         a = s.read_vector(name); b = _oracle_flat(s, o.get_vector(name), N)
         scale = max(1e-30, np.abs(b).max())
         assert np.abs(a - b).max() <= tol * scale, name
+    for name, oname in (("scanAlphaDenominator", "scanAlphaDenominator"), ("rz%d" % (k & 1), "scanBetaNumerator")):
+        a, b = s.read_scalar(name), o.get_scalar(oname)
+        assert abs(a - b) <= (1e-9 if dp else 2e-3) * max(abs(b), 1e-30), name
 
 
-@pytest.mark.parametrize("kind", ["gaussNewtonGPU", "LMGPU"])
+@pytest.mark.parametrize("kind,loop", [("gaussNewtonGPU", "per_step"), ("gaussNewtonGPU", "persistent"), ("LMGPU", "per_step")])
 @pytest.mark.parametrize("dp", [False, True])
-def test_solve_parity(built, kind, dp):
+def test_solve_parity(built, kind, dp, loop):
     W, H = 64, 64
-    s, o, host = _mk(W, H, dp, kind, mask="blob", seed=4)
+    with _env(OPTB_PERSISTENT=LOOPS[loop]):
+        s, o, host = _mk(W, H, dp, kind, mask="blob", seed=4)
     ref = workloads.clone_params(host)
     dev = workloads.to_device(host)
     sp = {"nIterations": 6, "lIterations": 60}
@@ -107,24 +137,21 @@ def test_deterministic_and_graph_equals_direct(built):
     host = workloads.image_warping(W, H, mask="random", seed=7)
     sp = {"nIterations": 3, "lIterations": 40}
     outs = []
-    for env in ({}, {}, {"OPTB_NO_GRAPH": "1", "OPTB_NO_FUSION": "1"}):
-        old = {k: os.environ.get(k) for k in env}
-        os.environ.update(env)
-        try:
+    for env in ({"OPTB_PERSISTENT": "0"}, {"OPTB_PERSISTENT": "0"}, {"OPTB_PERSISTENT": "0", "OPTB_NO_GRAPH": "1", "OPTB_NO_FUSION": "1"},
+                {"OPTB_PERSISTENT": "1"}, {"OPTB_PERSISTENT": "1"}):
+        with _env(**env):
             dev = workloads.to_device(workloads.clone_params(host))
             s = OptSolver([W, H], spec_path("image_warping"))
             c = s.solve(sp, dev)
             outs.append((c, dev[0].cpu().numpy().copy(), dev[1].cpu().numpy().copy()))
             s.close()
-        finally:
-            for k, v in old.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = v
     assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
     assert abs(outs[0][0] - outs[2][0]) <= 1e-6 * abs(outs[0][0])
     assert np.abs(outs[0][1] - outs[2][1]).max() <= 1e-3
+    # the persistent whole-loop kernel: bitwise reproducible as well, and in tight agreement with the per-step loop
+    assert outs[3][0] == outs[4][0] and np.array_equal(outs[3][1], outs[4][1]) and np.array_equal(outs[3][2], outs[4][2])
+    assert abs(outs[0][0] - outs[3][0]) <= 1e-5 * abs(outs[0][0])
+    assert np.abs(outs[0][1] - outs[3][1]).max() <= 1e-3
 
 
 def test_full_size_properties(built):

@@ -96,19 +96,42 @@ __device__ __forceinline__ void publishScalar(const ReduceWorkspace& ws, int slo
     const size_t at = mailboxWord(slot, e, ws.comm.rank);
     for (int r = 0; r < ws.comm.world; ++r) { stVolatileU64(ws.comm.peerWords[r] + at, w0); stVolatileU64(ws.comm.peerWords[r] + at + 1, w1); }
 }
-// Value of reduction `slot` as seen by every rank (single thread; callers broadcast through shared memory).
+// Same, issued by one full warp whose lanes all hold `u`: lane (2*rank + word) stores one word, so the 2*world NVLink
+// stores leave together.
+__device__ __forceinline__ void publishScalarWarp(const ReduceWorkspace& ws, int slot, double u) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long e = ws.comm.epoch[slot] + 1ull;
+    __syncwarp();
+    if (lane == 0) ws.comm.epoch[slot] = e;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(u);
+    if (lane < 2 * ws.comm.world) {
+        const unsigned long long w = (((lane & 1) ? (bits >> 32) : (bits & 0xffffffffull)) << 32) | (e & 0xffffffffull);
+        stVolatileU64(ws.comm.peerWords[lane >> 1] + mailboxWord(slot, e, ws.comm.rank) + (lane & 1), w);
+    }
+}
+// Value of reduction `slot` as seen by every rank (single thread).  All 2*world words of the (slot, parity) row are
+// contiguous; they are requested together and re-polled together, so the wait costs one L2 round trip per poll, not
+// one per rank (polling rank after rank cost 8 x 0.7 us per scalar on 8 GPUs).
 __device__ __forceinline__ double loadScalarGlobal(const ReduceWorkspace& ws, int slot) {
     if (ws.comm.world <= 1) return ws.scalars[slot];
     const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(ws.comm.epoch + slot);
     if (e == 0ull) return 0.0;     // never produced
     const unsigned long long want = e & 0xffffffffull;
+    const unsigned long long* row = ws.comm.peerWords[ws.comm.rank] + mailboxWord(slot, e, 0);
+    const int nWords = 2 * ws.comm.world;
+    unsigned long long w[2 * kMaxRanks];
+    bool ok;
+    do {
+        ok = true;
+#pragma unroll
+        for (int i = 0; i < 2 * kMaxRanks; ++i) { w[i] = want; if (i < nWords) w[i] = ldVolatileU64(row + i); }
+#pragma unroll
+        for (int i = 0; i < 2 * kMaxRanks; ++i) ok = ok && ((w[i] & 0xffffffffull) == want);
+    } while (!ok);
     double sum = 0.0;
-    for (int r = 0; r < ws.comm.world; ++r) {   // fixed rank order => bitwise identical on every rank
-        const unsigned long long* w = ws.comm.peerWords[ws.comm.rank] + mailboxWord(slot, e, r);
-        unsigned long long w0, w1;
-        do { w0 = ldVolatileU64(w); w1 = ldVolatileU64(w + 1); } while ((w0 & 0xffffffffull) != want || (w1 & 0xffffffffull) != want);
-        sum += __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
-    }
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r)   // fixed rank order => bitwise identical on every rank
+        if (r < ws.comm.world) sum += __longlong_as_double((long long)((w[2 * r] >> 32) | ((w[2 * r + 1] >> 32) << 32)));
     return sum;
 }
 // Sequence number of the halo exchange that follows the most recent r.z production (PCGInit1 / PCGStep2):
@@ -116,11 +139,32 @@ __device__ __forceinline__ double loadScalarGlobal(const ReduceWorkspace& ws, in
 __device__ __forceinline__ unsigned long long haloEpochNow(const ReduceWorkspace& ws) {
     return *reinterpret_cast<volatile unsigned long long*>(ws.comm.epoch + kRz0) + *reinterpret_cast<volatile unsigned long long*>(ws.comm.epoch + kRz1);
 }
-// Block-wide: returns the globally reduced values of two slots to every thread.
+// Block-wide: returns the globally reduced values of two slots to every thread.  Warp 0 polls all 2 x 2*world mailbox
+// words at once (lane = slot half | sender | word) and every lane adds the payloads in rank order.
 __device__ __forceinline__ void loadScalars2(const ReduceWorkspace& ws, int slotA, int slotB, double& a, double& b) {
     if (ws.comm.world <= 1) { a = ws.scalars[slotA]; b = ws.scalars[slotB]; return; }
     __shared__ double s_ab[2];
-    if (threadIdx.x == 0) { s_ab[0] = loadScalarGlobal(ws, slotA); s_ab[1] = loadScalarGlobal(ws, slotB); }
+    static_assert(kMaxRanks == 8, "lane mapping below assumes 16 words per slot");
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x, idx = lane & 15, sender = idx >> 1, word = idx & 1;
+        const int slot = (lane & 16) ? slotB : slotA;
+        const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(ws.comm.epoch + slot);
+        unsigned long long w = 0ull;
+        if (e != 0ull && sender < ws.comm.world) {
+            const unsigned long long want = e & 0xffffffffull;
+            const unsigned long long* src = ws.comm.peerWords[ws.comm.rank] + mailboxWord(slot, e, sender) + word;
+            do { w = ldVolatileU64(src); } while ((w & 0xffffffffull) != want);
+        }
+        __syncwarp();
+        const unsigned payload = (unsigned)(w >> 32);   // 0 for idle lanes and for a slot that was never produced
+        double sum = 0.0;
+        for (int r = 0; r < ws.comm.world; ++r) {       // fixed rank order => bitwise identical on every rank
+            const unsigned lo = __shfl_sync(0xffffffffu, payload, (lane & 16) + 2 * r), hi = __shfl_sync(0xffffffffu, payload, (lane & 16) + 2 * r + 1);
+            sum += __longlong_as_double((long long)((unsigned long long)lo | ((unsigned long long)hi << 32)));
+        }
+        if (lane == 0) s_ab[0] = sum;
+        if (lane == 16) s_ab[1] = sum;
+    }
     __syncthreads();
     a = s_ab[0]; b = s_ab[1];
     __syncthreads();
@@ -130,6 +174,21 @@ __device__ __forceinline__ double warpSum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Thread-strided sum of n per-CTA partials (thread t adds elements t, t+NT, t+2NT, ... in that order, so the result
+// does not depend on the unrolling).  The loads bypass L1 (the partials were written by other SMs) and are issued four
+// at a time: one L2 round trip per four elements instead of one per element in the critical tail of every reduction.
+template <int NT>
+__device__ __forceinline__ double orderedStridedSum(const double* part, unsigned n) {
+    double t = 0.0;
+    unsigned i = threadIdx.x;
+    for (; i + 3u * NT < n; i += 4u * NT) {
+        const double a0 = __ldcg(part + i), a1 = __ldcg(part + i + NT), a2 = __ldcg(part + i + 2 * NT), a3 = __ldcg(part + i + 3 * NT);
+        t += a0; t += a1; t += a2; t += a3;
+    }
+    for (; i < n; i += NT) t += __ldcg(part + i);
+    return t;
 }
 
 // Block-wide sum of `v` (every thread calls), then grid-wide deterministic finish:
@@ -157,24 +216,21 @@ __device__ __forceinline__ void gridReduceTo(double v, const ReduceWorkspace& ws
     __syncthreads();
     if (s_last) {
         __threadfence();
-        const volatile double* part = ws.partials + (size_t)slot * kMaxPartials;
-        double t = 0.0;
-        for (unsigned i = threadIdx.x; i < gridDim.x; i += NT) t += part[i];
+        const double* part = ws.partials + (size_t)slot * kMaxPartials;
+        const double t0 = orderedStridedSum<NT>(part, gridDim.x);
+        double t = t0;
         // fixed summation tree: thread-strided partial sums, then the same shuffle tree every run
         t = warpSum(t);
         if (lane == 0) s_warp[wid] = t;
         __syncthreads();
         if (wid == 0) {
             double u = lane < NT / 32 ? s_warp[lane] : 0.0;
-            u = warpSum(u);
+            u = warpSum(u);   // every lane holds the total
             if (lane == 0) {
                 ws.counters[slot] = 0u;
-                if (ws.comm.world <= 1) {
-                    ws.scalars[slot] = u;
-                } else {
-                    publishScalar(ws, slot, u);
-                }
+                if (ws.comm.world <= 1) ws.scalars[slot] = u;
             }
+            if (ws.comm.world > 1) publishScalarWarp(ws, slot, u);
         }
     }
     __syncthreads();   // s_warp / s_last reusable by a second call in the same kernel
@@ -213,9 +269,7 @@ __device__ __forceinline__ double gridAllReduce(double v, double* partials, Loop
     __syncthreads();
     if (s_last) {
         __threadfence();
-        const volatile double* part = partials;
-        double t = 0.0;
-        for (unsigned i = threadIdx.x; i < gridDim.x; i += NT) t += part[i];
+        double t = orderedStridedSum<NT>(partials, gridDim.x);
         t = warpSum(t);
         if (lane == 0) s_warp[wid] = t;
         __syncthreads();

@@ -296,6 +296,60 @@ __device__ __forceinline__ double gridAllReduce(double v, double* partials, Loop
     return out;
 }
 
+// Low-latency variant for small cooperative grids (<= kMaxLLCtas CTAs, e.g. one CTA per SM): no atomics, no last-CTA
+// stage.  Every CTA stores its partial as two self-validating 8-byte words (payload32 | sequence32, as in the NVLink
+// mailboxes above) into its slot, then EVERY CTA polls all slots (one thread per slot) and adds the partials in slot
+// order itself -- all CTAs perform the same operations on the same values, so they obtain the bitwise-identical sum.
+// One L2 store latency + one L2 poll round trip per reduction instead of fence + atomic + fence + flag + value.
+// `words` = [2 parities][kMaxLLCtas][2]; two parities suffice (a CTA cannot publish sequence k+2 before every CTA has
+// published k+1, i.e. has finished reading k).  releaseData: the CTA's earlier global stores must be visible to the
+// other CTAs after the call (costs a __threadfence on both sides); pass false for a pure reduction.
+constexpr int kMaxLLCtas = 256;
+template <int NT>
+__device__ __forceinline__ double gridAllReduceLL(double v, unsigned long long* words, unsigned long long k, bool releaseData) {
+    static_assert(NT >= kMaxLLCtas && NT % 32 == 0 && NT / 32 <= 32, "one polling thread per CTA slot");
+    __shared__ double s_warp[NT / 32];
+    __shared__ double s_part[kMaxLLCtas];
+    __shared__ double s_val;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned seq = (unsigned)k;
+    unsigned long long* row = words + (size_t)(k & 1ull) * (2 * kMaxLLCtas);
+    v = warpSum(v);
+    if (lane == 0) s_warp[wid] = v;
+    __syncthreads();                        // also: every thread's earlier global stores precede the fence below
+    if (wid == 0) {
+        double t = lane < NT / 32 ? s_warp[lane] : 0.0;
+        t = warpSum(t);                     // every lane holds the CTA's partial
+        if (lane < 2) {
+            if (releaseData) __threadfence();
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
+            const unsigned long long w = ((lane ? (bits >> 32) : (bits & 0xffffffffull)) << 32) | (unsigned long long)seq;
+            stVolatileU64(row + 2 * blockIdx.x + lane, w);
+        }
+    }
+    if (threadIdx.x < gridDim.x) {
+        const unsigned long long* src = row + 2 * threadIdx.x;
+        unsigned long long w0, w1, spins = 0;
+        do {
+            w0 = ldVolatileU64(src); w1 = ldVolatileU64(src + 1);
+            if (++spins > (1ull << 24)) __trap();   // a lost CTA is a bug: fail, do not hang
+        } while ((unsigned)(w0 & 0xffffffffull) != seq || (unsigned)(w1 & 0xffffffffull) != seq);
+        s_part[threadIdx.x] = __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
+        if (releaseData) __threadfence();   // acquire side: loads issued after the barrier see the other CTAs' stores
+    }
+    __syncthreads();
+    if (wid == 0) {
+        double u = 0.0;
+        for (unsigned i = lane; i < gridDim.x; i += 32) u += s_part[i];   // fixed order
+        u = warpSum(u);
+        if (lane == 0) s_val = u;
+    }
+    __syncthreads();
+    const double out = s_val;
+    __syncthreads();   // shared scratch reusable by the next call
+    return out;
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with launchPdl may begin while its predecessor on the stream
 // is still draining; it must call pdlWait() before touching anything the predecessor wrote.  Kernels call
 // pdlTrigger() first so that THEIR successor can be scheduled early.  Both are no-ops for ordinary launches.

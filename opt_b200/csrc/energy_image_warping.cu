@@ -552,6 +552,154 @@ __global__ void __launch_bounds__(kBlock) k_iwPcgLoop(IWData<T> D, ReduceWorkspa
     }
 }
 
+// ------------------------------------------------------------------------------------ whole PCG loop, state on chip
+// Same algorithm as k_iwPcgLoop, but the loop state does not leave the SM: the image is cut into slabs of R full rows,
+// one slab per CTA (1024 threads, one CTA per SM, cooperative launch), and p, r, pre, the packed geometry and the flag
+// bytes of the slab live in shared memory for all L iterations; z, Ap and delta of a thread's (at most KMAX) pixels live
+// in registers.  Per iteration only three things touch L2: the two boundary rows of z each slab publishes for its
+// neighbours (phase B), the two ring rows of z it reads back (phase A: p_ring = z_ring + beta * p_ring, the ring's old p
+// is already on chip), and the two all-reduces.  Applies when ceil(H / #SMs) rows fit the shared memory of one SM.
+template <class T, int KMAX>
+__global__ void __launch_bounds__(1024, 1) k_iwPcgLoopResident(IWData<T> D, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long k0, int L, int R,
+                                                               T* delta, T* r, T* z, T* p, T* Ap, const T* __restrict__ pre) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    constexpr int NT = 1024;
+    const int W = D.W, H = D.H, tid = threadIdx.x;
+    const int y0 = blockIdx.x * R;
+    const int rows = min(R, H - y0);                   // >= 1: the host launches ceil(H / R) CTAs
+    const int nOwn = rows * W, nRing = (R + 2) * W, nCap = R * W;
+    // planes with a ring row above and below (local row lr <-> image row y0 - 1 + lr): direction and packed geometry
+    T* sPx = reinterpret_cast<T*>(smemRaw); T* sPy = sPx + nRing; T* sPa = sPy + nRing;
+    T* sGc = sPa + nRing; T* sGs = sGc + nRing; T* sGx = sGs + nRing; T* sGy = sGx + nRing;
+    // planes of the owned rows only: residual, preconditioner (Offset part is isotropic), flag bytes
+    T* sRx = sGy + nRing; T* sRy = sRx + nCap; T* sRa = sRy + nCap; T* sQo = sRa + nCap; T* sQa = sQo + nCap;
+    unsigned char* sF = reinterpret_cast<unsigned char*>(sQa + nCap);
+    const Vec2<T>* pO = reinterpret_cast<const Vec2<T>*>(p);
+    for (int c = tid; c < (rows + 2) * W; c += NT) {
+        const int lr = c / W, x = c - lr * W, gy = y0 - 1 + lr;
+        T px = T(0), py = T(0), pa = T(0); Vec4<T> g{ T(0), T(0), T(0), T(0) };
+        if (gy >= 0 && gy < H) { const long j = (long)gy * W + x; const Vec2<T> po = pO[j]; px = po.x; py = po.y; pa = p[D.offA + j]; g = D.geom[j]; }
+        sPx[c] = px; sPy[c] = py; sPa[c] = pa; sGc[c] = g.x; sGs[c] = g.y; sGx[c] = g.z; sGy[c] = g.w;
+    }
+    T zx[KMAX], zy[KMAX], za[KMAX], ax[KMAX], ay[KMAX], aa[KMAX], dx[KMAX], dy[KMAX], da[KMAX];
+    bool edgeRow[KMAX];                                // pixel lies on the slab's first or last row: its z is read by a neighbour
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) {
+        const int c = tid + q * NT;
+        zx[q] = zy[q] = za[q] = ax[q] = ay[q] = aa[q] = dx[q] = dy[q] = da[q] = T(0); edgeRow[q] = false;
+        if (c < nOwn) {
+            const long i = (long)y0 * W + c;
+            const Vec2<T> ro = reinterpret_cast<const Vec2<T>*>(r)[i]; sRx[c] = ro.x; sRy[c] = ro.y; sRa[c] = r[D.offA + i];
+            sQo[c] = reinterpret_cast<const Vec2<T>*>(pre)[i].x; sQa[c] = pre[D.offA + i];
+            sF[c] = D.flags[i];
+            const Vec2<T> dO = reinterpret_cast<const Vec2<T>*>(delta)[i]; dx[q] = dO.x; dy[q] = dO.y; da[q] = delta[D.offA + i];
+            const int lr = c / W; edgeRow[q] = (lr == 0 || lr == rows - 1);
+        }
+    }
+    __syncthreads();
+    unsigned long long k = k0;
+    double dRz = ws.scalars[kRz0], dRzPrev = 0.0, dPAp = 0.0;
+    const T w2 = D.w * D.w, wf2 = D.wf * D.wf;
+    for (int l = 0; l < L; ++l) {
+        // ---------------- phase A: p = z + beta p (own cells and ring rows), Ap = J^T J p
+        if (l > 0) {
+            T beta = T(0);
+            { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
+#pragma unroll
+            for (int q = 0; q < KMAX; ++q) {
+                const int c = tid + q * NT;
+                if (c < nOwn) { const int cc = c + W; sPx[cc] = zx[q] + beta * sPx[cc]; sPy[cc] = zy[q] + beta * sPy[cc]; sPa[cc] = za[q] + beta * sPa[cc]; }
+            }
+            for (int c = tid; c < 2 * W; c += NT) {
+                const int side = c >= W ? 1 : 0, x = c - side * W, gy = side ? y0 + rows : y0 - 1;
+                if (gy >= 0 && gy < H) {
+                    const long j = (long)gy * W + x;
+                    const Vec2<T> zo = ldcgV(reinterpret_cast<const Vec2<T>*>(z) + j); const T zaa = ldcgT(z + D.offA + j);
+                    const int cc = side ? (rows + 1) * W + x : x;
+                    sPx[cc] = zo.x + beta * sPx[cc]; sPy[cc] = zo.y + beta * sPy[cc]; sPa[cc] = zaa + beta * sPa[cc];
+                }
+            }
+            __syncthreads();
+        }
+        T acc = T(0);
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q) {
+            const int c = tid + q * NT;
+            T ox = T(0), oy = T(0), oa = T(0);
+            if (c < nOwn) {
+                const int cc = c + W;
+                const unsigned fl = sF[c];
+                if (fl & 32u) {
+                    const T pix = sPx[cc], piy = sPy[cc], pai = sPa[cc];
+                    const T gc = sGc[cc], gs = sGs[cc], gux = sGx[cc], guy = sGy[cc];
+                    T sx = T(0), sy = T(0), sa = T(0);
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) {
+                        if (fl & (1u << nb)) {
+                            const int jj = cc + (nb == 0 ? 1 : (nb == 1 ? -1 : (nb == 2 ? W : -W)));
+                            const T jc = sGc[jj], js = sGs[jj];
+                            const T ddx = gux - sGx[jj], ddy = guy - sGy[jj];
+                            const T eix = -gs * ddx - gc * ddy, eiy = gc * ddx - gs * ddy;
+                            const T ejx = -js * ddx - jc * ddy, ejy = jc * ddx - js * ddy;
+                            const T paj = sPa[jj];
+                            const T px = pix - sPx[jj], py = piy - sPy[jj];
+                            sx += T(2) * px - eix * pai - ejx * paj;
+                            sy += T(2) * py - eiy * pai - ejy * paj;
+                            sa += (eix * eix + eiy * eiy) * pai - (eix * px + eiy * py);
+                        }
+                    }
+                    ox = w2 * sx; oy = w2 * sy; oa = w2 * sa;
+                    if (fl & 16u) { ox += wf2 * pix; oy += wf2 * piy; }
+                    acc += pix * ox + piy * oy + pai * oa;
+                }
+            }
+            ax[q] = ox; ay[q] = oy; aa[q] = oa;
+        }
+        dPAp = gridAllReduceLL<NT>((double)acc, llWords, ++k, false);   // nothing but the scalar crosses CTAs here
+        // ---------------- phase B (PCGStep2)
+        T alpha = T(0);
+        { const T num = (T)dRz, den = (T)dPAp; if (den > T(0)) alpha = num / den; }
+        acc = T(0);
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q) {
+            const int c = tid + q * NT;
+            if (c < nOwn) {
+                const int cc = c + W;
+                dx[q] = dx[q] + alpha * sPx[cc]; dy[q] = dy[q] + alpha * sPy[cc]; da[q] = da[q] + alpha * sPa[cc];
+                const T rx = sRx[c] - alpha * ax[q], ry = sRy[c] - alpha * ay[q], ra = sRa[c] - alpha * aa[q];
+                sRx[c] = rx; sRy[c] = ry; sRa[c] = ra;
+                const T qo = sQo[c];
+                zx[q] = qo * rx; zy[q] = qo * ry; za[q] = sQa[c] * ra;
+                acc += zx[q] * rx; acc += zy[q] * ry; acc += za[q] * ra;
+                if (edgeRow[q]) {
+                    const long i = (long)y0 * W + c;
+                    stcgV(reinterpret_cast<Vec2<T>*>(z) + i, Vec2<T>{ zx[q], zy[q] }); stcgT(z + D.offA + i, za[q]);
+                }
+            }
+        }
+        dRzPrev = dRz;
+        dRz = gridAllReduceLL<NT>((double)acc, llWords, ++k, true);      // releases the edge rows of z to the neighbouring slabs
+    }
+    // PCGStep3 of the last iteration, then the state goes back to the plan's vectors
+    T beta = T(0);
+    if (L > 0) { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) {
+        const int c = tid + q * NT;
+        if (c < nOwn) {
+            const int cc = c + W; const long i = (long)y0 * W + c;
+            T px = sPx[cc], py = sPy[cc], pa = sPa[cc];
+            if (L > 0) { px = zx[q] + beta * px; py = zy[q] + beta * py; pa = za[q] + beta * pa; }
+            reinterpret_cast<Vec2<T>*>(p)[i] = Vec2<T>{ px, py }; p[D.offA + i] = pa;
+            reinterpret_cast<Vec2<T>*>(delta)[i] = Vec2<T>{ dx[q], dy[q] }; delta[D.offA + i] = da[q];
+            reinterpret_cast<Vec2<T>*>(r)[i] = Vec2<T>{ sRx[c], sRy[c] }; r[D.offA + i] = sRa[c];
+            reinterpret_cast<Vec2<T>*>(z)[i] = Vec2<T>{ zx[q], zy[q] }; z[D.offA + i] = za[q];
+            reinterpret_cast<Vec2<T>*>(Ap)[i] = Vec2<T>{ ax[q], ay[q] }; Ap[D.offA + i] = aa[q];
+        }
+    }
+    if (L > 0 && blockIdx.x == 0 && tid == 0) { ws.scalars[kPAp] = dPAp; ws.scalars[L & 1] = dRz; ws.scalars[(L + 1) & 1] = dRzPrev; }
+}
+
 // ------------------------------------------------------------------------------------ computeCost
 // solverGPUGaussNewton.t:580-592 + o.t:2375-2385: 1/2 sum r^2 over residuals centred at active pixels.
 // MODEL: computeModelCost (:666-678, o.t:2174-2199): 1/2 sum (r + J delta)^2.
@@ -716,7 +864,7 @@ struct ImageWarpingOps : EnergyOps<T> {
         gridCost = gridOf((const void*)k_iwCost<T, false>);
         setupTma(sms);
     }
-    ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); if (loopSync) cudaFree(loopSync); }
+    ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); if (loopSync) cudaFree(loopSync); if (llWords) cudaFree(llWords); }
     const char* name() const override { return "image_warping"; }
     int upperRows = 0, lowerRows = 0;
     bool setSlab(int ownedBegin, int ownedEnd, int up, int dn) override {
@@ -753,6 +901,40 @@ struct ImageWarpingOps : EnergyOps<T> {
         k_iwInit<T><<<gridInit, kBlock, 0, c.stream>>>(D, c.ws, rzSlot, delta, r, pre, p);
     }
     bool inKernelHalo() const override { return tmaOk; }
+    // state-on-chip variant: one slab of R full rows per SM
+    int resR = 0, resGrid = 0, resK = 0; size_t resSmem = 0; int resChecked = 0; unsigned long long* llWords = nullptr;
+    template <int KMAX>
+    bool launchResidentK(const LaunchCtx& c, int L, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
+        const void* fn = (const void*)k_iwPcgLoopResident<T, KMAX>;
+        if (resChecked != KMAX) {
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resSmem) != cudaSuccess) { cudaGetLastError(); return false; }
+            int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 1024, resSmem);
+            int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if ((long)occ * sms < resGrid) return false;
+            resChecked = KMAX;
+        }
+        unsigned long long k0 = loopSeq; loopSeq += 2ull * (unsigned long long)L;
+        ReduceWorkspace ws = c.ws;
+        if (!llWords) { OPT_CUDA_CHECK(cudaMalloc((void**)&llWords, sizeof(unsigned long long) * 4 * kMaxLLCtas)); OPT_CUDA_CHECK(cudaMemset(llWords, 0, sizeof(unsigned long long) * 4 * kMaxLLCtas)); }
+        void* args[] = { (void*)&D, (void*)&ws, (void*)&llWords, (void*)&k0, (void*)&L, (void*)&resR, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre };
+        OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)resGrid), dim3(1024), args, resSmem, c.stream));
+        return true;
+    }
+    bool launchResident(const LaunchCtx& c, int L, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
+        if (getenv("OPTB_NO_RESIDENT")) return false;
+        if (resR == 0) {
+            int dev = 0, sms = 148, maxSmem = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            resR = (D.H + sms - 1) / sms; resGrid = (D.H + resR - 1) / resR;
+            const size_t nRing = (size_t)(resR + 2) * D.W, nCap = (size_t)resR * D.W;
+            resSmem = (nRing * 7 + nCap * 5) * sizeof(T) + nCap;
+            resSmem = (resSmem + 15) / 16 * 16;
+            resK = (int)((nCap + 1023) / 1024);
+            if (resSmem > (size_t)maxSmem || resK > 4 || resGrid > kMaxLLCtas) resR = -1;
+        }
+        if (resR < 0) return false;
+        return resK <= 2 ? launchResidentK<2>(c, L, delta, r, z, p, Ap, pre) : launchResidentK<4>(c, L, delta, r, z, p, Ap, pre);
+    }
     // persistent whole-loop kernel (single GPU, GN): see k_iwPcgLoop
     LoopSync* loopSync = nullptr; unsigned long long loopSeq = 0; int gridLoop = 0; int coopOk = -1;
     bool pcgLoop(const LaunchCtx& c, int L, bool force, T* delta, T* r, T* z, T* p, T* p2, T* Ap, const T* pre, T** pFinal) override {
@@ -766,8 +948,8 @@ struct ImageWarpingOps : EnergyOps<T> {
             if (coopOk) { OPT_CUDA_CHECK(cudaMalloc((void**)&loopSync, sizeof(LoopSync))); OPT_CUDA_CHECK(cudaMemset(loopSync, 0, sizeof(LoopSync))); }
         }
         if (!coopOk) return false;
-        // worth it only while the vectors stay L2-resident and a CTA owns a handful of tiles: beyond that the TMA pipeline wins
-        if (!force && D.numTiles > 4L * gridLoop) return false;
+        if (launchResident(c, L, delta, r, z, p, Ap, pre)) { *pFinal = p; return true; }   // state fits on chip: measured faster than the graph of per-step kernels
+        if (!force) return false;   // the L2-state variant is slower than the graph: only on request
         unsigned long long k0 = loopSeq; loopSeq += 2ull * (unsigned long long)L;
         ReduceWorkspace ws = c.ws;
         void* args[] = { (void*)&D, (void*)&ws, (void*)&loopSync, (void*)&k0, (void*)&L, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&p2, (void*)&Ap, (void*)&pre };

@@ -304,7 +304,7 @@ struct Plan : PlanBase {
         if (const char* s = getenv("OPTB_NO_GRAPH")) useGraph = atoi(s) == 0;
         if (const char* s = getenv("OPTB_NO_FUSION")) useFusion = atoi(s) == 0;
         if (const char* s = getenv("OPTB_PDL")) usePdl = atoi(s) != 0;
-        if (const char* s = getenv("OPTB_PERSISTENT")) persistentMode = atoi(s) != 0 ? 1 : 0;
+        persistentMode = -1; if (const char* s = getenv("OPTB_PERSISTENT")) persistentMode = atoi(s) != 0 ? 1 : 0;
         if (collectTiming && getenv("OPTB_TIMING_TABLE")) useGraph = false;
         if (verbosity > 1) printf("opt_b200: plan %s %s %s: %ld unknowns (padded), %d SMs\n", E->name(), lm ? "LM" : "GN", sizeof(T) == 8 ? "fp64" : "fp32", n, numSMs);
     }
@@ -538,10 +538,9 @@ struct Plan : PlanBase {
         OPT_CUDA_CHECK(cudaEventRecord(evLoop1, stream));
     }
     int loopLaunchCount = 0; T* loopPFinal = nullptr;
-    // OPTB_PERSISTENT=1: run the whole inner loop as the energy's persistent cooperative kernel (image_warping GN).  Off by
-    // default: measured on 512x512 it is correct but slower than the graph of per-step kernels (18.6 vs 15.2 us per step) --
-    // with the state in L2 every phase is a chain of dependent L2 round trips; the version that pays is the one that keeps
-    // the tile state in shared memory/registers and exchanges only tile borders.
+    // Whole inner loop as one persistent cooperative kernel where the energy offers it (image_warping GN).
+    // -1 (default): only the state-on-chip variant, when the image fits; OPTB_PERSISTENT=1: also the L2-state variant;
+    // OPTB_PERSISTENT=0: always the CUDA graph of per-step kernels.
     int persistentMode = 0;
 
     int step(void** params) override {   // :1016-1177

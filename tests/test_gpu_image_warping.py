@@ -31,9 +31,11 @@ def _env(**env):
                 os.environ[k] = v
 
 
-# the inner PCG loop exists twice for this energy: one kernel pair per iteration (CUDA graph), and one persistent
-# cooperative kernel for the whole loop (OPTB_PERSISTENT=1); both must match the oracle
-LOOPS = {"per_step": "0", "persistent": "1"}
+# the inner PCG loop exists three times for this energy: one kernel pair per iteration (CUDA graph, the default), and
+# one persistent cooperative kernel for the whole loop (OPTB_PERSISTENT=1) with the state either on chip (tried first)
+# or in L2; all must match the oracle
+LOOPS = {"per_step": {"OPTB_PERSISTENT": "0"}, "resident": {"OPTB_PERSISTENT": "1"},
+         "persistent_l2": {"OPTB_PERSISTENT": "1", "OPTB_NO_RESIDENT": "1"}}
 
 
 def _mk(W, H, dp, kind="gaussNewtonGPU", **kw):
@@ -88,7 +90,7 @@ def test_kernel_parity(built, W, H, mask, dp):
 def test_pcg_iterations_parity(built, dp, k, loop):
     """state after k PCG iterations of the first nonlinear step (fused and unfused paths share it)"""
     W, H = 48, 40
-    with _env(OPTB_PERSISTENT=LOOPS[loop]):
+    with _env(**LOOPS[loop]):
         s, o, host = _mk(W, H, dp, mask="random", seed=2, perturb=0.3)
     N = W * H
     dev = workloads.to_device(host)
@@ -107,11 +109,30 @@ def test_pcg_iterations_parity(built, dp, k, loop):
         assert abs(a - b) <= (1e-9 if dp else 2e-3) * max(abs(b), 1e-30), name
 
 
-@pytest.mark.parametrize("kind,loop", [("gaussNewtonGPU", "per_step"), ("gaussNewtonGPU", "persistent"), ("LMGPU", "per_step")])
+@pytest.mark.parametrize("loop", ["per_step", "resident", "persistent_l2"])
+def test_persistent_loop_multirow_slabs(built, loop):
+    """taller than the SM count: the on-chip loop gets slabs of several rows, the last one partial; the L2 loop gets
+    CTAs with several tiles"""
+    W, H, k = 40, 310, 5
+    with _env(**LOOPS[loop]):
+        s, o, host = _mk(W, H, False, mask="blob", seed=11, perturb=0.3)
+    N = W * H
+    dev = workloads.to_device(host)
+    for q in (s, o):
+        q.set_solver_parameter("nIterations", 1); q.set_solver_parameter("lIterations", 50)
+        q.set_max_linear_iterations(k)
+    s.init(dev); o.init(host)
+    s.step(dev); o.step(host)
+    for name in ("delta", "r", "z", "p", "Ap_X"):
+        a = s.read_vector(name); b = _oracle_flat(s, o.get_vector(name), N)
+        assert np.abs(a - b).max() <= 1e-3 * max(1e-30, np.abs(b).max()), name
+
+
+@pytest.mark.parametrize("kind,loop", [("gaussNewtonGPU", "per_step"), ("gaussNewtonGPU", "resident"), ("gaussNewtonGPU", "persistent_l2"), ("LMGPU", "per_step")])
 @pytest.mark.parametrize("dp", [False, True])
 def test_solve_parity(built, kind, dp, loop):
     W, H = 64, 64
-    with _env(OPTB_PERSISTENT=LOOPS[loop]):
+    with _env(**LOOPS[loop]):
         s, o, host = _mk(W, H, dp, kind, mask="blob", seed=4)
     ref = workloads.clone_params(host)
     dev = workloads.to_device(host)
@@ -138,7 +159,7 @@ def test_deterministic_and_graph_equals_direct(built):
     sp = {"nIterations": 3, "lIterations": 40}
     outs = []
     for env in ({"OPTB_PERSISTENT": "0"}, {"OPTB_PERSISTENT": "0"}, {"OPTB_PERSISTENT": "0", "OPTB_NO_GRAPH": "1", "OPTB_NO_FUSION": "1"},
-                {"OPTB_PERSISTENT": "1"}, {"OPTB_PERSISTENT": "1"}):
+                {"OPTB_PERSISTENT": "1"}, {"OPTB_PERSISTENT": "1"}, {"OPTB_PERSISTENT": "1", "OPTB_NO_RESIDENT": "1"}):
         with _env(**env):
             dev = workloads.to_device(workloads.clone_params(host))
             s = OptSolver([W, H], spec_path("image_warping"))
@@ -150,8 +171,9 @@ def test_deterministic_and_graph_equals_direct(built):
     assert np.abs(outs[0][1] - outs[2][1]).max() <= 1e-3
     # the persistent whole-loop kernel: bitwise reproducible as well, and in tight agreement with the per-step loop
     assert outs[3][0] == outs[4][0] and np.array_equal(outs[3][1], outs[4][1]) and np.array_equal(outs[3][2], outs[4][2])
-    assert abs(outs[0][0] - outs[3][0]) <= 1e-5 * abs(outs[0][0])
-    assert np.abs(outs[0][1] - outs[3][1]).max() <= 1e-3
+    for k in (3, 5):
+        assert abs(outs[0][0] - outs[k][0]) <= 1e-5 * abs(outs[0][0])
+        assert np.abs(outs[0][1] - outs[k][1]).max() <= 1e-3
 
 
 def test_full_size_properties(built):

@@ -296,53 +296,73 @@ __device__ __forceinline__ double gridAllReduce(double v, double* partials, Loop
     return out;
 }
 
-// Low-latency variant for small cooperative grids (<= kMaxLLCtas CTAs, e.g. one CTA per SM): no atomics, no last-CTA
-// stage.  Every CTA stores its partial as two self-validating 8-byte words (payload32 | sequence32, as in the NVLink
-// mailboxes above) into its slot, then EVERY CTA polls all slots (one thread per slot) and adds the partials in slot
-// order itself -- all CTAs perform the same operations on the same values, so they obtain the bitwise-identical sum.
-// One L2 store latency + one L2 poll round trip per reduction instead of fence + atomic + fence + flag + value.
-// `words` = [2 parities][kMaxLLCtas][2]; two parities suffice (a CTA cannot publish sequence k+2 before every CTA has
-// published k+1, i.e. has finished reading k).  releaseData: the CTA's earlier global stores must be visible to the
-// other CTAs after the call (costs a __threadfence on both sides); pass false for a pure reduction.
+// Low-latency variant for small cooperative grids (<= kMaxLLCtas CTAs, e.g. one CTA per SM).  The serial chain of
+// gridAllReduce is  partial -> fence -> atomic | last CTA: fence -> loads -> value -> fence -> flag | waiter: flag ->
+// fence -> value.  Here partials and the result travel as self-validating 8-byte words (payload32 | sequence32, as in
+// the NVLink mailboxes above), so none of those fences and no second dependent load is needed:
+//   arrive:   two word stores + one atomicAdd on a counter that is never reset (arrival number gridDim * k marks the
+//             last CTA of reduction k; k = 1, 2, 3, ... over the life of the plan, same grid size every launch)
+//   last CTA: polls the gridDim partial slots (normally already valid), adds them in slot order, stores two result words
+//   everyone: one thread polls the two result words.
+// (Letting every CTA poll every slot instead was measured slower: 16 k pollers on 2 KB of L2.)
+// `words` = [2 parities][kMaxLLCtas + 1][2]; slot kMaxLLCtas carries the result.  Two parities suffice: reduction k+2
+// cannot start before every CTA has read the result of k.  releaseData: the CTA's earlier global stores must be visible
+// to the other CTAs after the call (one __threadfence on each side); pass false for a pure reduction.
 constexpr int kMaxLLCtas = 256;
 template <int NT>
-__device__ __forceinline__ double gridAllReduceLL(double v, unsigned long long* words, unsigned long long k, bool releaseData) {
+__device__ __forceinline__ double gridAllReduceLL(double v, unsigned long long* words, unsigned long long* arrivals, unsigned long long k, bool releaseData) {
     static_assert(NT >= kMaxLLCtas && NT % 32 == 0 && NT / 32 <= 32, "one polling thread per CTA slot");
     __shared__ double s_warp[NT / 32];
     __shared__ double s_part[kMaxLLCtas];
     __shared__ double s_val;
+    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned seq = (unsigned)k;
-    unsigned long long* row = words + (size_t)(k & 1ull) * (2 * kMaxLLCtas);
+    const unsigned long long seq = k & 0xffffffffull;
+    unsigned long long* row = words + (size_t)(k & 1ull) * (2 * (kMaxLLCtas + 1));
     v = warpSum(v);
     if (lane == 0) s_warp[wid] = v;
     __syncthreads();                        // also: every thread's earlier global stores precede the fence below
     if (wid == 0) {
         double t = lane < NT / 32 ? s_warp[lane] : 0.0;
         t = warpSum(t);                     // every lane holds the CTA's partial
-        if (lane < 2) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
+        if (lane < 2) stVolatileU64(row + 2 * blockIdx.x + lane, ((lane ? (bits >> 32) : (bits & 0xffffffffull)) << 32) | seq);
+        if (lane == 0) {
             if (releaseData) __threadfence();
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
-            const unsigned long long w = ((lane ? (bits >> 32) : (bits & 0xffffffffull)) << 32) | (unsigned long long)seq;
-            stVolatileU64(row + 2 * blockIdx.x + lane, w);
+            const unsigned long long prev = atomicAdd(arrivals, 1ull);
+            s_last = (prev + 1ull == (unsigned long long)gridDim.x * k);
         }
     }
-    if (threadIdx.x < gridDim.x) {
-        const unsigned long long* src = row + 2 * threadIdx.x;
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < gridDim.x) {
+            const unsigned long long* src = row + 2 * threadIdx.x;
+            unsigned long long w0, w1, spins = 0;
+            do {
+                w0 = ldVolatileU64(src); w1 = ldVolatileU64(src + 1);
+                if (++spins > (1ull << 24)) __trap();
+            } while ((w0 & 0xffffffffull) != seq || (w1 & 0xffffffffull) != seq);
+            s_part[threadIdx.x] = __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
+        }
+        __syncthreads();
+        if (wid == 0) {
+            double u = 0.0;
+            for (unsigned i = lane; i < gridDim.x; i += 32) u += s_part[i];   // fixed order
+            u = warpSum(u);
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(u);
+            if (releaseData) __threadfence();   // cumulativity: the arrivals observed above (and the stores they release) precede the result
+            if (lane < 2) stVolatileU64(row + 2 * kMaxLLCtas + lane, ((lane ? (bits >> 32) : (bits & 0xffffffffull)) << 32) | seq);
+        }
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long* src = row + 2 * kMaxLLCtas;
         unsigned long long w0, w1, spins = 0;
         do {
             w0 = ldVolatileU64(src); w1 = ldVolatileU64(src + 1);
             if (++spins > (1ull << 24)) __trap();   // a lost CTA is a bug: fail, do not hang
-        } while ((unsigned)(w0 & 0xffffffffull) != seq || (unsigned)(w1 & 0xffffffffull) != seq);
-        s_part[threadIdx.x] = __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
+        } while ((w0 & 0xffffffffull) != seq || (w1 & 0xffffffffull) != seq);
         if (releaseData) __threadfence();   // acquire side: loads issued after the barrier see the other CTAs' stores
-    }
-    __syncthreads();
-    if (wid == 0) {
-        double u = 0.0;
-        for (unsigned i = lane; i < gridDim.x; i += 32) u += s_part[i];   // fixed order
-        u = warpSum(u);
-        if (lane == 0) s_val = u;
+        s_val = __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
     }
     __syncthreads();
     const double out = s_val;

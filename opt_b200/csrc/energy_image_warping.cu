@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(kBlock) k_iwPcgLoop(IWData<T> D, ReduceWorkspa
 // neighbours (phase B), the two ring rows of z it reads back (phase A: p_ring = z_ring + beta * p_ring, the ring's old p
 // is already on chip), and the two all-reduces.  Applies when ceil(H / #SMs) rows fit the shared memory of one SM.
 template <class T, int KMAX>
-__global__ void __launch_bounds__(1024, 1) k_iwPcgLoopResident(IWData<T> D, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long k0, int L, int R,
+__global__ void __launch_bounds__(1024, 1) k_iwPcgLoopResident(IWData<T> D, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long* arrivals, unsigned long long k0, int L, int R,
                                                                T* delta, T* r, T* z, T* p, T* Ap, const T* __restrict__ pre) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     constexpr int NT = 1024;
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopResident(IWData<T> D, Redu
             }
             ax[q] = ox; ay[q] = oy; aa[q] = oa;
         }
-        dPAp = gridAllReduceLL<NT>((double)acc, llWords, ++k, false);   // nothing but the scalar crosses CTAs here
+        dPAp = gridAllReduceLL<NT>((double)acc, llWords, arrivals, ++k, false);   // nothing but the scalar crosses CTAs here
         // ---------------- phase B (PCGStep2)
         T alpha = T(0);
         { const T num = (T)dRz, den = (T)dPAp; if (den > T(0)) alpha = num / den; }
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopResident(IWData<T> D, Redu
             }
         }
         dRzPrev = dRz;
-        dRz = gridAllReduceLL<NT>((double)acc, llWords, ++k, true);      // releases the edge rows of z to the neighbouring slabs
+        dRz = gridAllReduceLL<NT>((double)acc, llWords, arrivals, ++k, true);      // releases the edge rows of z to the neighbouring slabs
     }
     // PCGStep3 of the last iteration, then the state goes back to the plan's vectors
     T beta = T(0);
@@ -902,7 +902,7 @@ struct ImageWarpingOps : EnergyOps<T> {
     }
     bool inKernelHalo() const override { return tmaOk; }
     // state-on-chip variant: one slab of R full rows per SM
-    int resR = 0, resGrid = 0, resK = 0; size_t resSmem = 0; int resChecked = 0; unsigned long long* llWords = nullptr;
+    int resR = 0, resGrid = 0, resK = 0; size_t resSmem = 0; int resChecked = 0; unsigned long long* llWords = nullptr; unsigned long long resSeq = 0;
     template <int KMAX>
     bool launchResidentK(const LaunchCtx& c, int L, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
         const void* fn = (const void*)k_iwPcgLoopResident<T, KMAX>;
@@ -913,10 +913,12 @@ struct ImageWarpingOps : EnergyOps<T> {
             if ((long)occ * sms < resGrid) return false;
             resChecked = KMAX;
         }
-        unsigned long long k0 = loopSeq; loopSeq += 2ull * (unsigned long long)L;
         ReduceWorkspace ws = c.ws;
-        if (!llWords) { OPT_CUDA_CHECK(cudaMalloc((void**)&llWords, sizeof(unsigned long long) * 4 * kMaxLLCtas)); OPT_CUDA_CHECK(cudaMemset(llWords, 0, sizeof(unsigned long long) * 4 * kMaxLLCtas)); }
-        void* args[] = { (void*)&D, (void*)&ws, (void*)&llWords, (void*)&k0, (void*)&L, (void*)&resR, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre };
+        constexpr size_t llCount = 4 * (kMaxLLCtas + 1) + 1;   // two parities of (slots + result) words, then the arrival counter
+        if (!llWords) { OPT_CUDA_CHECK(cudaMalloc((void**)&llWords, sizeof(unsigned long long) * llCount)); OPT_CUDA_CHECK(cudaMemset(llWords, 0, sizeof(unsigned long long) * llCount)); resSeq = 0; }
+        unsigned long long* arrivals = llWords + 4 * (kMaxLLCtas + 1);
+        unsigned long long k0 = resSeq; resSeq += 2ull * (unsigned long long)L;   // own sequence: the arrival counter counts gridDim per reduction
+        void* args[] = { (void*)&D, (void*)&ws, (void*)&llWords, (void*)&arrivals, (void*)&k0, (void*)&L, (void*)&resR, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre };
         OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)resGrid), dim3(1024), args, resSmem, c.stream));
         return true;
     }

@@ -937,8 +937,22 @@ void installPrelude(Interp& I) {
         int w = P.dag.unary(Op::Sqrt, C);
         return std::vector<Value>{ I2.lift1(a[0], [&](int v) { return P.dag.binary(Op::Mul, w, v); }) };
     });
-    for (const char* nyi : { "Slice" })
-        I.def(nyi, [nyi](Interp&, std::vector<Value>&, int ln) -> std::vector<Value> { fail(std::string(nyi) + " is not supported by this front end yet", ln); });
+    // lib.t:60-74: Slice(image, s, e) is callable like the image and yields channels [s, e) (a scalar when e == s + 1)
+    I.def("Slice", [num](Interp&, std::vector<Value>& a, int ln) {
+        if (a.size() != 3) fail("Slice(image, firstChannel, endChannel)", ln);
+        const Value im = a[0]; const int s = (int)num(a[1], ln, "first channel"), e = (int)num(a[2], ln, "end channel");
+        if (s < 0 || e <= s) fail("Slice: empty or negative channel range", ln);
+        Value f; f.type = Value::Builtin;
+        f.bf = std::make_shared<std::function<std::vector<Value>(Interp&, std::vector<Value>&, int)>>([im, s, e](Interp& I3, std::vector<Value>& args, int ln2) {
+            std::vector<Value> r = I3.call(im, args, ln2);
+            if (r.empty()) fail("Slice: the image access returned nothing", ln2);
+            std::vector<int> v = I3.toVec(r[0]);
+            if ((int)v.size() < e) fail("Slice: channel range exceeds the image's channels", ln2);
+            if (s + 1 == e) return std::vector<Value>{ I3.mkExpr(v[s]) };
+            return std::vector<Value>{ I3.mkVec(std::vector<int>(v.begin() + s, v.begin() + e)) };
+        });
+        return std::vector<Value>{ f };
+    });
     // ---- a little of the Lua standard library
     I.def("print", [](Interp&, std::vector<Value>&, int) { return std::vector<Value>{}; });
     I.def("tostring", [](Interp&, std::vector<Value>& a, int) { Value v = a.empty() ? Value() : a[0]; if (v.type == Value::Num) { char b[64]; if (v.n == (long long)v.n) snprintf(b, sizeof b, "%lld", (long long)v.n); else snprintf(b, sizeof b, "%.14g", v.n); return std::vector<Value>{ Value::str(b) }; } if (v.type == Value::Str) return std::vector<Value>{ v }; return std::vector<Value>{ Value::str("<value>") }; });

@@ -141,6 +141,27 @@ def test_front_end_accepts_a_new_energy_and_reports_errors(built, tmp_path):
     assert not ok and "line 3" in msg
 
 
+def test_front_end_slice(built, tmp_path):
+    """lib.t Slice(image, s, e): a view of channels [s, e) that is called like the image (scalar when e == s + 1)"""
+    from opt_b200.solver import frontend_compile
+    spec = tmp_path / "slice.t"
+    spec.write_text("""
+        local W, H = Dim("W", 0), Dim("H", 1)
+        local X = Unknown("X", opt_float3, { W, H }, 0)
+        local T = Array("T", opt_float3, { W, H }, 1)
+        local xy, zc = Slice(X, 0, 2), Slice(X, 2, 3)
+        local txy = Slice(T, 0, 2)
+        Energy(xy(0, 0) - txy(0, 0))                       -- 2 residual rows
+        Energy(Select(InBounds(1, 0), zc(0, 0) - zc(1, 0), 0))  -- 1 row, scalar slice at an offset
+    """)
+    ok, msg = frontend_compile(str(spec))
+    assert ok and "3 residual groups" in msg, msg
+    bad = tmp_path / "slice_bad.t"
+    bad.write_text("local W = Dim('W', 0)\nlocal X = Unknown('X', opt_float2, {W}, 0)\nEnergy(Slice(X, 1, 3)(0))\n")
+    ok, msg = frontend_compile(str(bad))
+    assert not ok and "channel range" in msg, msg
+
+
 def test_front_end_compiles_every_reference_spec(built):
     """when the reference tree is mounted: every .t file it ships runs through the front end"""
     import glob

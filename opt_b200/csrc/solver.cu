@@ -313,6 +313,7 @@ struct Plan : PlanBase {
     }
     ~Plan() override {
         cudaStreamSynchronize(stream);
+        dropTimedLaunches();
         if (loopExec) cudaGraphExecDestroy(loopExec);
         for (T* v : { delta, r, z, p, p2, Ap, pre, b, Adelta, CtC, SSq, prevX }) if (v) cudaFree(v);
         for (void* q : ipcOpened) cudaIpcCloseMemHandle(q);
@@ -442,6 +443,7 @@ struct Plan : PlanBase {
         E->newSolve();
         enter();
         nIter = 0; finished = false; reported = false; launches = 0;
+        if (timingOn) { OPT_CUDA_CHECK(cudaStreamSynchronize(stream)); dropTimedLaunches(); }   // a previous solve that was abandoned before it finished
         trust_region_radius = (T)sp.trust_region_radius; radius_decrease_factor = (T)sp.radius_decrease_factor;
         min_lm_diagonal = (T)sp.min_lm_diagonal; max_lm_diagonal = (T)sp.max_lm_diagonal;
         E->precompute(ctx());
@@ -559,6 +561,7 @@ struct Plan : PlanBase {
         OPT_CUDA_CHECK(cudaEventRecord(e.a, stream));
         timedLaunches.push_back(e);
     }
+    void dropTimedLaunches() { for (auto& e : timedLaunches) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); } timedLaunches.clear(); }
     void tEnd() { if (timingOn && !timedLaunches.empty()) OPT_CUDA_CHECK(cudaEventRecord(timedLaunches.back().b, stream)); }
     void finishSolve() {   // cleanup(pd), solverGPUGaussNewton.t:1009-1014
         if (verbosity > 0) printf("final cost=%f\n", (double)prevCost);

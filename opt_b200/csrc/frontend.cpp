@@ -30,7 +30,18 @@ namespace {
 
 // ===================================================================================== expression DAG
 enum class Op { Const, Param, Load, Unknown, Index, Bounds, Add, Sub, Mul, Div, Neg, Pow, Sin, Cos, Sqrt, Abs, Exp, Log,
+                Tan, Tanh, Sinh, Cosh, Asin, Acos, Atan, Asinh, Acosh, Log10,   // the rest of ad.t:747-763 (single-argument ones)
                 Less, LessEq, Greater, GreaterEq, Eq, Or, Not, Select, Sample };
+// single-argument math functions beyond the common ones: DSL name, device function (generic_device.cuh), host folding
+struct Math1 { Op op; const char* name; const char* device; double (*host)(double); };
+static const Math1 kMath1[] = {
+    { Op::Tan, "tan", "geTan", [](double x) { return std::tan(x); } },     { Op::Tanh, "tanh", "geTanh", [](double x) { return std::tanh(x); } },
+    { Op::Sinh, "sinh", "geSinh", [](double x) { return std::sinh(x); } },  { Op::Cosh, "cosh", "geCosh", [](double x) { return std::cosh(x); } },
+    { Op::Asin, "asin", "geAsin", [](double x) { return std::asin(x); } },  { Op::Acos, "acos", "geAcos", [](double x) { return std::acos(x); } },
+    { Op::Atan, "atan", "geAtan", [](double x) { return std::atan(x); } },  { Op::Asinh, "asinh", "geAsinh", [](double x) { return std::asinh(x); } },
+    { Op::Acosh, "acosh", "geAcosh", [](double x) { return std::acosh(x); } }, { Op::Log10, "log10", "geLog10", [](double x) { return std::log10(x); } },
+};
+static const Math1* math1Of(Op op) { for (const Math1& m : kMath1) if (m.op == op) return &m; return nullptr; }
 struct Node {
     Op op = Op::Const;
     double value = 0;        // Const
@@ -68,7 +79,8 @@ struct Dag {
             switch (op) {
                 case Op::Neg: return constant(-v); case Op::Sin: return constant(std::sin(v)); case Op::Cos: return constant(std::cos(v));
                 case Op::Sqrt: return constant(std::sqrt(v)); case Op::Abs: return constant(std::fabs(v)); case Op::Exp: return constant(std::exp(v));
-                case Op::Log: return constant(std::log(v)); case Op::Not: return constant(v != 0 ? 0.0 : 1.0); default: break;
+                case Op::Log: return constant(std::log(v)); case Op::Not: return constant(v != 0 ? 0.0 : 1.0);
+                default: if (const Math1* m = math1Of(op)) return constant(m->host(v)); break;
             }
         }
         Node n; n.op = op; n.args = { a }; return add(n);
@@ -881,6 +893,7 @@ void installPrelude(Interp& I) {
     cmp("less", Op::Less); cmp("lesseq", Op::LessEq); cmp("greater", Op::Greater); cmp("greatereq", Op::GreaterEq); cmp("eq", Op::Eq);
     auto un = [&](const char* name, Op op) { I.def(name, [&P, op, name](Interp& I2, std::vector<Value>& a, int ln) { if (a.size() != 1) fail(std::string(name) + "(x)", ln); return std::vector<Value>{ I2.lift1(a[0], [&](int x) { return P.dag.unary(op, x); }) }; }); };
     un("sqrt", Op::Sqrt); un("Sqrt", Op::Sqrt); un("sin", Op::Sin); un("cos", Op::Cos); un("abs", Op::Abs); un("exp", Op::Exp); un("log", Op::Log); un("Not", Op::Not); un("not_", Op::Not);
+    for (const Math1& m : kMath1) un(m.name, m.op);
     I.def("pow", [&P](Interp& I2, std::vector<Value>& a, int ln) { if (a.size() != 2) fail("pow(a, b)", ln); return std::vector<Value>{ I2.lift2(a[0], a[1], [&](int x, int y) { return P.dag.binary(Op::Pow, x, y); }) }; });
     I.def("And", [&P](Interp& I2, std::vector<Value>& a, int) { int r = P.dag.constant(1); for (auto& v : a) r = P.dag.binary(Op::Mul, r, I2.toExpr(v)); return std::vector<Value>{ I2.mkExpr(r) }; });
     I.globals->vars["and_"] = I.globals->vars["And"];
@@ -1027,6 +1040,7 @@ struct Codegen {
     }
     static std::string lit(double v) {
         if (std::isinf(v)) return v > 0 ? "T(1e300*1e300)" : "T(-1e300*1e300)";
+        if (std::isnan(v)) return "T((1e300*1e300) * 0.0)";   // a folded domain error (asin(2), log(-1)...) stays a NaN, as it would be at run time
         char b[64]; snprintf(b, sizeof b, "%.17g", v); std::string s = b;
         if (s.find_first_of(".en") == std::string::npos) s += ".0";
         return "T(" + s + ")";
@@ -1078,6 +1092,8 @@ struct Codegen {
             case Op::Abs: out << "geAbs(" << A(0) << ")"; break;
             case Op::Exp: out << "geExp(" << A(0) << ")"; break;
             case Op::Log: out << "geLog(" << A(0) << ")"; break;
+            case Op::Tan: case Op::Tanh: case Op::Sinh: case Op::Cosh: case Op::Asin: case Op::Acos: case Op::Atan: case Op::Asinh: case Op::Acosh: case Op::Log10:
+                out << math1Of(n.op)->device << "(" << A(0) << ")"; break;
             case Op::Less: out << "(" << val(0) << " < " << val(1) << " ? T(1) : T(0))"; break;
             case Op::LessEq: out << "(" << val(0) << " <= " << val(1) << " ? T(1) : T(0))"; break;
             case Op::Greater: out << "(" << val(0) << " > " << val(1) << " ? T(1) : T(0))"; break;

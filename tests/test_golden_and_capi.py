@@ -162,6 +162,20 @@ def test_front_end_slice(built, tmp_path):
     assert not ok and "channel range" in msg, msg
 
 
+@pytest.mark.parametrize("dp", [False, True])
+def test_front_end_math_functions(built, tmp_path, dp):
+    """every single-argument function of the reference's ad.t (:747-763) is known to the front end and to the device-side
+    dual numbers (NVRTC compiles the generated residuals in both precisions); constants fold on the host"""
+    from opt_b200.solver import frontend_compile
+    spec = tmp_path / "math.t"
+    fns = ["sqrt", "sin", "cos", "tan", "exp", "log", "log10", "abs", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh"]
+    body = "\n".join(f"Energy({f}(X(0) * 0.1 + {c}) - {f}({c}) * Y(0))" for f in fns for c in (["0.5"] if f in ("asin", "acos") else ["1.5"]))
+    body += "\nEnergy(asin(2.0) * X(0))"                   # a folded domain error must still be valid generated code
+    spec.write_text('local N = Dim("N", 0)\nlocal X = Unknown("X", opt_float, { N }, 0)\nlocal Y = Array("Y", opt_float, { N }, 1)\n' + body + "\nEnergy(pow(X(0), 2.0) - Y(0))\n")
+    ok, msg = frontend_compile(str(spec), double_precision=dp)
+    assert ok and f"{len(fns) + 2} residual groups" in msg, msg
+
+
 def test_front_end_compiles_every_reference_spec(built):
     """when the reference tree is mounted: every .t file it ships runs through the front end"""
     import glob

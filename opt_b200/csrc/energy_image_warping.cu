@@ -700,6 +700,152 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopResident(IWData<T> D, Redu
     if (L > 0 && blockIdx.x == 0 && tid == 0) { ws.scalars[kPAp] = dPAp; ws.scalars[L & 1] = dRz; ws.scalars[(L + 1) & 1] = dRzPrev; }
 }
 
+// ------------------------------------------------------------------------------------ whole PCG loop, state on chip, 2-D tiles
+// k_iwPcgLoopResident with tiles of tw x th pixels instead of slabs of full rows: the ring is the tile's perimeter (all
+// four sides), so wide images whose row slabs would be all ring still fit (the shape the
+// multi-GPU version needs).  OPT-IN (OPTB_RESIDENT_TILE=WxH) and NOT yet run on hardware: written after the round's GPU
+// budget was spent; the validated default is the row-slab kernel above.
+template <class T, int KMAX>
+__global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long* arrivals,
+                                                           unsigned long long k0, int L, int tw, int th, int tilesAcross,
+                                                           T* delta, T* r, T* z, T* p, T* Ap, const T* __restrict__ pre) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    constexpr int NT = 1024;
+    const int W = D.W, H = D.H, tid = threadIdx.x;
+    const int tx0 = (blockIdx.x % tilesAcross) * tw, ty0 = (blockIdx.x / tilesAcross) * th;
+    const int twE = min(tw, W - tx0), thE = min(th, H - ty0);     // clipped tile (>= 1 x 1 by construction)
+    const int pw = tw + 2;                                        // pitch of the ring-included planes
+    const int nRing = (th + 2) * pw, nCap = tw * th;
+    T* sPx = reinterpret_cast<T*>(smemRaw); T* sPy = sPx + nRing; T* sPa = sPy + nRing;
+    T* sGc = sPa + nRing; T* sGs = sGc + nRing; T* sGx = sGs + nRing; T* sGy = sGx + nRing;
+    T* sRx = sGy + nRing; T* sRy = sRx + nCap; T* sRa = sRy + nCap; T* sQo = sRa + nCap; T* sQa = sQo + nCap;
+    unsigned char* sF = reinterpret_cast<unsigned char*>(sQa + nCap);
+    const Vec2<T>* pO = reinterpret_cast<const Vec2<T>*>(p);
+    for (int c = tid; c < (thE + 2) * pw; c += NT) {              // ring-included planes; cells outside the image are zero
+        const int lr = c / pw, lc = c - lr * pw, gx = tx0 - 1 + lc, gy = ty0 - 1 + lr;
+        T px = T(0), py = T(0), pa = T(0); Vec4<T> g{ T(0), T(0), T(0), T(0) };
+        if (lc <= twE + 1 && gx >= 0 && gx < W && gy >= 0 && gy < H) { const long j = (long)gy * W + gx; const Vec2<T> po = pO[j]; px = po.x; py = po.y; pa = p[D.offA + j]; g = D.geom[j]; }
+        sPx[c] = px; sPy[c] = py; sPa[c] = pa; sGc[c] = g.x; sGs[c] = g.y; sGx[c] = g.z; sGy[c] = g.w;
+    }
+    T zx[KMAX], zy[KMAX], za[KMAX], ax[KMAX], ay[KMAX], aa[KMAX], dx[KMAX], dy[KMAX], da[KMAX];
+    int ccOf[KMAX]; long giOf[KMAX];                              // ring-plane cell and global pixel index of the thread's pixels (-1: none)
+    bool edge[KMAX];                                              // on the tile's perimeter: its z is read by a neighbouring tile
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) {
+        const int c = tid + q * NT;
+        zx[q] = zy[q] = za[q] = ax[q] = ay[q] = aa[q] = dx[q] = dy[q] = da[q] = T(0); edge[q] = false; ccOf[q] = -1; giOf[q] = -1;
+        if (c < nCap) {
+            const int ly = c / tw, lx = c - ly * tw;
+            if (lx < twE && ly < thE) {
+                const long i = (long)(ty0 + ly) * W + tx0 + lx;
+                ccOf[q] = (ly + 1) * pw + lx + 1; giOf[q] = i;
+                const Vec2<T> ro = reinterpret_cast<const Vec2<T>*>(r)[i]; sRx[c] = ro.x; sRy[c] = ro.y; sRa[c] = r[D.offA + i];
+                sQo[c] = reinterpret_cast<const Vec2<T>*>(pre)[i].x; sQa[c] = pre[D.offA + i];
+                sF[c] = D.flags[i];
+                const Vec2<T> dO = reinterpret_cast<const Vec2<T>*>(delta)[i]; dx[q] = dO.x; dy[q] = dO.y; da[q] = delta[D.offA + i];
+                edge[q] = (ly == 0 || ly == thE - 1 || lx == 0 || lx == twE - 1);
+            }
+        }
+    }
+    __syncthreads();
+    unsigned long long k = k0;
+    double dRz = ws.scalars[kRz0], dRzPrev = 0.0, dPAp = 0.0;
+    const T w2 = D.w * D.w, wf2 = D.wf * D.wf;
+    const int nPerim = 2 * (twE + thE);
+    for (int l = 0; l < L; ++l) {
+        if (l > 0) {
+            T beta = T(0);
+            { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
+#pragma unroll
+            for (int q = 0; q < KMAX; ++q)
+                if (ccOf[q] >= 0) { const int cc = ccOf[q]; sPx[cc] = zx[q] + beta * sPx[cc]; sPy[cc] = zy[q] + beta * sPy[cc]; sPa[cc] = za[q] + beta * sPa[cc]; }
+            for (int c = tid; c < nPerim; c += NT) {              // ring cells: top row, bottom row, left column, right column
+                int lr, lc;
+                if (c < twE) { lr = 0; lc = c + 1; }
+                else if (c < 2 * twE) { lr = thE + 1; lc = c - twE + 1; }
+                else if (c < 2 * twE + thE) { lr = c - 2 * twE + 1; lc = 0; }
+                else { lr = c - 2 * twE - thE + 1; lc = twE + 1; }
+                const int gx = tx0 - 1 + lc, gy = ty0 - 1 + lr;
+                if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+                    const long j = (long)gy * W + gx;
+                    const Vec2<T> zo = ldcgV(reinterpret_cast<const Vec2<T>*>(z) + j); const T zaa = ldcgT(z + D.offA + j);
+                    const int cc = lr * pw + lc;
+                    sPx[cc] = zo.x + beta * sPx[cc]; sPy[cc] = zo.y + beta * sPy[cc]; sPa[cc] = zaa + beta * sPa[cc];
+                }
+            }
+            __syncthreads();
+        }
+        T acc = T(0);
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q) {
+            T ox = T(0), oy = T(0), oa = T(0);
+            if (ccOf[q] >= 0) {
+                const int cc = ccOf[q];
+                const unsigned fl = sF[tid + q * NT];
+                if (fl & 32u) {
+                    const T pix = sPx[cc], piy = sPy[cc], pai = sPa[cc];
+                    const T gc = sGc[cc], gs = sGs[cc], gux = sGx[cc], guy = sGy[cc];
+                    T sx = T(0), sy = T(0), sa = T(0);
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) {
+                        if (fl & (1u << nb)) {
+                            const int jj = cc + (nb == 0 ? 1 : (nb == 1 ? -1 : (nb == 2 ? pw : -pw)));
+                            const T jc = sGc[jj], js = sGs[jj];
+                            const T ddx = gux - sGx[jj], ddy = guy - sGy[jj];
+                            const T eix = -gs * ddx - gc * ddy, eiy = gc * ddx - gs * ddy;
+                            const T ejx = -js * ddx - jc * ddy, ejy = jc * ddx - js * ddy;
+                            const T paj = sPa[jj];
+                            const T px = pix - sPx[jj], py = piy - sPy[jj];
+                            sx += T(2) * px - eix * pai - ejx * paj;
+                            sy += T(2) * py - eiy * pai - ejy * paj;
+                            sa += (eix * eix + eiy * eiy) * pai - (eix * px + eiy * py);
+                        }
+                    }
+                    ox = w2 * sx; oy = w2 * sy; oa = w2 * sa;
+                    if (fl & 16u) { ox += wf2 * pix; oy += wf2 * piy; }
+                    acc += pix * ox + piy * oy + pai * oa;
+                }
+            }
+            ax[q] = ox; ay[q] = oy; aa[q] = oa;
+        }
+        dPAp = gridAllReduceLL<NT>((double)acc, llWords, arrivals, ++k, false);
+        T alpha = T(0);
+        { const T num = (T)dRz, den = (T)dPAp; if (den > T(0)) alpha = num / den; }
+        acc = T(0);
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q) {
+            if (ccOf[q] >= 0) {
+                const int cc = ccOf[q], c = tid + q * NT;
+                dx[q] = dx[q] + alpha * sPx[cc]; dy[q] = dy[q] + alpha * sPy[cc]; da[q] = da[q] + alpha * sPa[cc];
+                const T rx = sRx[c] - alpha * ax[q], ry = sRy[c] - alpha * ay[q], ra = sRa[c] - alpha * aa[q];
+                sRx[c] = rx; sRy[c] = ry; sRa[c] = ra;
+                const T qo = sQo[c];
+                zx[q] = qo * rx; zy[q] = qo * ry; za[q] = sQa[c] * ra;
+                acc += zx[q] * rx; acc += zy[q] * ry; acc += za[q] * ra;
+                if (edge[q]) { stcgV(reinterpret_cast<Vec2<T>*>(z) + giOf[q], Vec2<T>{ zx[q], zy[q] }); stcgT(z + D.offA + giOf[q], za[q]); }
+            }
+        }
+        dRzPrev = dRz;
+        dRz = gridAllReduceLL<NT>((double)acc, llWords, arrivals, ++k, true);
+    }
+    T beta = T(0);
+    if (L > 0) { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) {
+        if (ccOf[q] >= 0) {
+            const int cc = ccOf[q], c = tid + q * NT; const long i = giOf[q];
+            T px = sPx[cc], py = sPy[cc], pa = sPa[cc];
+            if (L > 0) { px = zx[q] + beta * px; py = zy[q] + beta * py; pa = za[q] + beta * pa; }
+            reinterpret_cast<Vec2<T>*>(p)[i] = Vec2<T>{ px, py }; p[D.offA + i] = pa;
+            reinterpret_cast<Vec2<T>*>(delta)[i] = Vec2<T>{ dx[q], dy[q] }; delta[D.offA + i] = da[q];
+            reinterpret_cast<Vec2<T>*>(r)[i] = Vec2<T>{ sRx[c], sRy[c] }; r[D.offA + i] = sRa[c];
+            reinterpret_cast<Vec2<T>*>(z)[i] = Vec2<T>{ zx[q], zy[q] }; z[D.offA + i] = za[q];
+            reinterpret_cast<Vec2<T>*>(Ap)[i] = Vec2<T>{ ax[q], ay[q] }; Ap[D.offA + i] = aa[q];
+        }
+    }
+    if (L > 0 && blockIdx.x == 0 && tid == 0) { ws.scalars[kPAp] = dPAp; ws.scalars[L & 1] = dRz; ws.scalars[(L + 1) & 1] = dRzPrev; }
+}
+
 // ------------------------------------------------------------------------------------ computeCost
 // solverGPUGaussNewton.t:580-592 + o.t:2375-2385: 1/2 sum r^2 over residuals centred at active pixels.
 // MODEL: computeModelCost (:666-678, o.t:2174-2199): 1/2 sum (r + J delta)^2.
@@ -864,7 +1010,7 @@ struct ImageWarpingOps : EnergyOps<T> {
         gridCost = gridOf((const void*)k_iwCost<T, false>);
         setupTma(sms);
     }
-    ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); if (loopSync) cudaFree(loopSync); if (llWords) cudaFree(llWords); }
+    ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); if (loopSync) cudaFree(loopSync); if (llWords) cudaFree(llWords); if (tileWords) cudaFree(tileWords); }
     const char* name() const override { return "image_warping"; }
     int upperRows = 0, lowerRows = 0;
     bool setSlab(int ownedBegin, int ownedEnd, int up, int dn) override {
@@ -922,8 +1068,44 @@ struct ImageWarpingOps : EnergyOps<T> {
         OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)resGrid), dim3(1024), args, resSmem, c.stream));
         return true;
     }
+    // 2-D tile variant (opt-in, OPTB_RESIDENT_TILE=WxH): own sequence/arrival state because its grid size differs
+    int tileW = 0, tileH = 0, tileGrid = 0, tileK = 0, tileAcross = 0; size_t tileSmem = 0; unsigned long long* tileWords = nullptr; unsigned long long tileSeq = 0;
+    template <int KMAX>
+    bool launchTileK(const LaunchCtx& c, int L, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
+        const void* fn = (const void*)k_iwPcgLoopTile<T, KMAX>;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileSmem) != cudaSuccess) { cudaGetLastError(); return false; }
+        int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 1024, tileSmem);
+        int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if ((long)occ * sms < tileGrid) return false;
+        constexpr size_t llCount = 4 * (kMaxLLCtas + 1) + 1;
+        if (!tileWords) { OPT_CUDA_CHECK(cudaMalloc((void**)&tileWords, sizeof(unsigned long long) * llCount)); OPT_CUDA_CHECK(cudaMemset(tileWords, 0, sizeof(unsigned long long) * llCount)); tileSeq = 0; }
+        unsigned long long* arrivals = tileWords + 4 * (kMaxLLCtas + 1);
+        unsigned long long k0 = tileSeq; tileSeq += 2ull * (unsigned long long)L;
+        ReduceWorkspace ws = c.ws;
+        void* args[] = { (void*)&D, (void*)&ws, (void*)&tileWords, (void*)&arrivals, (void*)&k0, (void*)&L, (void*)&tileW, (void*)&tileH, (void*)&tileAcross,
+                         (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre };
+        OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)tileGrid), dim3(1024), args, tileSmem, c.stream));
+        return true;
+    }
+    bool launchTile(const LaunchCtx& c, int L, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
+        const char* spec = getenv("OPTB_RESIDENT_TILE");
+        if (!spec) return false;
+        if (tileW == 0) {
+            int a = 0, b = 0;
+            if (sscanf(spec, "%dx%d", &a, &b) != 2 || a < 1 || b < 1) { tileW = -1; return false; }
+            tileW = a; tileH = b; tileAcross = (D.W + a - 1) / a; tileGrid = tileAcross * ((D.H + b - 1) / b);
+            const size_t nRing = (size_t)(b + 2) * (a + 2), nCap = (size_t)a * b;
+            tileSmem = ((nRing * 7 + nCap * 5) * sizeof(T) + nCap + 15) / 16 * 16;
+            tileK = (int)((nCap + 1023) / 1024);
+            int dev = 0, maxSmem = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            if (tileSmem > (size_t)maxSmem || tileK > 4 || tileGrid > kMaxLLCtas) tileW = -1;
+        }
+        if (tileW < 0) return false;
+        return tileK <= 2 ? launchTileK<2>(c, L, delta, r, z, p, Ap, pre) : launchTileK<4>(c, L, delta, r, z, p, Ap, pre);
+    }
     bool launchResident(const LaunchCtx& c, int L, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
         if (getenv("OPTB_NO_RESIDENT")) return false;
+        if (launchTile(c, L, delta, r, z, p, Ap, pre)) return true;
         if (resR == 0) {
             int dev = 0, sms = 148, maxSmem = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

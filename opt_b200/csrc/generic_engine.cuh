@@ -70,6 +70,14 @@ static __global__ void k_geKeys(long nEnt, const int* __restrict__ col, const un
         colM[t] = c; keys[t] = c >= 0 ? c : nU; ids[t] = (int)t;
     }
 }
+// The masked columns and the transposed structure are built from the Exclude() flags of one linearisation; the reference
+// re-evaluates the exclusion in every kernel, so a caller may change a mask image between two Opt_ProblemStep calls.
+// This compares the fresh flags with the ones the structure was built from (one byte per unknown).
+static __global__ void k_geActiveChanged(int nU, const unsigned char* __restrict__ now, const unsigned char* __restrict__ built, int* __restrict__ changed) {
+    bool diff = false;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nU; u += gridDim.x * blockDim.x) diff = diff || (now[u] != built[u]);
+    if (diff) *changed = 1;   // every writer stores the same value
+}
 static __global__ void k_geColStart(long nEnt, const int* __restrict__ sortedKeys, int nU, int* __restrict__ colStart) {
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t <= nEnt; t += (long)gridDim.x * blockDim.x) {
         const int k = t < nEnt ? sortedKeys[t] : nU, kp = t > 0 ? sortedKeys[t - 1] : -1;
@@ -228,7 +236,8 @@ struct GenericOpsBase : EnergyOps<T> {
     long nSlots = 0, capSlots = 0; int nSlices = 0;
     void* scanTemp = nullptr; size_t scanBytes = 0;
     GeLayout* dLayout = nullptr;
-    unsigned char *rowCost = nullptr, *active = nullptr;
+    unsigned char *rowCost = nullptr, *active = nullptr, *activeBuilt = nullptr;
+    int *dChanged = nullptr, *hChanged = nullptr;
     void* cubTemp = nullptr; size_t cubBytes = 0;
     long capRows = 0, capEnt = 0;
     bool structureValid = false;
@@ -243,6 +252,8 @@ struct GenericOpsBase : EnergyOps<T> {
         this->layoutUnknowns();
         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         OPT_CUDA_CHECK(cudaMalloc((void**)&active, this->nUnknownsPadded)); OPT_CUDA_CHECK(cudaMemset(active, 0, this->nUnknownsPadded));
+        OPT_CUDA_CHECK(cudaMalloc((void**)&activeBuilt, this->nUnknownsPadded)); OPT_CUDA_CHECK(cudaMemset(activeBuilt, 0, this->nUnknownsPadded));
+        OPT_CUDA_CHECK(cudaMalloc((void**)&dChanged, sizeof(int))); OPT_CUDA_CHECK(cudaMallocHost((void**)&hChanged, sizeof(int)));
         OPT_CUDA_CHECK(cudaMalloc((void**)&colStart, sizeof(int) * (this->nUnknownsPadded + 2)));
         if (this->nUnknownsPadded % 32) { fprintf(stderr, "opt_b200: internal error, unknown vector not padded to a multiple of 32\n"); exit(2); }
         nSlices = (int)(this->nUnknownsPadded / 32);
@@ -252,7 +263,8 @@ struct GenericOpsBase : EnergyOps<T> {
         OPT_CUDA_CHECK(cudaMalloc(&scanTemp, scanBytes));
     }
     ~GenericOpsBase() override { for (void* q : { (void*)F, (void*)val, (void*)y, (void*)col, (void*)entRow, (void*)keys, (void*)ids, (void*)keysSorted, (void*)idsSorted, (void*)colStart, (void*)rowCost, (void*)active, (void*)rowS, (void*)valS, (void*)dLayout, cubTemp,
-                                                       (void*)colM, (void*)sliceSlots, (void*)sliceStart, (void*)srcS, scanTemp }) if (q) cudaFree(q); }
+                                                       (void*)colM, (void*)sliceSlots, (void*)sliceStart, (void*)srcS, scanTemp, (void*)activeBuilt, (void*)dChanged }) if (q) cudaFree(q);
+                                 if (hChanged) cudaFreeHost(hChanged); }
     int grid(long n, int block = kBlock) const { long g = (n + block - 1) / block; long cap = (long)sms * 8; if (g > cap) g = cap; if (g > kMaxPartials) g = kMaxPartials; return g < 1 ? 1 : (int)g; }
     void bind(void** q) override {
         GeLayout N{};
@@ -288,10 +300,19 @@ struct GenericOpsBase : EnergyOps<T> {
     void linearise(const LaunchCtx& c) {
         for (int a = 0; a < (int)this->unknowns.size(); ++a) launchActive(c, a, grid(this->unknowns[a].elements, 256));
         for (int g = 0; g < L.nGroups; ++g) if (L.group[g].count > 0) launchFill(c, g, grid(L.group[g].count, 128));
-        // The sparsity pattern depends on the graph indices / dimensions only; it is rebuilt at every Opt_ProblemInit
-        // (newSolve) and whenever the sizes change, not per nonlinear iteration.
+        // The sparsity pattern depends on the graph indices / dimensions and on the Exclude() flags; it is rebuilt at every
+        // Opt_ProblemInit (newSolve), whenever the sizes change, and when a mask changed since it was built -- not per
+        // nonlinear iteration.  (The stream is idle here: the previous step ended with the cost read-back.)
+        if (structureValid) {
+            OPT_CUDA_CHECK(cudaMemsetAsync(dChanged, 0, sizeof(int), c.stream));
+            k_geActiveChanged<<<grid(this->nUnknownsPadded), kBlock, 0, c.stream>>>((int)this->nUnknownsPadded, active, activeBuilt, dChanged);
+            OPT_CUDA_CHECK(cudaMemcpyAsync(hChanged, dChanged, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+            OPT_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+            if (*hChanged) structureValid = false;
+        }
         if (!structureValid) {
             const int nU = (int)this->nUnknownsPadded;
+            OPT_CUDA_CHECK(cudaMemcpyAsync(activeBuilt, active, this->nUnknownsPadded, cudaMemcpyDeviceToDevice, c.stream));
             k_geKeys<<<grid(L.nEnt), kBlock, 0, c.stream>>>(L.nEnt, col, active, nU, keys, ids, colM);
             int endBit = 1; while ((1L << endBit) <= nU && endBit < 31) ++endBit;
             cub::DeviceRadixSort::SortPairs(cubTemp, cubBytes, keys, keysSorted, ids, idsSorted, (int)L.nEnt, 0, endBit, c.stream);

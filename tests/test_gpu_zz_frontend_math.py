@@ -42,3 +42,49 @@ def test_math_function_values_and_derivatives(built, tmp_path, fn):
     got = s.unflatten(r0)[0].reshape(-1)
     assert np.abs(got - (-jac * res)).max() <= 1e-11 * max(1.0, np.abs(jac * res).max())
     s.close()
+
+
+MASK_SPEC = """
+local W, H = Dim("W", 0), Dim("H", 1)
+local X = Unknown("X", opt_float, { W, H }, 0)
+local Y = Array("Y", opt_float, { W, H }, 1)
+local M = Array("M", opt_float, { W, H }, 2)
+UsePreconditioner(true)
+Exclude(Not(eq(M(0, 0), 0)))
+Energy(X(0, 0) - Y(0, 0))
+for dx, dy in Stencil { { 1, 0 }, { 0, 1 } } do
+    Energy(Select(InBounds(dx, dy), 2.0 * (X(0, 0) - X(dx, dy)), 0))
+end
+"""
+
+
+def test_exclude_mask_may_change_between_steps(built, tmp_path):
+    """the reference evaluates Exclude() in every kernel, so a caller may edit a mask image between two Opt_ProblemStep
+    calls; the generic engine caches masked columns per solve and must notice (generic_engine.cuh k_geActiveChanged)"""
+    import torch
+    from opt_b200 import OptSolver
+    W, H = 24, 17
+    spec = tmp_path / "masked_smooth.t"; spec.write_text(MASK_SPEC)
+    rng = np.random.default_rng(2)
+    Y = rng.normal(size=W * H); X0 = Y + 0.3 * rng.normal(size=W * H)
+    M1 = (rng.random(W * H) < 0.15).astype(np.float64); M2 = (rng.random(W * H) < 0.15).astype(np.float64)
+    params = {"nIterations": 5, "lIterations": 20}
+    # solver A: one step with mask 1, then the mask buffer is overwritten in place, one more step
+    devA = [torch.from_numpy(X0.copy()).cuda(), torch.from_numpy(Y).cuda(), torch.from_numpy(M1.copy()).cuda()]
+    a = OptSolver([W, H], str(spec), "gaussNewtonGPU", double_precision=True)
+    a.set_solver_parameters(params)
+    a.init(devA); a.step(devA)
+    X1 = devA[0].cpu().numpy().copy()
+    devA[2].copy_(torch.from_numpy(M2))
+    a.step(devA)
+    XA = devA[0].cpu().numpy().copy()
+    a.close()
+    # solver B: starts from X1 with mask 2
+    devB = [torch.from_numpy(X1.copy()).cuda(), torch.from_numpy(Y).cuda(), torch.from_numpy(M2.copy()).cuda()]
+    b = OptSolver([W, H], str(spec), "gaussNewtonGPU", double_precision=True)
+    b.set_solver_parameters(params)
+    b.init(devB); b.step(devB)
+    XB = devB[0].cpu().numpy().copy()
+    b.close()
+    assert np.abs(XA - XB).max() <= 1e-12 * max(1.0, np.abs(XB).max())
+    assert np.array_equal(XA[M2 != 0], X1[M2 != 0])            # pixels excluded by the NEW mask did not move in the second step

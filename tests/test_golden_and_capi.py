@@ -176,6 +176,16 @@ def test_front_end_math_functions(built, tmp_path, dp):
     assert ok and f"{len(fns) + 2} residual groups" in msg, msg
 
 
+def test_device_dual_number_math_on_the_host(tmp_path):
+    """generic_device.cuh compiled for the CPU behind shims (tests/host/device_math_host.cpp): value and derivative of
+    every dual-number function against central finite differences -- the math the generic engine differentiates with"""
+    import subprocess
+    exe = tmp_path / "device_math_host"
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "host", "device_math_host.cpp")])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "ALL_OK" in r.stdout, r.stdout
+
+
 def test_front_end_compiles_every_reference_spec(built):
     """when the reference tree is mounted: every .t file it ships runs through the front end"""
     import glob

@@ -1,0 +1,70 @@
+"""No GPU needed: the code the .t front end GENERATES for every energy the oracle knows is executed on the CPU -- through the
+generic engine's own device bodies (geActiveBody / geFillBody), compiled for the host behind shims by
+tests/host/spec_eval_host.cpp -- and its cost, J^T F and diag(J^T J) are compared with the CPU oracle in fp64.
+This pins interpreter + analysis + code generation + dual-number Jacobians + Exclude / bounds rules without a device;
+the GPU tests (test_gpu_generic_energies.py, @frontend cases) then only have to add the launch plumbing."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from opt_b200 import spec_path, workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CXX = "/usr/bin/g++"
+
+CASES = {
+    # energy: (dims, host-parameter generator (fp64), positions of the unknown arrays)
+    "image_warping": ([24, 18], lambda: workloads.image_warping(24, 18, dtype=np.float64, mask="random", seed=4, perturb=0.3), [0, 1]),
+    "arap_mesh_deformation": ([11 * 9], lambda: workloads.arap_mesh(11, 9, dtype=np.float64, n_handles=7, perturb=0.2), [2, 3]),
+    "poisson_image_editing": ([21, 17], lambda: workloads.poisson(21, 17, dtype=np.float64), [0]),
+    "curveFitting": ([96, 1], lambda: workloads.curve_fitting(96, dtype=np.float64), [0]),
+    "shape_from_shading": ([26, 22], lambda: workloads.shape_from_shading(26, 22, dtype=np.float64), [16]),
+    "robust_nonrigid_alignment": ([8 * 7], lambda: workloads.robust_nonrigid(8, 7, dtype=np.float64, perturb=0.1), [2, 3, 4]),
+}
+
+
+@pytest.fixture(scope="module")
+def fe_probe(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("fe") / "fe_probe"
+    subprocess.check_call([CXX, "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tools", "fe_probe.cpp"), os.path.join(ROOT, "opt_b200", "csrc", "frontend.cpp")])
+    return str(exe)
+
+
+def _write_params(host, d):
+    for k, v in enumerate(host):
+        if isinstance(v, np.ndarray):
+            np.ascontiguousarray(v).tofile(os.path.join(d, f"p{k}.bin"))
+        elif isinstance(v, (int, np.integer)) and not isinstance(v, bool):
+            np.array([v], np.int32).tofile(os.path.join(d, f"p{k}.bin"))
+        else:
+            np.array([v], np.float32).tofile(os.path.join(d, f"p{k}.bin"))     # Param(..., float, k): the callers pass float* (oracle.ParamPack does the same)
+
+
+@pytest.mark.parametrize("energy", sorted(CASES))
+def test_generated_code_matches_oracle_on_the_host(fe_probe, tmp_path, energy):
+    from oracle.oracle import Oracle
+    dims, gen, upos = CASES[energy]
+    host = gen()
+    spec = spec_path(energy)
+    inc = tmp_path / "generated.inc"
+    out = subprocess.run([fe_probe, "--emit", str(inc), spec], capture_output=True, text=True)
+    assert out.returncode == 0 and inc.exists(), out.stdout + out.stderr
+    exe = tmp_path / "spec_eval_host"
+    subprocess.check_call([CXX, "-O1", "-std=c++17", f'-DGEN_SOURCE="{inc}"', "-o", str(exe), os.path.join(ROOT, "tests", "host", "spec_eval_host.cpp"),
+                           os.path.join(ROOT, "opt_b200", "csrc", "frontend.cpp")])
+    data = tmp_path / "params"; data.mkdir()
+    _write_params(host, str(data))
+    res = tmp_path / "out.bin"
+    r = subprocess.run([str(exe), spec, str(data), str(res)] + [str(x) for x in dims], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("COST "), r.stdout + r.stderr
+    cost = float(r.stdout.split()[1])
+    o = Oracle(energy, "gaussNewtonGPU", dims, True)
+    ocost, g, diag = o.eval_jtf(host)
+    both = np.fromfile(str(res), np.float64)
+    assert both.size == 2 * g.size, (both.size, g.size)
+    jtf, dg = both[:g.size], both[g.size:]
+    assert abs(cost - ocost) <= 1e-11 * max(1.0, abs(ocost)), (cost, ocost)
+    assert np.abs(jtf - g).max() <= 1e-10 * max(1.0, np.abs(g).max())
+    assert np.abs(dg - diag).max() <= 1e-10 * max(1.0, np.abs(diag).max())

@@ -27,7 +27,10 @@ namespace optb {
 #include GEN_SOURCE
 }
 using namespace optb;
-typedef double T;
+#ifndef HOST_T
+#define HOST_T double
+#endif
+typedef HOST_T T;   // opt_float of the run (-DHOST_T=float for specs that declare float unknowns)
 
 static std::vector<char> readFile(const std::string& path) {
     FILE* f = fopen(path.c_str(), "rb");
@@ -62,7 +65,8 @@ int main(int argc, char** argv) {
         void* q = param(im.paramIndex);
         P.img[i] = q;
         if (im.unknown) {
-            if (im.type != fe::ScalarType::OptFloat && im.type != fe::ScalarType::Double) { fprintf(stderr, "this harness runs in fp64: unknown '%s' must be opt_float\n", im.name.c_str()); return 3; }
+            const bool okType = im.type == fe::ScalarType::OptFloat || (sizeof(T) == 8 ? im.type == fe::ScalarType::Double : im.type == fe::ScalarType::Float);
+            if (!okType) { fprintf(stderr, "unknown '%s' does not have the precision this harness was built for\n", im.name.c_str()); return 3; }
             P.U[im.unknownId] = GeArray<T>{ (T*)q, unknowns[im.unknownId].elements, im.channels, unknowns[im.unknownId].offset };
         }
     }
@@ -71,7 +75,8 @@ int main(int argc, char** argv) {
         const void* q = param(cs.params[k].paramIndex);
         switch (cs.params[k].type) {     // DynamicOps::readScalar
             case fe::ScalarType::Float: P.par[k] = (double)*(const float*)q; break;
-            case fe::ScalarType::Double: case fe::ScalarType::OptFloat: P.par[k] = *(const double*)q; break;
+            case fe::ScalarType::Double: P.par[k] = *(const double*)q; break;
+            case fe::ScalarType::OptFloat: P.par[k] = (double)*(const T*)q; break;
             case fe::ScalarType::Int32: P.par[k] = (double)*(const int*)q; break;
             default: P.par[k] = (double)*(const unsigned char*)q;
         }

@@ -45,12 +45,28 @@ def _write_params(host, d):
             np.array([v], np.float32).tofile(os.path.join(d, f"p{k}.bin"))     # Param(..., float, k): the callers pass float* (oracle.ParamPack does the same)
 
 
+REFERENCE = "/root/reference"
+
+
+def _reference_spec(energy):
+    if energy == "curveFitting":
+        return os.path.join(REFERENCE, "tests", "minimal_graph_only", "curveFitting.t")
+    if energy == "laplacian":
+        return os.path.join(REFERENCE, "tests", "minimal", "laplacian.t")
+    return os.path.join(REFERENCE, "examples", energy, energy + ".t")
+
+
+@pytest.mark.parametrize("source", ["specs", "reference"])
 @pytest.mark.parametrize("energy", sorted(CASES))
-def test_generated_code_matches_oracle_on_the_host(fe_probe, tmp_path, energy):
+def test_generated_code_matches_oracle_on_the_host(fe_probe, tmp_path, energy, source):
+    """source = "specs": this repository's own statement of the energy; "reference": the reference's .t file itself, read
+    where it lies (only when the reference tree is mounted) -- the oracle restates exactly that file"""
     from oracle.oracle import Oracle
     dims, gen, upos = CASES[energy]
     host = gen()
-    spec = spec_path(energy)
+    spec = spec_path(energy) if source == "specs" else _reference_spec(energy)
+    if source == "reference" and not os.path.exists(spec):
+        pytest.skip("reference tree not mounted")
     inc = tmp_path / "generated.inc"
     out = subprocess.run([fe_probe, "--emit", str(inc), spec], capture_output=True, text=True)
     assert out.returncode == 0 and inc.exists(), out.stdout + out.stderr

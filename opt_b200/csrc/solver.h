@@ -159,6 +159,7 @@ bool compileSpecToCubin(const fe::CompiledSpec& cs, bool doublePrecision, std::v
 // per-energy factories (energy_*.cu); return nullptr when the energy/precision is not built
 template <class T> EnergyOps<T>* makeImageWarping(const unsigned* dims);
 template <class T> EnergyOps<T>* makeArapMesh(const unsigned* dims);
+template <class T> EnergyOps<T>* makeSfs(const unsigned* dims);   // energy_sfs.cu (opt-in: OPTB_SFS_HAND=1)
 template <class T> EnergyOps<T>* makeGenericEnergy(const std::string& energy, const unsigned* dims);
 
 }  // namespace optb

@@ -562,7 +562,6 @@ struct Interp {
         if (!args.empty() && args[0].type == Value::Obj && dynamic_cast<GraphElemObj*>(args[0].obj.get())) {
             auto* ge = dynamic_cast<GraphElemObj*>(args[0].obj.get());
             if (ge->dims != im->dims) fail("graph element is in a different index space from the image", ln);
-            if (nd != 1) fail("graph access is supported for 1-D index spaces only", ln);
             graph = true; gslot = ge->globalSlot; used = 1;
         } else {
             if ((int)args.size() < nd) fail("image access needs one offset per dimension", ln);
@@ -1121,7 +1120,17 @@ struct Codegen {
             if (nd > 2) out << "            const long i2 = i / (n0 * n1);\n";
         } else {
             out << "            const long i0 = i, n0 = 0; (void)i0; (void)n0;\n";
-            for (int s : slots) out << "            const long e" << s << " = (long)P.gidx[" << s << "][i];\n";
+            // a vertex of an nd-dimensional index space is stored as nd interleaved int32 (the reference's Index struct
+            // {d0, d1, ...}, o.t:355-387, util.t:677-682); its linear offset is d0 + n0 * (d1 + n1 * d2)
+            for (int s : slots) {
+                const std::vector<int>& sd = P.slotDims[s];
+                const int nd = (int)sd.size();
+                out << "            const long e" << s << " = (long)P.gidx[" << s << "][" << nd << " * i]";
+                if (nd > 1) out << " + (long)P.dim[" << sd[0] << "] * ((long)P.gidx[" << s << "][" << nd << " * i + 1]";
+                if (nd > 2) out << " + (long)P.dim[" << sd[1] << "] * (long)P.gidx[" << s << "][" << nd << " * i + 2]";
+                if (nd > 1) out << ")";
+                out << ";\n";
+            }
         }
     }
 };

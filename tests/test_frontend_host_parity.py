@@ -89,3 +89,50 @@ def test_generated_code_matches_oracle_on_the_host(fe_probe, tmp_path, energy, s
     assert abs(cost - ocost) <= (1e-11 if dp else 1e-5) * max(1.0, abs(ocost)), (cost, ocost)
     assert np.abs(jtf - g).max() <= tol * max(1.0, np.abs(g).max())
     assert np.abs(dg - diag).max() <= tol * max(1.0, np.abs(diag).max())
+
+
+GRAPH2D_SPEC = """
+local W, H = Dim("W", 0), Dim("H", 1)
+local X = Unknown("X", opt_float2, { W, H }, 0)
+local T = Array("T", opt_float2, { W, H }, 1)
+local G = Graph("G", 2, "a", { W, H }, 3, "b", { W, H }, 4)
+local w = Param("w", float, 5)
+UsePreconditioner(true)
+Energy(X(0, 0) - T(0, 0))
+Energy(w * (X(G.a) - X(G.b) - 0.5 * T(G.a)))
+"""
+
+
+def test_graph_over_a_2d_index_space_on_the_host(fe_probe, tmp_path):
+    """graph vertices of a 2-D index space are (d0, d1) int32 pairs (the reference's Index struct, o.t:355-387); the generated
+    code, run on the CPU, must match a direct numpy statement of the energy"""
+    W, H, E = 9, 7, 40
+    rng = np.random.default_rng(4)
+    X = rng.normal(size=(H, W, 2)); T = rng.normal(size=(H, W, 2))
+    a = np.stack([rng.integers(0, W, E), rng.integers(0, H, E)], -1).astype(np.int32)      # (x, y) pairs
+    b = np.stack([rng.integers(0, W, E), rng.integers(0, H, E)], -1).astype(np.int32)
+    w = 0.7
+    spec = tmp_path / "graph2d.t"; spec.write_text(GRAPH2D_SPEC)
+    inc = tmp_path / "generated.inc"
+    out = subprocess.run([fe_probe, "--emit", str(inc), str(spec)], capture_output=True, text=True)
+    assert out.returncode == 0 and inc.exists(), out.stdout + out.stderr
+    exe = tmp_path / "spec_eval_host"
+    subprocess.check_call([CXX, "-O1", "-std=c++17", f'-DGEN_SOURCE="{inc}"', "-o", str(exe), os.path.join(ROOT, "tests", "host", "spec_eval_host.cpp"),
+                           os.path.join(ROOT, "opt_b200", "csrc", "frontend.cpp")])
+    data = tmp_path / "params"; data.mkdir()
+    _write_params([X.reshape(-1, 2), T.reshape(-1, 2), E, a, b, w], str(data))
+    res = tmp_path / "out.bin"
+    r = subprocess.run([str(exe), str(spec), str(data), str(res), str(W), str(H)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("COST "), r.stdout + r.stderr
+    cost = float(r.stdout.split()[1])
+    w32 = float(np.float32(w))
+    r0 = X - T
+    xa, xb, ta = X[a[:, 1], a[:, 0]], X[b[:, 1], b[:, 0]], T[a[:, 1], a[:, 0]]
+    r1 = w32 * (xa - xb - 0.5 * ta)
+    ref_cost = 0.5 * (r0 ** 2).sum() + 0.5 * (r1 ** 2).sum()
+    g = r0.copy()
+    np.add.at(g, (a[:, 1], a[:, 0]), w32 * r1)
+    np.add.at(g, (b[:, 1], b[:, 0]), -w32 * r1)
+    jtf = np.fromfile(str(res), np.float64)[:W * H * 2].reshape(H, W, 2)
+    assert abs(cost - ref_cost) <= 1e-12 * ref_cost
+    assert np.abs(jtf - g).max() <= 1e-12 * np.abs(g).max()

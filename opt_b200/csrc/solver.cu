@@ -760,6 +760,7 @@ static EnergyOps<T>* makeEnergy(const std::string& energy, const unsigned* dims)
     // OPTB_GENERIC=1 routes every energy (image_warping included) through the generic cached-Jacobian engine
     if (energy == "image_warping" && !getenv("OPTB_GENERIC")) return makeImageWarping<T>(dims);
     if (energy == "arap_mesh_deformation" && !getenv("OPTB_GENERIC")) return makeArapMesh<T>(dims);
+    if (energy == "robust_nonrigid_alignment" && getenv("OPTB_RNA_HAND") && !getenv("OPTB_GENERIC")) return makeRna<T>(dims);   // hand-written set, opt-in until it has run on hardware
     if (energy == "shape_from_shading" && getenv("OPTB_SFS_HAND") && !getenv("OPTB_GENERIC")) return makeSfs<T>(dims);   // hand-written set, opt-in until it has run on hardware
     return makeGenericEnergy<T>(energy, dims);
 }

@@ -160,6 +160,7 @@ bool compileSpecToCubin(const fe::CompiledSpec& cs, bool doublePrecision, std::v
 template <class T> EnergyOps<T>* makeImageWarping(const unsigned* dims);
 template <class T> EnergyOps<T>* makeArapMesh(const unsigned* dims);
 template <class T> EnergyOps<T>* makeSfs(const unsigned* dims);   // energy_sfs.cu (opt-in: OPTB_SFS_HAND=1)
+template <class T> EnergyOps<T>* makeRna(const unsigned* dims);   // energy_rna.cu (opt-in: OPTB_RNA_HAND=1)
 template <class T> EnergyOps<T>* makeGenericEnergy(const std::string& energy, const unsigned* dims);
 
 }  // namespace optb

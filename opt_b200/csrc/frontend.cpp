@@ -1188,16 +1188,13 @@ CompiledSpec finish(Problem& P) {
     for (const ImageDecl& im : P.images) {
         if (!im.unknown) continue;
         cg.out << "        case " << im.unknownId << ": {\n";
-        bool any = false;
         for (size_t k = 0; k < P.excludes.size(); ++k) {
             if (exInfos[k].dims != im.dims) continue;
             cg.out << "          {\n";
             cg.prologue(exInfos[k], {});
             std::set<int> done; cg.emit(P.excludes[k], done, exInfos[k], true);
             cg.out << "            if (" << cg.v(P.excludes[k]) << " != T(0)) return true;\n          }\n";
-            any = true;
         }
-        (void)any;
         cg.out << "        } break;\n";
     }
     cg.out << "        default: break;\n        }\n        (void)P; (void)i;\n        return false;\n    }\n};\n";

@@ -370,6 +370,83 @@ __device__ __forceinline__ double gridAllReduceLL(double v, unsigned long long* 
     return out;
 }
 
+// Multi-GPU form of gridAllReduceLL (one cooperative kernel per rank, all ranks launch it collectively): the local part is
+// identical; the last CTA of each rank then publishes the RANK's partial to every rank's NVLink mailbox (slot `slot`,
+// sequence k, sender = this rank -- the wire format of publishScalar) instead of a local result slot, and warp 0 of every CTA
+// polls the `world` senders of its own mailbox (one lane per word, as loadScalars2) and adds them in rank order, so every
+// CTA of every rank obtains the bitwise-identical sum.  releaseData additionally makes this CTA's earlier stores -- local
+// ones AND NVLink stores into a neighbour's memory -- visible to every rank after the call (system-scope fences).
+// NOT yet run on hardware (written after the round's GPU budget was spent).
+template <int NT>
+__device__ __forceinline__ double gridAllReduceLLMulti(double v, unsigned long long* words, unsigned long long* arrivals, unsigned long long k, bool releaseData,
+                                                       const CommView& comm, int slot) {
+    static_assert(NT >= kMaxLLCtas && NT % 32 == 0 && NT / 32 <= 32, "one polling thread per CTA slot");
+    static_assert(kMaxRanks == 8, "lane mapping below assumes at most 16 mailbox words per slot");
+    __shared__ double s_warp[NT / 32];
+    __shared__ double s_part[kMaxLLCtas];
+    __shared__ double s_val;
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned long long seq = k & 0xffffffffull;
+    unsigned long long* row = words + (size_t)(k & 1ull) * (2 * (kMaxLLCtas + 1));
+    v = warpSum(v);
+    if (lane == 0) s_warp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double t = lane < NT / 32 ? s_warp[lane] : 0.0;
+        t = warpSum(t);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
+        if (lane < 2) stVolatileU64(row + 2 * blockIdx.x + lane, ((lane ? (bits >> 32) : (bits & 0xffffffffull)) << 32) | seq);
+        if (lane == 0) {
+            if (releaseData) __threadfence_system();
+            const unsigned long long prev = atomicAdd(arrivals, 1ull);
+            s_last = (prev + 1ull == (unsigned long long)gridDim.x * k);
+        }
+    }
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < gridDim.x) {
+            const unsigned long long* src = row + 2 * threadIdx.x;
+            unsigned long long w0, w1, spins = 0;
+            do {
+                w0 = ldVolatileU64(src); w1 = ldVolatileU64(src + 1);
+                if (++spins > (1ull << 24)) __trap();
+            } while ((w0 & 0xffffffffull) != seq || (w1 & 0xffffffffull) != seq);
+            s_part[threadIdx.x] = __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
+        }
+        __syncthreads();
+        if (wid == 0) {
+            double u = 0.0;
+            for (unsigned i = lane; i < gridDim.x; i += 32) u += s_part[i];   // fixed order
+            u = warpSum(u);
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(u);
+            if (releaseData) __threadfence_system();
+            if (lane < 2 * comm.world)   // lane = 2 * destination rank + word
+                stVolatileU64(comm.peerWords[lane >> 1] + mailboxWord(slot, k, comm.rank) + (lane & 1), (((lane & 1) ? (bits >> 32) : (bits & 0xffffffffull)) << 32) | seq);
+        }
+    }
+    if (wid == 0) {
+        unsigned long long w = 0ull;
+        if (lane < 2 * comm.world) {     // lane = 2 * sender + word
+            const unsigned long long* src = comm.peerWords[comm.rank] + mailboxWord(slot, k, lane >> 1) + (lane & 1);
+            unsigned long long spins = 0;
+            do { w = ldVolatileU64(src); if (++spins > (1ull << 26)) __trap(); } while ((w & 0xffffffffull) != seq);   // a lost rank is a bug: fail, do not hang
+        }
+        __syncwarp();
+        const unsigned payload = (unsigned)(w >> 32);
+        double sum = 0.0;
+        for (int r = 0; r < comm.world; ++r) {   // fixed rank order => bitwise identical on every rank
+            const unsigned lo = __shfl_sync(0xffffffffu, payload, 2 * r), hi = __shfl_sync(0xffffffffu, payload, 2 * r + 1);
+            sum += __longlong_as_double((long long)((unsigned long long)lo | ((unsigned long long)hi << 32)));
+        }
+        if (lane == 0) { if (releaseData) __threadfence_system(); s_val = sum; }
+    }
+    __syncthreads();
+    const double out = s_val;
+    __syncthreads();
+    return out;
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with launchPdl may begin while its predecessor on the stream
 // is still draining; it must call pdlWait() before touching anything the predecessor wrote.  Kernels call
 // pdlTrigger() first so that THEIR successor can be scheduled early.  Both are no-ops for ordinary launches.

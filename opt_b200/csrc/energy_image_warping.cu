@@ -22,6 +22,7 @@
 // caller's buffers, never evaluates sin/cos (the reference's generated Step1 evaluates ~5 per
 // pixel), and reads 7 floats + 1 byte per pixel instead of the spec's 9 + mask.  HBM-bound stencil:
 // one thread per pixel over 32x8 tiles, neighbours through L1/L2, persistent grid sized to the SMs.
+#include <algorithm>
 #include <cstdint>
 #include <map>
 #include <type_traits>
@@ -705,21 +706,32 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopResident(IWData<T> D, Redu
 // four sides), so wide images whose row slabs would be all ring still fit (the shape the
 // multi-GPU version needs).  OPT-IN (OPTB_RESIDENT_TILE=WxH) and NOT yet run on hardware: written after the round's GPU
 // budget was spent; the validated default is the row-slab kernel above.
-template <class T, int KMAX>
+// MULTI (one process per GPU, row-slab decomposition, every rank launches this kernel collectively): the tiles cover the
+// rank's OWNED rows [D.y0, D.y1); ring cells in a halo row read the z the neighbouring rank stored there; tiles on the first /
+// last owned row also store their edge row of z into the neighbour's halo row over NVLink; the reductions span all ranks
+// (gridAllReduceLLMulti); and because the per-step path keeps X consistent on halo rows by recomputing delta there
+// (DESIGN.md section 6), boundary tiles accumulate delta for their ring row too ("shadow delta", sH*).
+template <class T> struct IWTileMulti { T* zUp; T* zDn; long upO, upA, dnO, dnA; };   // neighbour z vectors (nullptr: none) and where my edge rows land in them
+constexpr int kLoopMailboxSlot = 8;   // spare scalar slot of CommBlock::words used by the persistent loop's own sequence numbers
+template <class T, int KMAX, bool MULTI>
 __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long* arrivals,
-                                                           unsigned long long k0, int L, int tw, int th, int tilesAcross,
+                                                           unsigned long long k0, int L, int tw, int th, int tilesAcross, IWTileMulti<T> M,
                                                            T* delta, T* r, T* z, T* p, T* Ap, const T* __restrict__ pre) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     constexpr int NT = 1024;
     const int W = D.W, H = D.H, tid = threadIdx.x;
-    const int tx0 = (blockIdx.x % tilesAcross) * tw, ty0 = (blockIdx.x / tilesAcross) * th;
-    const int twE = min(tw, W - tx0), thE = min(th, H - ty0);     // clipped tile (>= 1 x 1 by construction)
+    const int tx0 = (blockIdx.x % tilesAcross) * tw, ty0 = D.y0 + (blockIdx.x / tilesAcross) * th;
+    const int twE = min(tw, W - tx0), thE = min(th, D.y1 - ty0);   // clipped tile (>= 1 x 1 by construction); single GPU: [D.y0, D.y1) = [0, H)
     const int pw = tw + 2;                                        // pitch of the ring-included planes
     const int nRing = (th + 2) * pw, nCap = tw * th;
     T* sPx = reinterpret_cast<T*>(smemRaw); T* sPy = sPx + nRing; T* sPa = sPy + nRing;
     T* sGc = sPa + nRing; T* sGs = sGc + nRing; T* sGx = sGs + nRing; T* sGy = sGx + nRing;
     T* sRx = sGy + nRing; T* sRy = sRx + nCap; T* sRa = sRy + nCap; T* sQo = sRa + nCap; T* sQa = sQo + nCap;
     unsigned char* sF = reinterpret_cast<unsigned char*>(sQa + nCap);
+    // MULTI: shadow delta of the ring row above (side 0) / below (side 1) when that row belongs to a neighbouring rank
+    T* sH = reinterpret_cast<T*>(smemRaw + (((size_t)(nRing * 7 + nCap * 5) * sizeof(T) + nCap + 15) / 16) * 16);   // [2 sides][3 planes][tw]
+    const bool shadowUp = MULTI && M.zUp != nullptr && ty0 == D.y0, shadowDn = MULTI && M.zDn != nullptr && ty0 + thE == D.y1;
+    if (MULTI) for (int c = tid; c < 6 * tw; c += NT) sH[c] = T(0);
     const Vec2<T>* pO = reinterpret_cast<const Vec2<T>*>(p);
     for (int c = tid; c < (thE + 2) * pw; c += NT) {              // ring-included planes; cells outside the image are zero
         const int lr = c / pw, lc = c - lr * pw, gx = tx0 - 1 + lc, gy = ty0 - 1 + lr;
@@ -730,10 +742,11 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWo
     T zx[KMAX], zy[KMAX], za[KMAX], ax[KMAX], ay[KMAX], aa[KMAX], dx[KMAX], dy[KMAX], da[KMAX];
     int ccOf[KMAX]; long giOf[KMAX];                              // ring-plane cell and global pixel index of the thread's pixels (-1: none)
     bool edge[KMAX];                                              // on the tile's perimeter: its z is read by a neighbouring tile
+    bool pushUp[KMAX], pushDn[KMAX];                              // MULTI: first / last owned row with a neighbouring rank beyond it
 #pragma unroll
     for (int q = 0; q < KMAX; ++q) {
         const int c = tid + q * NT;
-        zx[q] = zy[q] = za[q] = ax[q] = ay[q] = aa[q] = dx[q] = dy[q] = da[q] = T(0); edge[q] = false; ccOf[q] = -1; giOf[q] = -1;
+        zx[q] = zy[q] = za[q] = ax[q] = ay[q] = aa[q] = dx[q] = dy[q] = da[q] = T(0); edge[q] = false; ccOf[q] = -1; giOf[q] = -1; pushUp[q] = pushDn[q] = false;
         if (c < nCap) {
             const int ly = c / tw, lx = c - ly * tw;
             if (lx < twE && ly < thE) {
@@ -744,12 +757,19 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWo
                 sF[c] = D.flags[i];
                 const Vec2<T> dO = reinterpret_cast<const Vec2<T>*>(delta)[i]; dx[q] = dO.x; dy[q] = dO.y; da[q] = delta[D.offA + i];
                 edge[q] = (ly == 0 || ly == thE - 1 || lx == 0 || lx == twE - 1);
+                if (MULTI) { pushUp[q] = M.zUp != nullptr && ty0 + ly == D.y0; pushDn[q] = M.zDn != nullptr && ty0 + ly == D.y1 - 1; }
             }
         }
     }
     __syncthreads();
     unsigned long long k = k0;
-    double dRz = ws.scalars[kRz0], dRzPrev = 0.0, dPAp = 0.0;
+    double dRz, dRzPrev = 0.0, dPAp = 0.0;
+    if (MULTI) {   // r.z of PCGInit1 was all-reduced through the mailboxes
+        __shared__ double s_rz0;
+        if (tid == 0) s_rz0 = loadScalarGlobal(ws, kRz0);
+        __syncthreads();
+        dRz = s_rz0;
+    } else dRz = ws.scalars[kRz0];
     const T w2 = D.w * D.w, wf2 = D.wf * D.wf;
     const int nPerim = 2 * (twE + thE);
     for (int l = 0; l < L; ++l) {
@@ -808,9 +828,14 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWo
             }
             ax[q] = ox; ay[q] = oy; aa[q] = oa;
         }
-        dPAp = gridAllReduceLL<NT>((double)acc, llWords, arrivals, ++k, false);
+        dPAp = MULTI ? gridAllReduceLLMulti<NT>((double)acc, llWords, arrivals, ++k, false, ws.comm, kLoopMailboxSlot)
+                     : gridAllReduceLL<NT>((double)acc, llWords, arrivals, ++k, false);
         T alpha = T(0);
         { const T num = (T)dRz, den = (T)dPAp; if (den > T(0)) alpha = num / den; }
+        if (MULTI) {   // shadow delta of the neighbour's row: same alpha, same p (the ring cells) => bitwise the neighbour's own delta
+            if (shadowUp) for (int c = tid; c < twE; c += NT) { const int cc = c + 1; sH[c] += alpha * sPx[cc]; sH[tw + c] += alpha * sPy[cc]; sH[2 * tw + c] += alpha * sPa[cc]; }
+            if (shadowDn) for (int c = tid; c < twE; c += NT) { const int cc = (thE + 1) * pw + c + 1; sH[3 * tw + c] += alpha * sPx[cc]; sH[4 * tw + c] += alpha * sPy[cc]; sH[5 * tw + c] += alpha * sPa[cc]; }
+        }
         acc = T(0);
 #pragma unroll
         for (int q = 0; q < KMAX; ++q) {
@@ -823,10 +848,16 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWo
                 zx[q] = qo * rx; zy[q] = qo * ry; za[q] = sQa[c] * ra;
                 acc += zx[q] * rx; acc += zy[q] * ry; acc += za[q] * ra;
                 if (edge[q]) { stcgV(reinterpret_cast<Vec2<T>*>(z) + giOf[q], Vec2<T>{ zx[q], zy[q] }); stcgT(z + D.offA + giOf[q], za[q]); }
+                if (MULTI && (pushUp[q] || pushDn[q])) {   // my edge row is the neighbouring rank's halo row: store it there over NVLink
+                    const long x = giOf[q] % W;
+                    if (pushUp[q]) { M.zUp[M.upO + 2 * x] = zx[q]; M.zUp[M.upO + 2 * x + 1] = zy[q]; M.zUp[M.upA + x] = za[q]; }
+                    if (pushDn[q]) { M.zDn[M.dnO + 2 * x] = zx[q]; M.zDn[M.dnO + 2 * x + 1] = zy[q]; M.zDn[M.dnA + x] = za[q]; }
+                }
             }
         }
         dRzPrev = dRz;
-        dRz = gridAllReduceLL<NT>((double)acc, llWords, arrivals, ++k, true);
+        dRz = MULTI ? gridAllReduceLLMulti<NT>((double)acc, llWords, arrivals, ++k, true, ws.comm, kLoopMailboxSlot)
+                    : gridAllReduceLL<NT>((double)acc, llWords, arrivals, ++k, true);
     }
     T beta = T(0);
     if (L > 0) { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
@@ -843,7 +874,14 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWo
             reinterpret_cast<Vec2<T>*>(Ap)[i] = Vec2<T>{ ax[q], ay[q] }; Ap[D.offA + i] = aa[q];
         }
     }
-    if (L > 0 && blockIdx.x == 0 && tid == 0) { ws.scalars[kPAp] = dPAp; ws.scalars[L & 1] = dRz; ws.scalars[(L + 1) & 1] = dRzPrev; }
+    if (MULTI) {   // delta of the neighbour's boundary row, so that the update of X on my halo rows matches the owner's
+        if (shadowUp) for (int c = tid; c < twE; c += NT) { const long j = (long)(D.y0 - 1) * W + tx0 + c; reinterpret_cast<Vec2<T>*>(delta)[j] = Vec2<T>{ sH[c], sH[tw + c] }; delta[D.offA + j] = sH[2 * tw + c]; }
+        if (shadowDn) for (int c = tid; c < twE; c += NT) { const long j = (long)D.y1 * W + tx0 + c; reinterpret_cast<Vec2<T>*>(delta)[j] = Vec2<T>{ sH[3 * tw + c], sH[4 * tw + c] }; delta[D.offA + j] = sH[5 * tw + c]; }
+    }
+    // single GPU: leave the scalars as the per-step loop does.  MULTI: the per-step loop keeps them in the mailboxes with their own
+    // epochs; this kernel's sequence lives in a spare slot, so kRz0/kRz1/kPAp keep the values PCGInit1 published (nothing reads them
+    // before the next PCGInit1 except the debugging read-back)
+    if (!MULTI && L > 0 && blockIdx.x == 0 && tid == 0) { ws.scalars[kPAp] = dPAp; ws.scalars[L & 1] = dRz; ws.scalars[(L + 1) & 1] = dRzPrev; }
 }
 
 // ------------------------------------------------------------------------------------ computeCost
@@ -1068,11 +1106,13 @@ struct ImageWarpingOps : EnergyOps<T> {
         OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)resGrid), dim3(1024), args, resSmem, c.stream));
         return true;
     }
-    // 2-D tile variant (opt-in, OPTB_RESIDENT_TILE=WxH): own sequence/arrival state because its grid size differs
+    // 2-D tile variant (opt-in, OPTB_RESIDENT_TILE=WxH; chosen automatically for the multi-GPU form): own sequence/arrival
+    // state because its grid size differs
     int tileW = 0, tileH = 0, tileGrid = 0, tileK = 0, tileAcross = 0; size_t tileSmem = 0; unsigned long long* tileWords = nullptr; unsigned long long tileSeq = 0;
-    template <int KMAX>
-    bool launchTileK(const LaunchCtx& c, int L, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
-        const void* fn = (const void*)k_iwPcgLoopTile<T, KMAX>;
+    bool tileMulti = false;
+    template <int KMAX, bool MULTI>
+    bool launchTileK(const LaunchCtx& c, int L, const IWTileMulti<T>& M, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
+        const void* fn = (const void*)k_iwPcgLoopTile<T, KMAX, MULTI>;
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileSmem) != cudaSuccess) { cudaGetLastError(); return false; }
         int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 1024, tileSmem);
         int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1082,30 +1122,60 @@ struct ImageWarpingOps : EnergyOps<T> {
         unsigned long long* arrivals = tileWords + 4 * (kMaxLLCtas + 1);
         unsigned long long k0 = tileSeq; tileSeq += 2ull * (unsigned long long)L;
         ReduceWorkspace ws = c.ws;
-        void* args[] = { (void*)&D, (void*)&ws, (void*)&tileWords, (void*)&arrivals, (void*)&k0, (void*)&L, (void*)&tileW, (void*)&tileH, (void*)&tileAcross,
+        IWTileMulti<T> Mv = M;
+        void* args[] = { (void*)&D, (void*)&ws, (void*)&tileWords, (void*)&arrivals, (void*)&k0, (void*)&L, (void*)&tileW, (void*)&tileH, (void*)&tileAcross, (void*)&Mv,
                          (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre };
         OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)tileGrid), dim3(1024), args, tileSmem, c.stream));
         return true;
     }
-    bool launchTile(const LaunchCtx& c, int L, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
-        const char* spec = getenv("OPTB_RESIDENT_TILE");
-        if (!spec) return false;
-        if (tileW == 0) {
-            int a = 0, b = 0;
-            if (sscanf(spec, "%dx%d", &a, &b) != 2 || a < 1 || b < 1) { tileW = -1; return false; }
-            tileW = a; tileH = b; tileAcross = (D.W + a - 1) / a; tileGrid = tileAcross * ((D.H + b - 1) / b);
-            const size_t nRing = (size_t)(b + 2) * (a + 2), nCap = (size_t)a * b;
-            tileSmem = ((nRing * 7 + nCap * 5) * sizeof(T) + nCap + 15) / 16 * 16;
-            tileK = (int)((nCap + 1023) / 1024);
-            int dev = 0, maxSmem = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-            if (tileSmem > (size_t)maxSmem || tileK > 4 || tileGrid > kMaxLLCtas) tileW = -1;
+    size_t tileSmemFor(int a, int b, bool multi) const {
+        const size_t nRing = (size_t)(b + 2) * (a + 2), nCap = (size_t)a * b;
+        size_t bytes = ((nRing * 7 + nCap * 5) * sizeof(T) + nCap + 15) / 16 * 16;
+        if (multi) bytes += (size_t)6 * a * sizeof(T);
+        return (bytes + 15) / 16 * 16;
+    }
+    bool chooseTile(bool multi) {   // fills tileW/H/...; false when no shape fits
+        int dev = 0, maxSmem = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int rows = D.y1 - D.y0, maxTiles = std::min(sms, kMaxLLCtas);
+        auto fits = [&](int a, int b) {
+            const long tiles = (long)((D.W + a - 1) / a) * ((rows + b - 1) / b);
+            return tiles <= maxTiles && (long)a * b <= 4096 && tileSmemFor(a, b, multi) + 4096 <= (size_t)maxSmem;
+        };
+        int a = 0, b = 0;
+        if (const char* spec = getenv("OPTB_RESIDENT_TILE")) { if (sscanf(spec, "%dx%d", &a, &b) != 2 || a < 1 || b < 1 || !fits(a, b)) return false; }
+        else {
+            if (!multi) return false;                       // single GPU: the row-slab kernel is the default, tiles only on request
+            bool found = false;
+            const int widths[6] = { D.W, 1024, 512, 256, 128, 64 };
+            for (int aw : widths) {   // widest tiles first: fewest ring cells per pixel for a given area
+                if (aw > D.W) continue;
+                for (int bh = 1; bh <= rows && !found; ++bh) if (fits(aw, bh)) { a = aw; b = bh; found = true; }
+                if (found) break;
+            }
+            if (!found) return false;
         }
+        tileW = a; tileH = b; tileAcross = (D.W + a - 1) / a; tileGrid = tileAcross * ((rows + b - 1) / b);
+        tileSmem = tileSmemFor(a, b, multi); tileK = (int)(((size_t)a * b + 1023) / 1024); tileMulti = multi;
+        return true;
+    }
+    bool launchTile(const LaunchCtx& c, int L, const HaloPlan* haloZ, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
+        const bool multi = haloZ != nullptr;
+        if (tileW == 0 || tileMulti != multi) { if (!chooseTile(multi)) { tileW = -1; tileMulti = multi; } }
         if (tileW < 0) return false;
-        return tileK <= 2 ? launchTileK<2>(c, L, delta, r, z, p, Ap, pre) : launchTileK<4>(c, L, delta, r, z, p, Ap, pre);
+        IWTileMulti<T> M{};
+        if (multi) {   // where my first / last owned row lands in the neighbours' z vectors: the destinations of haloSegments()
+            M.zUp = (T*)haloZ->peerVec[0]; M.zDn = (T*)haloZ->peerVec[1];
+            const long W = D.W;
+            M.upO = 2 * W * (upperRows - 1); M.upA = alignUp64(2 * W * upperRows) + W * (upperRows - 1);
+            M.dnO = 0; M.dnA = alignUp64(2 * W * lowerRows);
+            return tileK <= 2 ? launchTileK<2, true>(c, L, M, delta, r, z, p, Ap, pre) : launchTileK<4, true>(c, L, M, delta, r, z, p, Ap, pre);
+        }
+        return tileK <= 2 ? launchTileK<2, false>(c, L, M, delta, r, z, p, Ap, pre) : launchTileK<4, false>(c, L, M, delta, r, z, p, Ap, pre);
     }
     bool launchResident(const LaunchCtx& c, int L, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
         if (getenv("OPTB_NO_RESIDENT")) return false;
-        if (launchTile(c, L, delta, r, z, p, Ap, pre)) return true;
+        if (launchTile(c, L, nullptr, delta, r, z, p, Ap, pre)) return true;
         if (resR == 0) {
             int dev = 0, sms = 148, maxSmem = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -1121,8 +1191,16 @@ struct ImageWarpingOps : EnergyOps<T> {
     }
     // persistent whole-loop kernel (single GPU, GN): see k_iwPcgLoop
     LoopSync* loopSync = nullptr; unsigned long long loopSeq = 0; int gridLoop = 0; int coopOk = -1;
-    bool pcgLoop(const LaunchCtx& c, int L, bool force, T* delta, T* r, T* z, T* p, T* p2, T* Ap, const T* pre, T** pFinal) override {
-        if (L <= 0 || D.y0 != 0 || D.y1 != D.H) return false;
+    bool pcgLoop(const LaunchCtx& c, int L, bool force, T* delta, T* r, T* z, T* p, T* p2, T* Ap, const T* pre, T** pFinal, const HaloPlan* haloZ) override {
+        if (L <= 0) return false;
+        if (haloZ) {   // multi-GPU: only the tile kernel has a multi-rank form, and only on request (not yet run on hardware)
+            if (!force) return false;
+            int dev = 0, coop = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+            if (!coop || !launchTile(c, L, haloZ, delta, r, z, p, Ap, pre)) return false;
+            *pFinal = p;
+            return true;
+        }
+        if (D.y0 != 0 || D.y1 != D.H) return false;
         if (coopOk < 0) {
             int dev = 0, coop = 0, sms = 148, occ = 0;
             cudaGetDevice(&dev); cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -517,9 +517,10 @@ struct Plan : PlanBase {
     void runLoop(int L) {
         bool fuse = loopFuses();
         OPT_CUDA_CHECK(cudaEventRecord(evLoop0, stream));
-        if (persistentMode != 0 && !lm && world == 1 && L > 0) {   // whole loop as one cooperative kernel where the energy offers it
+        if (persistentMode != 0 && !lm && L > 0 && (world == 1 || persistentMode > 0)) {   // whole loop as one cooperative kernel where the energy offers it
             T* pf = nullptr;
-            if (E->pcgLoop(ctx(), L, persistentMode > 0, delta, r, z, p, p2, Ap, pre, &pf)) {
+            if (world > 1 && !pHaloFresh) { exchangeHalo(haloP, p); pHaloFresh = true; }   // the multi-rank form stages p's halo rows from memory
+            if (E->pcgLoop(ctx(), L, persistentMode > 0, delta, r, z, p, p2, Ap, pre, &pf, world > 1 ? &haloZ : nullptr)) {
                 pFinal = pf; ++launches;
                 OPT_CUDA_CHECK(cudaEventRecord(evLoop1, stream));
                 return;
@@ -546,7 +547,7 @@ struct Plan : PlanBase {
         }
         OPT_CUDA_CHECK(cudaEventRecord(evLoop1, stream));
     }
-    int loopLaunchCount = 0; T* loopPFinal = nullptr;
+    int loopLaunchCount = 0; T* loopPFinal = nullptr; bool pHaloFresh = false;
     // ---- collectPerKernelTimingInfo (util.t:405-511, :820-842): event pairs aggregated by name in first-seen order and
     // printed when the solve ends (verbosity > 0), in the reference's table format.
     struct TimedLaunch { const char* name; cudaEvent_t a, b; };
@@ -610,7 +611,8 @@ struct Plan : PlanBase {
             k_setScalar<<<1, 1, 0, stream>>>(ws, kFlags, 0.0); launches += 2;
         }
         int L = sp.lIterations; if (maxLinIters >= 0 && maxLinIters < L) L = maxLinIters;
-        if (!(world > 1 && loopFuses() && E->inKernelHalo() && L > 0)) exchangeHalo(haloP, p);   // initial direction on the halo rows
+        pHaloFresh = false;
+        if (!(world > 1 && loopFuses() && E->inKernelHalo() && L > 0)) { exchangeHalo(haloP, p); pHaloFresh = true; }   // initial direction on the halo rows
         if (!timingFine) tBegin("PCG loop");
         runLoop(L);
         if (!timingFine) tEnd();

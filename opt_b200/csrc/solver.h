@@ -88,8 +88,9 @@ struct EnergyOps {
     // p/p2 are the two direction buffers (p holds the initial direction); *pFinal receives the buffer holding p
     // afterwards; the scalars kRz0/kRz1/kPAp are left exactly as the kernel-per-step loop would leave them.
     // Returns false (nothing launched) when not implemented / not applicable; `force` overrides the size heuristic.
+    // haloZ != nullptr: multi-GPU (the plan's halo description of z, host copy); p's halo rows have been exchanged by the caller.
     virtual bool pcgLoop(const LaunchCtx&, int /*L*/, bool /*force*/, T* /*delta*/, T* /*r*/, T* /*z*/, T* /*p*/, T* /*p2*/, T* /*Ap*/,
-                         const T* /*pre*/, T** /*pFinal*/) { return false; }
+                         const T* /*pre*/, T** /*pFinal*/, const HaloPlan* /*haloZ*/ = nullptr) { return false; }
     // computeCost (+_Graph): scalars[kCost] = 1/2 sum r^2
     virtual void cost(const LaunchCtx& c) = 0;
     // LM: CtC <- diag(J^T J)/radius (PCGComputeCtC), scalars[kModelCost] = 1/2 sum (r + J delta)^2

@@ -77,6 +77,8 @@ def main():
     while s.step(dev):
         costs.append(s.current_cost())
     torch.cuda.synchronize()
+    launches = s.launches_last_step()
+    max_launches = int(os.environ.get("OPTB_TEST_MAX_LAUNCHES", "0"))    # > 0: the caller expects the one-launch persistent loop
     off = gather_owned_rows(dev[0].cpu().numpy().reshape(-1, 2), W, slab).reshape(-1, 2)
     ang = gather_owned_rows(dev[1].cpu().numpy(), W, slab).reshape(-1)
     all_costs = [None] * world
@@ -96,6 +98,9 @@ def main():
         print(f"multi_gpu_check world={world} {W}x{H} {kind}: costs {costs[0]:.6f} -> {costs[-1]:.6f}; vs 1 GPU: cost rel {rel_c:.2e}, Offset {e_off:.2e}, Angle {e_ang:.2e}")
         print("  multi :", [f"{c:.6g}" for c in costs]); print("  single:", [f"{c:.6g}" for c in c1])
         ok = rel_c < 1e-4 and e_off < 1e-5 and e_ang < 2e-3 and len(costs) == len(c1)
+        print(f"  launches in the last step: {launches}")
+        if max_launches > 0 and launches > max_launches:
+            print(f"  expected at most {max_launches} launches: the persistent multi-GPU loop was not taken"); ok = False
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

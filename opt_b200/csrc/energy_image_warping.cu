@@ -1194,6 +1194,9 @@ struct ImageWarpingOps : EnergyOps<T> {
     bool pcgLoop(const LaunchCtx& c, int L, bool force, T* delta, T* r, T* z, T* p, T* p2, T* Ap, const T* pre, T** pFinal, const HaloPlan* haloZ) override {
         if (L <= 0) return false;
         if (haloZ) {   // multi-GPU: only the tile kernel has a multi-rank form, and only on request (not yet run on hardware)
+            // NOTE: the ranks must all take the same branch (the kernel's reductions are collective).  The decision depends on the
+            // slab height only, so equal slabs (H divisible by the number of ranks -- bench.py, the tests) decide alike; with
+            // unequal slabs a rank that does not fit would fall back alone: make the decision collective before this becomes a default.
             if (!force) return false;
             int dev = 0, coop = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
             if (!coop || !launchTile(c, L, haloZ, delta, r, z, p, Ap, pre)) return false;

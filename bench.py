@@ -87,8 +87,49 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(steps=1, rows=256, pcg_iters=4):
-    """times the CPU oracle (port) on a W_FULL x rows slab of the workload; returns PCG steps/s scaled to the full image"""
+def cpu_sample_reference(rows=256, pcg_iters=4, target_seconds=0.0):
+    """kind "reference": matrix-free PCG steps built from the reference's OWN per-pixel functions (examples/image_warping/src/
+    WarpingSolverEquations.h: evalMinusJTFDevice, applyJTJDevice) compiled for the host into oracle/_ref/libref_iw.so
+    (oracle/ref_build.sh, oracle/ref_iw_shim.cpp ref_iw_pcg), OpenMP over the pixels, on a W_FULL x rows slab.
+    Returns None when the library is not there (it is built where /root/reference is mounted and travels with the snapshot)."""
+    import ctypes
+    import numpy as np
+    from opt_b200 import workloads
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libref_iw.so")
+    if not os.path.exists(so):
+        return None
+    L = ctypes.CDLL(so)
+    if not hasattr(L, "ref_iw_pcg"):
+        return None
+    L.ref_iw_pcg.restype = ctypes.c_double
+    host = workloads.image_warping(W_FULL, rows, seed=0, mask="none", n_constraints=3)
+    off, ang, ur, cons, m, wf, wr = host[0], host[1], host[2], host[3], host[4], host[5], host[6]
+    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    nt = ctypes.c_int(0); rz = ctypes.c_double(0)
+    t0 = time.time()
+    # the hand-written solver takes the UNSQUARED weights (its energy is sum w r^2, twice Opt's convention: oracle/ref_iw_shim.cpp)
+    call = lambda n: L.ref_iw_pcg(ctypes.c_int(W_FULL), ctypes.c_int(rows), fp(off), fp(ang), fp(ur), fp(m), fp(cons), ctypes.c_float(wf * wf), ctypes.c_float(wr * wr),
+                                  ctypes.c_int(n), ctypes.byref(nt), ctypes.byref(rz))
+    if target_seconds > 0:      # size the sample: a short calibration run, then enough iterations for about target_seconds of CPU work
+        cal = call(4)
+        pcg_iters = int(min(2000, max(pcg_iters, target_seconds / max(cal / 4, 1e-6))))
+    sec = call(pcg_iters)
+    wall = time.time() - t0
+    if not (sec > 0) or not np.isfinite(rz.value):
+        return None
+    full_rate = (pcg_iters / sec) * rows / H_FULL           # cost is linear in pixels
+    return {"value": full_rate, "unit": "PCG steps/s", "cores": int(nt.value), "kind": "reference",
+            "sample": f"the reference's own evalMinusJTFDevice/applyJTJDevice (WarpingSolverEquations.h, compiled for the host: oracle/_ref) in a matrix-free "
+                      f"PCG with OpenMP over the pixels, {W_FULL}x{rows} slab, {pcg_iters} PCG steps in {sec:.2f}s (wall incl. set-up {wall:.1f}s), "
+                      f"scaled by {rows}/{H_FULL} to the full image"}, wall
+
+
+def cpu_sample(steps=1, rows=256, pcg_iters=4, target_seconds=10.0):
+    """CPU baseline on a W_FULL x rows slab of the workload, PCG steps/s scaled to the full image: the reference's own equations on the
+    host when oracle/_ref is there (kind "reference"), else the CPU oracle (kind "port")"""
+    ref = cpu_sample_reference(rows=rows, pcg_iters=max(pcg_iters, 8), target_seconds=target_seconds)
+    if ref is not None:
+        return ref
     from opt_b200 import workloads
     from oracle.oracle import Oracle, num_threads
     host = workloads.image_warping(W_FULL, rows, seed=0, mask="none", n_constraints=3)
@@ -123,7 +164,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "pcg_steps_per_s", "value": rate, "unit": "PCG steps/s", "n_gpus": args.gpus,
             "steps": len(timed), "warmup": args.warmup, "ms_per_step": 1000.0 * L_ITERS / rate, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"image_warping {W_FULL}x{H_FULL} fp32 GN, lIterations={L_ITERS}", "note": "CPU port of the reference solver on host cores; bounded slab sample scaled to the full image"},
+            "config": {"workload": f"image_warping {W_FULL}x{H_FULL} fp32 GN, lIterations={L_ITERS}", "note": "reference arm on host cores (cpu_baseline.kind says which code: the reference's own equations from oracle/_ref, else the oracle port); bounded slab sample scaled to the full image"},
             "cpu_baseline": cb, "e2e": {"value": rate, "unit": "PCG steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

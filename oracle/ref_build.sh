@@ -8,7 +8,7 @@ REF=/root/reference
 [ -d "$REF" ] || { echo "ref_build: $REF not mounted, keeping prebuilt oracle/_ref"; exit 0; }
 mkdir -p "$HERE/_ref"
 CXX=/usr/bin/g++
-FLAGS="-O2 -fPIC -shared -std=c++14 -w -I/usr/local/cuda/include"
+FLAGS="-O2 -fopenmp -fPIC -shared -std=c++14 -w -I/usr/local/cuda/include"
 if [ ! -f "$HERE/_ref/libref_iw.so" ] || [ "$HERE/ref_iw_shim.cpp" -nt "$HERE/_ref/libref_iw.so" ]; then
   $CXX $FLAGS -I"$REF/examples/image_warping/src" -o "$HERE/_ref/libref_iw.so" "$HERE/ref_iw_shim.cpp"
 fi

@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 static inline float __shfl_down(float v, int, int) { return v; }
 static inline void __syncthreads() {}
 #include "WarpingSolverState.h"
@@ -39,5 +42,75 @@ void ref_iw_applyjtj(int W, int H, float2* x, float* A, float2* urshape, float* 
         if (mask[i] == 0) { float a; out[i] = applyJTJDevice(i, in, st, pr, a); outA[i] = a; }
         else { out[i] = make_float2(0, 0); outA[i] = 0; }
     }
+}
+// Matrix-free PCG iterations timed on the host cores, built from the reference's OWN per-pixel functions
+// (evalMinusJTFDevice for the right-hand side and its inverted Jacobi preconditioner, applyJTJDevice for A p): the same call
+// sequence as the hand-written solver's PCGInit_Kernel1/2 and PCGStep_Kernel1/2/3 (WarpingSolver.cu:87-260), with the
+// kernels' thread grids replaced by OpenMP loops over the pixels.  This is bench.py's CPU baseline of kind "reference":
+// the reference's own arithmetic for PCGStep1, run on the CPU.  Returns the seconds spent in `steps` iterations
+// (the initialisation is not timed); *threads = OpenMP threads used; *rz = r.z after the last step (so the loop cannot be
+// optimised away and the caller can see that it converges).
+double ref_iw_pcg(int W, int H, float2* x, float* A, float2* urshape, float* mask, float2* constraints, float weightFit, float weightReg,
+                  int steps, int* threads, double* rzOut) {
+    const int N = W * H;
+    SolverInput in; in.N = N; in.width = W; in.height = H; in.d_constraints = constraints;
+    SolverParameters pr; pr.weightFitting = weightFit; pr.weightRegularizer = weightReg; pr.nNonLinearIterations = 0; pr.nLinIterations = 0;
+    std::vector<float2> delta(N), r(N), z(N), p(N), Ap(N), pre(N);
+    std::vector<float> deltaA(N), rA(N), zA(N), pA(N), ApA(N), preA(N);
+    SolverState st{}; st.d_x = x; st.d_A = A; st.d_urshape = urshape; st.d_mask = mask; st.d_delta = delta.data(); st.d_deltaA = deltaA.data();
+    st.d_precondioner = pre.data(); st.d_precondionerA = preA.data(); st.d_p = p.data(); st.d_pA = pA.data();
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+#endif
+    if (threads) *threads = nt;
+    double rz = 0;
+#pragma omp parallel for reduction(+ : rz) schedule(static)
+    for (int i = 0; i < N; ++i) {
+        float2 b = make_float2(0, 0); float bA = 0;
+        if (mask[i] == 0) { SolverInput in_ = in; SolverState st_ = st; SolverParameters pr_ = pr; b = evalMinusJTFDevice(i, in_, st_, pr_, bA); }
+        else { pre[i] = make_float2(0, 0); preA[i] = 0; delta[i] = make_float2(0, 0); deltaA[i] = 0; }
+        r[i] = b; rA[i] = bA;
+        p[i] = make_float2(pre[i].x * b.x, pre[i].y * b.y); pA[i] = preA[i] * bA;
+        rz += (double)b.x * p[i].x + (double)b.y * p[i].y + (double)bA * pA[i];
+    }
+    double t0 = 0, t1 = 0;
+#ifdef _OPENMP
+    t0 = omp_get_wtime();
+#else
+    t0 = (double)clock() / CLOCKS_PER_SEC;
+#endif
+    for (int it = 0; it < steps; ++it) {
+        double pAp = 0;
+#pragma omp parallel for reduction(+ : pAp) schedule(static)
+        for (int i = 0; i < N; ++i) {                                   // PCGStep_Kernel1: Ap = J^T J p, p.Ap
+            float2 o = make_float2(0, 0); float oA = 0;
+            if (mask[i] == 0) { SolverInput in_ = in; SolverState st_ = st; SolverParameters pr_ = pr; o = applyJTJDevice(i, in_, st_, pr_, oA); }
+            Ap[i] = o; ApA[i] = oA;
+            pAp += (double)p[i].x * o.x + (double)p[i].y * o.y + (double)pA[i] * oA;
+        }
+        const float alpha = pAp > 0 ? (float)(rz / pAp) : 0.f;
+        double rzNew = 0;
+#pragma omp parallel for reduction(+ : rzNew) schedule(static)
+        for (int i = 0; i < N; ++i) {                                   // PCGStep_Kernel2: delta, r, z, r.z
+            delta[i].x += alpha * p[i].x; delta[i].y += alpha * p[i].y; deltaA[i] += alpha * pA[i];
+            r[i].x -= alpha * Ap[i].x; r[i].y -= alpha * Ap[i].y; rA[i] -= alpha * ApA[i];
+            z[i] = make_float2(pre[i].x * r[i].x, pre[i].y * r[i].y); zA[i] = preA[i] * rA[i];
+            rzNew += (double)z[i].x * r[i].x + (double)z[i].y * r[i].y + (double)zA[i] * rA[i];
+        }
+        const float beta = rz > 0 ? (float)(rzNew / rz) : 0.f;
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < N; ++i) {                                   // PCGStep_Kernel3: p = z + beta p
+            p[i].x = z[i].x + beta * p[i].x; p[i].y = z[i].y + beta * p[i].y; pA[i] = zA[i] + beta * pA[i];
+        }
+        rz = rzNew;
+    }
+#ifdef _OPENMP
+    t1 = omp_get_wtime();
+#else
+    t1 = (double)clock() / CLOCKS_PER_SEC;
+#endif
+    if (rzOut) *rzOut = rz;
+    return t1 - t0;
 }
 }

@@ -12,3 +12,6 @@ FLAGS="-O2 -fopenmp -fPIC -shared -std=c++14 -w -I/usr/local/cuda/include"
 if [ ! -f "$HERE/_ref/libref_iw.so" ] || [ "$HERE/ref_iw_shim.cpp" -nt "$HERE/_ref/libref_iw.so" ]; then
   $CXX $FLAGS -I"$REF/examples/image_warping/src" -o "$HERE/_ref/libref_iw.so" "$HERE/ref_iw_shim.cpp"
 fi
+if [ ! -f "$HERE/_ref/libref_arap.so" ] || [ "$HERE/ref_arap_shim.cpp" -nt "$HERE/_ref/libref_arap.so" ]; then
+  $CXX $FLAGS -I"$REF/examples/arap_mesh_deformation/src" -o "$HERE/_ref/libref_arap.so" "$HERE/ref_arap_shim.cpp"
+fi

@@ -1,22 +1,22 @@
--- 3-D as-rigid-as-possible mesh deformation over a vertex graph (opt_b200 test spec; same energy
--- and parameter positions as the arap_mesh_deformation example of niessner/Opt).
---   params: 0 w_fitSqrt  1 w_regSqrt  2 Offset (unknown)  3 Angle (unknown)  4 UrShape  5 Constraints
---           6 edge count  7 v0 indices  8 v1 indices
-local N = Dim("N", 0)
-local w_fitSqrt   = Param("w_fitSqrt", float, 0)
-local w_regSqrt   = Param("w_regSqrt", float, 1)
-local Offset      = Unknown("Offset", opt_float3, { N }, 2)
-local Angle       = Unknown("Angle", opt_float3, { N }, 3)
-local UrShape     = Array("UrShape", opt_float3, { N }, 4)
-local Constraints = Array("Constraints", opt_float3, { N }, 5)
-local G = Graph("G", 6, "v0", { N }, 7, "v1", { N }, 8)
+-- As-rigid-as-possible deformation of a triangle mesh given as a vertex graph (test specification of opt_b200; the parameter
+-- table matches the arap_mesh_deformation example of niessner/Opt).
+--   slot 0 / 1: square roots of the handle and rigidity weights
+--   slot 2: vertex positions, UNKNOWN      slot 3: vertex Euler angles, UNKNOWN      slot 4: rest positions
+--   slot 5: handle targets (x below -999999.9 = free vertex)      slot 6: number of directed edges      slots 7, 8: edge tail / head
+local verts = { Dim("N", 0) }
+local sqrtHandle, sqrtRigid = Param("w_fitSqrt", float, 0), Param("w_regSqrt", float, 1)
+local pos    = Unknown("Offset", opt_float3, verts, 2)
+local euler  = Unknown("Angle", opt_float3, verts, 3)
+local rest   = Array("UrShape", opt_float3, verts, 4)
+local handle = Array("Constraints", opt_float3, verts, 5)
+local edges  = Graph("G", 6, "v0", verts, 7, "v1", verts, 8)
 UsePreconditioner(true)
 
--- handle vertices: first channel below -999999.9 means "free vertex"
-local isHandle = greatereq(Constraints(0, 0), -999999.9)
-Energy(Select(isHandle, w_fitSqrt * (Offset(0) - Constraints(0)), 0))
+-- handle vertices are pulled to their targets
+local grabbed = greatereq(handle(0, 0), -999999.9)
+Energy(Select(grabbed, sqrtHandle * (pos(0) - handle(0)), 0))
 
--- per directed edge: rotated rest edge must match the deformed edge
-local restEdge = UrShape(G.v0) - UrShape(G.v1)
-local nowEdge = Offset(G.v0) - Offset(G.v1)
-Energy(w_regSqrt * (nowEdge - Rotate3D(Angle(G.v0), restEdge)))
+-- along every directed edge the deformed edge should be the rest edge turned by the tail vertex's rotation
+local tail, head = edges.v0, edges.v1
+local turned = Rotate3D(euler(tail), rest(tail) - rest(head))
+Energy(sqrtRigid * ((pos(tail) - pos(head)) - turned))

@@ -1,15 +1,15 @@
--- Poisson image blending (opt_b200 test spec; same energy and parameter positions as the
--- poisson_image_editing example of niessner/Opt).  params: 0 X (unknown, 4ch)  1 T  2 M
-local W = Dim("W", 0)
-local H = Dim("H", 1)
-local X = Unknown("X", opt_float4, { W, H }, 0)
-local T = Array("T", opt_float4, { W, H }, 1)
-local M = Array("M", opt_float, { W, H }, 2)
+-- Seamless cloning: inside the blend region the result must have the gradients of the inserted image (test specification of
+-- opt_b200; the parameter table matches the poisson_image_editing example of niessner/Opt).
+--   slot 0: result, 4 channels, UNKNOWN      slot 1: inserted image, 4 channels      slot 2: mask (0 = inside the blend region)
+local canvas = { Dim("W", 0), Dim("H", 1) }
+local result  = Unknown("X", opt_float4, canvas, 0)
+local source  = Array("T", opt_float4, canvas, 1)
+local regionMask = Array("M", opt_float, canvas, 2)
 UsePreconditioner(false)
-Exclude(Not(eq(M(0, 0), 0)))
--- gradients of the result must match gradients of the inserted image
-for dx, dy in Stencil { { 1, 0 }, { -1, 0 }, { 0, 1 }, { 0, -1 } } do
-    local gradX = X(0, 0) - X(dx, dy)
-    local gradT = T(0, 0) - T(dx, dy)
-    Energy(Select(InBounds(dx, dy), gradX - gradT, 0))
+Exclude(Not(eq(regionMask(0, 0), 0)))
+
+local function difference(img, dx, dy) return img(0, 0) - img(dx, dy) end
+for _, d in ipairs({ { 1, 0 }, { -1, 0 }, { 0, 1 }, { 0, -1 } }) do
+    local mismatch = difference(result, d[1], d[2]) - difference(source, d[1], d[2])
+    Energy(Select(InBounds(d[1], d[2]), mismatch, 0))
 end

@@ -1,83 +1,63 @@
--- shape-from-shading depth refinement (opt_b200 test spec; same energy and parameter positions as the
--- shape_from_shading example of niessner/Opt).
---   params: 0 w_p  1 w_s  2 w_g  3 f_x  4 f_y  5 u_x  6 u_y  7..15 L_1..L_9 (all float)
---           16 X (unknown depth)  17 D_i  18 Im  19 edgeMaskR (uint8)  20 edgeMaskC (uint8)
-local W = Dim("W", 0)
-local H = Dim("H", 1)
-local dom = { W, H }
-local sqrt_w_p = sqrt(Param("w_p", float, 0))
-local sqrt_w_s = sqrt(Param("w_s", float, 1))
-local sqrt_w_g = sqrt(Param("w_g", float, 2))
-local f_x = Param("f_x", float, 3)
-local f_y = Param("f_y", float, 4)
-local u_x = Param("u_x", float, 5)
-local u_y = Param("u_y", float, 6)
-local light = {}
-for k = 1, 9 do
-    light[k] = Param("L_" .. k .. "", float, 6 + k)
+-- Depth refinement from shading (test specification of opt_b200; the parameter table matches the shape_from_shading example of
+-- niessner/Opt).  The rendered shading of the refined depth (second-order spherical harmonics of the surface normal) must
+-- reproduce the intensity gradients of the colour image, while the depth stays near the sensor depth and locally smooth.
+--   slots 0..2: weights of the depth, smoothness and shading terms (their square roots are used)
+--   slots 3..6: camera intrinsics f_x, f_y, u_x, u_y          slots 7..15: nine lighting coefficients
+--   slot 16: refined depth, UNKNOWN      slot 17: sensor depth (<= 0: no measurement)      slot 18: intensity
+--   slots 19, 20: uint8 masks that switch the horizontal / vertical shading-gradient term off across image edges
+local image = { Dim("W", 0), Dim("H", 1) }
+local function scalar(label, slot) return Param(label, float, slot) end
+local sqrtDepth, sqrtSmooth, sqrtShade = sqrt(scalar("w_p", 0)), sqrt(scalar("w_s", 1)), sqrt(scalar("w_g", 2))
+local fx, fy, cx, cy = scalar("f_x", 3), scalar("f_y", 4), scalar("u_x", 5), scalar("u_y", 6)
+local sh = {}
+for k = 1, 9 do sh[k] = scalar("L_" .. k .. "", 6 + k) end
+local depth     = Unknown("X", opt_float, image, 16)
+local sensor    = Array("D_i", opt_float, image, 17)
+local intensity = Array("Im", opt_float, image, 18)
+local keepAcrossRows = Array("edgeMaskR", uint8, image, 19)
+local keepAcrossCols = Array("edgeMaskC", uint8, image, 20)
+
+local u, v = Index(0), Index(1)
+local discontinuity = 0.01
+local function measured(dx, dy) return greater(sensor(dx, dy), 0) end
+Exclude(Not(measured(0, 0)))
+
+-- unnormalised normal from the depths at a pixel, its left and its upper neighbour; then normalised where it has a length
+local function unitNormal(dx, dy)
+    local here, left, up = depth(dx, dy), depth(dx - 1, dy), depth(dx, dy - 1)
+    local a = up * (here - left) / fy
+    local b = left * (here - up) / fx
+    local c = (a * (cx - (dx + u)) / fx) + (b * (cy - (dy + v)) / fy) - (left * up / (fx * fy))
+    local sq = a * a + b * b + c * c
+    return Select(greater(sq, 0.0), 1.0 / sqrt(sq), 1.0) * Vector(a, b, c)
 end
-local X         = Unknown("X", opt_float, dom, 16)
-local D_i       = Array("D_i", opt_float, dom, 17)
-local Im        = Array("Im", opt_float, dom, 18)
-local edgeMaskR = Array("edgeMaskR", uint8, dom, 19)
-local edgeMaskC = Array("edgeMaskC", uint8, dom, 20)
-
-local col, row = Index(0), Index(1)
-local JUMP = 0.01
-
-local function hasDepth(dx, dy) return greater(D_i(dx, dy), 0) end
-
--- back-projected point of pixel (dx,dy)
-local function point(dx, dy)
-    local depth = X(dx, dy)
-    return Vector((((dx + col) - u_x) / f_x) * depth, (((dy + row) - u_y) / f_y) * depth, depth)
+local function rendered(dx, dy)
+    local n = unitNormal(dx, dy)
+    local a, b, c = n[0], n[1], n[2]
+    return sh[1] + sh[2] * b + sh[3] * c + sh[4] * a + sh[5] * a * b + sh[6] * b * c
+         + sh[7] * (-a * a - b * b + 2 * c * c) + sh[8] * c * a + sh[9] * (a * a - b * b)
 end
-
--- unit normal from depth differences
-local function normal(dx, dy)
-    local i = dx + col
-    local j = dy + row
-    local nx = X(dx, dy - 1) * (X(dx, dy) - X(dx - 1, dy)) / f_y
-    local ny = X(dx - 1, dy) * (X(dx, dy) - X(dx, dy - 1)) / f_x
-    local nz = (nx * (u_x - i) / f_x) + (ny * (u_y - j) / f_y) - (X(dx - 1, dy) * X(dx, dy - 1) / (f_x * f_y))
-    local len2 = nx * nx + ny * ny + nz * nz
-    local scale = Select(greater(len2, 0.0), 1.0 / sqrt(len2), 1.0)
-    return scale * Vector(nx, ny, nz)
+local function observed(dx, dy) return intensity(dx, dy) * 0.5 + 0.25 * (intensity(dx - 1, dy) + intensity(dx, dy - 1)) end
+local interior = InBoundsExpanded(0, 0, 1)
+local function mismatch(dx, dy)
+    local usable = measured(dx - 1, dy) * measured(dx, dy) * measured(dx, dy - 1)
+    return Select(InBoundsExpanded(0, 0, 1) * usable, rendered(dx, dy) - observed(dx, dy), 0)
 end
+local shadingError = ComputedArray("B_I", image, mismatch(0, 0))
 
--- second-order spherical-harmonics shading
-local function shading(dx, dy)
-    local n = normal(dx, dy)
-    local nx, ny, nz = n[0], n[1], n[2]
-    return light[1] + light[2] * ny + light[3] * nz + light[4] * nx
-         + light[5] * nx * ny + light[6] * ny * nz + light[7] * (-nx * nx - ny * ny + 2 * nz * nz)
-         + light[8] * nz * nx + light[9] * (nx * nx - ny * ny)
+-- 1. depth prior
+Energy(Select(measured(0, 0), sqrtDepth * (depth(0, 0) - sensor(0, 0)), 0))
+-- 2. shading-gradient consistency, horizontal then vertical
+Energy(Select(interior, sqrtShade * ((shadingError(0, 0) - shadingError(1, 0)) * keepAcrossRows(0, 0)), 0))
+Energy(Select(interior, sqrtShade * ((shadingError(0, 0) - shadingError(0, 1)) * keepAcrossCols(0, 0)), 0))
+-- 3. Laplacian of the back-projected surface where the depth has no discontinuity
+local function backProject(dx, dy)
+    local d = depth(dx, dy)
+    return Vector((((dx + u) - cx) / fx) * d, (((dy + v) - cy) / fy) * d, d)
 end
-
-local function intensity(dx, dy)
-    return Im(dx, dy) * 0.5 + 0.25 * (Im(dx - 1, dy) + Im(dx, dy - 1))
-end
-
-local function shadingError(dx, dy)
-    local ok = hasDepth(dx - 1, dy) * hasDepth(dx, dy) * hasDepth(dx, dy - 1)
-    return Select(InBoundsExpanded(0, 0, 1) * ok, shading(dx, dy) - intensity(dx, dy), 0)
-end
-local B_I = ComputedArray("B_I", dom, shadingError(0, 0))
-
-Exclude(Not(hasDepth(0, 0)))
-
--- stay close to the measured depth
-Energy(Select(hasDepth(0, 0), sqrt_w_p * (X(0, 0) - D_i(0, 0)), 0))
-
--- shading gradients must match intensity gradients (except across masked edges)
-local inner = InBoundsExpanded(0, 0, 1)
-Energy(Select(inner, sqrt_w_g * ((B_I(0, 0) - B_I(1, 0)) * edgeMaskR(0, 0)), 0))
-Energy(Select(inner, sqrt_w_g * ((B_I(0, 0) - B_I(0, 1)) * edgeMaskC(0, 0)), 0))
-
--- Laplacian smoothness of the back-projected surface where the depth is continuous
-local function smooth(dx, dy) return less(abs(X(0, 0) - X(dx, dy)), JUMP) end
-local flat = hasDepth(0, 0) * hasDepth(0, -1) * hasDepth(0, 1) * hasDepth(-1, 0) * hasDepth(1, 0)
-           * smooth(0, -1) * smooth(0, 1) * smooth(-1, 0) * smooth(1, 0) * InBoundsExpanded(0, 0, 1)
-local flatArray = ComputedArray("valid", dom, flat)
-local lap = 4.0 * point(0, 0) - (point(-1, 0) + point(0, -1) + point(1, 0) + point(0, 1))
-Energy(Select(eq(flatArray(0, 0), 1), sqrt_w_s * lap, 0))
+local function continuous(dx, dy) return less(abs(depth(0, 0) - depth(dx, dy)), discontinuity) end
+local smoothHere = measured(0, 0) * measured(0, -1) * measured(0, 1) * measured(-1, 0) * measured(1, 0)
+                 * continuous(0, -1) * continuous(0, 1) * continuous(-1, 0) * continuous(1, 0) * InBoundsExpanded(0, 0, 1)
+local smoothFlag = ComputedArray("valid", image, smoothHere)
+local laplace = 4.0 * backProject(0, 0) - (backProject(-1, 0) + backProject(0, -1) + backProject(1, 0) + backProject(0, 1))
+Energy(Select(eq(smoothFlag(0, 0), 1), sqrtSmooth * laplace, 0))

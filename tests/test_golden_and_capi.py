@@ -77,7 +77,9 @@ def test_spec_front_end_accepts_registered_and_rejects_others(built, tmp_path):
     assert spec_energy_name(str(p)) == (True, "image_warping")
     # ... but any change of the energy does
     p2 = tmp_path / "changed.t"
-    p2.write_text(src.replace("w_regSqrt * (", "2 * w_regSqrt * ("))
+    changed = src.replace("sqrtRigid * (", "2 * sqrtRigid * (")
+    assert changed != src
+    p2.write_text(changed)
     ok, msg = spec_energy_name(str(p2))
     assert not ok and "not one of the energies" in msg
     ok, msg = spec_energy_name(str(tmp_path / "missing.t"))

@@ -442,6 +442,13 @@ struct Interp {
     Problem& P;
     std::shared_ptr<Scope> globals = std::make_shared<Scope>();
     int line = 0;
+    // resource limits: a specification is untrusted text run inside the caller's process (the reference runs it in a Lua VM)
+    int depth = 0;            // nested function calls
+    long steps = 0;           // statements executed
+    static constexpr int kMaxDepth = 200;
+    static constexpr long kMaxSteps = 5000000;
+    static constexpr size_t kMaxString = 1 << 20;
+    struct DepthGuard { int& d; explicit DepthGuard(int& x) : d(x) { ++d; } ~DepthGuard() { --d; } };
     explicit Interp(Problem& p) : P(p) {}
 
     // ---------- value helpers
@@ -519,6 +526,8 @@ struct Interp {
     // ---------- calling
     std::vector<Value> call(const Value& f, std::vector<Value>& args, int ln) {
         line = ln;
+        if (depth >= kMaxDepth) fail("stack overflow: function calls nested deeper than " + std::to_string(kMaxDepth), ln);
+        DepthGuard guard(depth);
         if (f.type == Value::Builtin) return (*f.bf)(*this, args, ln);
         if (f.type == Value::Fn) {
             auto sc = std::make_shared<Scope>(); sc->parent = f.fn->env;
@@ -610,7 +619,9 @@ struct Interp {
         line = ln;
         if (op == "..") {
             auto s = [&](const Value& v) { if (v.type == Value::Str) return v.s; if (v.type == Value::Num) { char buf[64]; if (v.n == (long long)v.n) snprintf(buf, sizeof buf, "%lld", (long long)v.n); else snprintf(buf, sizeof buf, "%.14g", v.n); return std::string(buf); } fail("attempt to concatenate a non-string value", ln); };
-            return Value::str(s(a) + s(b));
+            const std::string sa = s(a), sb = s(b);
+            if (sa.size() + sb.size() > kMaxString) fail("string too long", ln);
+            return Value::str(sa + sb);
         }
         if (op == "==" || op == "~=") {
             bool eq = false;
@@ -717,6 +728,7 @@ struct Interp {
     void execBlock(const Block& b, const std::shared_ptr<Scope>& sc) { for (const StatP& s : b) exec(s, sc); }
     void exec(const StatP& s, const std::shared_ptr<Scope>& sc) {
         line = s->line;
+        if (++steps > kMaxSteps) fail("the specification did not finish: more than " + std::to_string(kMaxSteps) + " statements executed", s->line);
         switch (s->k) {
             case Stat::Local: {
                 std::vector<Value> vals = evalArgs(s->exprs, sc);

@@ -188,6 +188,21 @@ def test_device_dual_number_math_on_the_host(tmp_path):
     assert r.returncode == 0 and "ALL_OK" in r.stdout, r.stdout
 
 
+@pytest.mark.parametrize("body,needle", [
+    ("local function f(n) return f(n + 1) end\nf(0)\n", "stack overflow"),
+    ("local t = {}\nfor i = 1, 100000000 do t[i] = i end\n", "did not finish"),
+    ("local s = 'a'\nfor i = 1, 40 do s = s .. s end\n", "string too long"),
+    ("local N = Dim('N', 0)\nlocal X = Unknown('X', opt_float, { N }, 0)\nfor i = 1, 100 do Energy(X(0) - i) end\n", "more than 64"),
+])
+def test_front_end_resource_limits(built, tmp_path, body, needle):
+    """a specification is untrusted text executed inside the caller's process: runaway recursion, loops, strings and residual counts
+    end in an error message (and a NULL plan through Opt_ProblemPlan), never in a crash or a hang"""
+    from opt_b200.solver import frontend_compile
+    spec = tmp_path / "hostile.t"; spec.write_text(body)
+    ok, msg = frontend_compile(str(spec))
+    assert not ok and needle in msg, msg
+
+
 def test_front_end_compiles_every_reference_spec(built):
     """when the reference tree is mounted: every .t file it ships runs through the front end"""
     import glob

@@ -55,10 +55,12 @@ struct Node {
     // Sample (bilinear read of a 2-D image at computed coordinates, o.t:582-589): id = image, off[0]/off[1] = images holding d/dx and d/dy
     // (-1: none), chan; args = { x, y }
     std::vector<int> args;
+    int height = 0;          // longest path to a leaf; bounded, because analysis and code generation walk the DAG recursively
 };
 struct Dag {
     std::vector<Node> nodes;
     std::unordered_map<std::string, int> index;
+    static constexpr int kMaxHeight = 4000, kMaxNodes = 2000000;
     int add(const Node& n) {
         std::ostringstream k;
         k.precision(17);
@@ -67,7 +69,12 @@ struct Dag {
         for (int a : n.args) k << ':' << a;
         auto it = index.find(k.str());
         if (it != index.end()) return it->second;
+        int h = 0;
+        for (int a : n.args) h = std::max(h, nodes[a].height + 1);
+        if (h > kMaxHeight) fail("residual expression too deep (a chain of more than " + std::to_string(kMaxHeight) + " operations)");
+        if ((int)nodes.size() >= kMaxNodes) fail("residual expressions too large (more than " + std::to_string(kMaxNodes) + " distinct operations)");
         nodes.push_back(n);
+        nodes.back().height = h;
         index[k.str()] = (int)nodes.size() - 1;
         return (int)nodes.size() - 1;
     }
@@ -160,6 +167,7 @@ using Block = std::vector<StatP>;
 struct Expr {
     enum K { Nil, True, False, Number, String, Name, Index, Call, Method, Function, Binop, Unop, TableCtor, Vararg } k = Nil;
     int line = 0; double num = 0; std::string str;                       // Number / String / Name / Method name / operator
+    int depth = 0;                                                       // height of the tree below this node (bounded by the parser)
     ExprP a, b;                                                          // Index(a,b), Binop(a,b), Unop(a), Call(a), Method(a)
     std::vector<ExprP> args;                                             // Call / Method args; TableCtor positional values
     std::vector<std::pair<ExprP, ExprP>> fields;                         // TableCtor keyed fields
@@ -244,6 +252,20 @@ struct Lexer {
 // ------------------------------------------------------------------------------------- parser
 struct Parser {
     Lexer lx; Token tok, ahead; bool hasAhead = false;
+    // limits that keep the recursive-descent parser, the tree-walking interpreter and the tree's destructor off the end of the stack
+    int nest = 0;
+    static constexpr int kMaxNest = 200, kMaxDepth = 2000;
+    struct NestGuard { Parser& p; explicit NestGuard(Parser& q) : p(q) { if (++p.nest > kMaxNest) fail("the specification nests too deeply (more than " + std::to_string(kMaxNest) + " levels)", p.tok.line); } ~NestGuard() { --p.nest; } };
+    ExprP fin(ExprP e) {   // records the height of a freshly built node: long operator / suffix chains are built iteratively, not recursively
+        int d = 0;
+        if (e->a) d = std::max(d, e->a->depth);
+        if (e->b) d = std::max(d, e->b->depth);
+        for (auto& x : e->args) if (x) d = std::max(d, x->depth);
+        for (auto& f : e->fields) { if (f.first) d = std::max(d, f.first->depth); if (f.second) d = std::max(d, f.second->depth); }
+        e->depth = d + 1;
+        if (e->depth > kMaxDepth) fail("expression too long (more than " + std::to_string(kMaxDepth) + " chained operators)", e->line);
+        return e;
+    }
     explicit Parser(const std::string& s) : lx(s) { tok = lx.next(); }
     void advance() { if (hasAhead) { tok = ahead; hasAhead = false; } else tok = lx.next(); }
     const Token& peek() { if (!hasAhead) { ahead = lx.next(); hasAhead = true; } return ahead; }
@@ -257,6 +279,7 @@ struct Parser {
 
     bool blockEnd() const { return tok.t == Token::Eof || isKw("end") || isKw("else") || isKw("elseif") || isKw("until"); }
     std::shared_ptr<Block> block() {
+        NestGuard guard(*this);
         auto b = std::make_shared<Block>();
         while (!blockEnd()) {
             if (acceptSym(";")) continue;
@@ -350,7 +373,7 @@ struct Parser {
     std::vector<ExprP> exprList() { std::vector<ExprP> v; v.push_back(expression()); while (acceptSym(",")) v.push_back(expression()); return v; }
     ExprP primary() {
         if (tok.t == Token::Name) { ExprP e = mk(Expr::Name); e->str = tok.s; advance(); return e; }
-        if (acceptSym("(")) { ExprP e = expression(); expectSym(")"); ExprP p = mk(Expr::Unop); p->str = "()"; p->a = e; return p; }
+        if (acceptSym("(")) { ExprP e = expression(); expectSym(")"); ExprP p = mk(Expr::Unop); p->str = "()"; p->a = e; return fin(p); }
         fail("unexpected symbol near '" + tok.s + "'", tok.line);
     }
     std::vector<ExprP> callArgs() {
@@ -365,10 +388,10 @@ struct Parser {
     ExprP suffixed() {
         ExprP e = primary();
         for (;;) {
-            if (acceptSym(".")) { ExprP i = mk(Expr::Index); i->a = e; ExprP k = mk(Expr::String); k->str = expectName(); i->b = k; e = i; }
-            else if (acceptSym("[")) { ExprP i = mk(Expr::Index); i->a = e; i->b = expression(); expectSym("]"); e = i; }
-            else if (acceptSym(":")) { ExprP m = mk(Expr::Method); m->a = e; m->str = expectName(); m->args = callArgs(); e = m; }
-            else if (isSym("(") || isSym("{") || tok.t == Token::String) { ExprP c = mk(Expr::Call); c->a = e; c->args = callArgs(); e = c; }
+            if (acceptSym(".")) { ExprP i = mk(Expr::Index); i->a = e; ExprP k = mk(Expr::String); k->str = expectName(); i->b = k; e = fin(i); }
+            else if (acceptSym("[")) { ExprP i = mk(Expr::Index); i->a = e; i->b = expression(); expectSym("]"); e = fin(i); }
+            else if (acceptSym(":")) { ExprP m = mk(Expr::Method); m->a = e; m->str = expectName(); m->args = callArgs(); e = fin(m); }
+            else if (isSym("(") || isSym("{") || tok.t == Token::String) { ExprP c = mk(Expr::Call); c->a = e; c->args = callArgs(); e = fin(c); }
             else return e;
         }
     }
@@ -382,7 +405,7 @@ struct Parser {
             if (!acceptSym(",") && !acceptSym(";")) break;
         }
         expectSym("}");
-        return t;
+        return fin(t);
     }
     ExprP simple() {
         if (tok.t == Token::Number) { ExprP e = mk(Expr::Number); e->num = tok.n; advance(); return e; }
@@ -408,15 +431,16 @@ struct Parser {
         return 0;
     }
     ExprP expression(int limit = 0) {
+        NestGuard guard(*this);
         ExprP left;
         if (isKw("not") || isSym("-") || isSym("#")) {
-            ExprP u = mk(Expr::Unop); u->str = tok.s; advance(); u->a = expression(7); left = u;
+            ExprP u = mk(Expr::Unop); u->str = tok.s; advance(); u->a = expression(7); left = fin(u);
         } else left = simple();
         for (;;) {
             bool right; int p = prec(tok, &right);
             if (p == 0 || p <= limit) break;
             ExprP b = mk(Expr::Binop); b->str = tok.s; advance();
-            b->a = left; b->b = expression(right ? p - 1 : p); left = b;
+            b->a = left; b->b = expression(right ? p - 1 : p); left = fin(b);
         }
         return left;
     }

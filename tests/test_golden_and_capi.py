@@ -193,6 +193,10 @@ def test_device_dual_number_math_on_the_host(tmp_path):
     ("local t = {}\nfor i = 1, 100000000 do t[i] = i end\n", "did not finish"),
     ("local s = 'a'\nfor i = 1, 40 do s = s .. s end\n", "string too long"),
     ("local N = Dim('N', 0)\nlocal X = Unknown('X', opt_float, { N }, 0)\nfor i = 1, 100 do Energy(X(0) - i) end\n", "more than 64"),
+    ("local x = " + "(" * 100000 + "1" + ")" * 100000 + "\n", "nests too deeply"),
+    ("if true then " * 50000 + "end " * 50000 + "\n", "nests too deeply"),
+    ("local x = 1" + " + 1" * 100000 + "\n", "expression too long"),
+    ("local N = Dim('N', 0)\nlocal X = Unknown('X', opt_float, { N }, 0)\nlocal s = X(0)\nfor i = 1, 100000 do s = s * 1.0001 + X(0) end\nEnergy(s)\n", "too deep"),
 ])
 def test_front_end_resource_limits(built, tmp_path, body, needle):
     """a specification is untrusted text executed inside the caller's process: runaway recursion, loops, strings and residual counts

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("dp", [True, False])
-@pytest.mark.parametrize("nx,ny", [(8, 7), (13, 9)])
+@pytest.mark.parametrize("nx,ny", [(8, 7), (13, 9), (2, 1), (1, 1), (3, 2)])
 def test_rna_per_vertex_math_matches_oracle(tmp_path, nx, ny, dp):
     from oracle.oracle import Oracle
     dt = np.float64 if dp else np.float32

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("dp", [True, False])
-@pytest.mark.parametrize("W,H,seed", [(26, 22, 0), (40, 31, 1)])
+@pytest.mark.parametrize("W,H,seed", [(26, 22, 0), (40, 31, 1), (3, 3, 0), (2, 5, 0), (1, 1, 0), (7, 3, 2)])
 def test_sfs_per_pixel_math_matches_oracle(tmp_path, W, H, seed, dp):
     from oracle.oracle import Oracle
     dt = np.float64 if dp else np.float32
@@ -37,7 +37,8 @@ def test_sfs_per_pixel_math_matches_oracle(tmp_path, W, H, seed, dp):
     assert r.returncode == 0 and r.stdout.startswith("COST "), r.stdout + r.stderr
     tok = r.stdout.split()
     cost, model, n_inc, n_flat = float(tok[1]), float(tok[3]), int(tok[5]), int(tok[7])
-    assert n_inc > 0.5 * W * H and n_flat > 0          # the workload exercises every term
+    if W * H > 100:
+        assert n_inc > 0.5 * W * H and n_flat > 0      # the workload exercises every term
     o = Oracle("shape_from_shading", "LMGPU", [W, H], dp)
     ocost, g, diag = o.eval_jtf(host)
     ref = o.apply_jtj(host, x)

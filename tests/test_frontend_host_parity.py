@@ -26,6 +26,16 @@ CASES = {
     "laplacian": ([19, 13], lambda: workloads.laplacian(19, 13, dtype=np.float32), [0]),
 }
 FP32 = {"laplacian"}
+# degenerate sizes: single pixels / rows, images without an interior, a mesh of two vertices, a graph of three samples
+TINY = {
+    "image_warping": ([5, 1], lambda: workloads.image_warping(5, 1, dtype=np.float64, perturb=0.3), [0, 1]),
+    "poisson_image_editing": ([1, 1], lambda: workloads.poisson(1, 1, dtype=np.float64), [0]),
+    "laplacian": ([1, 3], lambda: workloads.laplacian(1, 3, dtype=np.float32), [0]),
+    "arap_mesh_deformation": ([2], lambda: workloads.arap_mesh(2, 1, dtype=np.float64, n_handles=1, perturb=0.2), [2, 3]),
+    "shape_from_shading": ([3, 3], lambda: workloads.shape_from_shading(3, 3, dtype=np.float64), [16]),
+    "robust_nonrigid_alignment": ([2], lambda: workloads.robust_nonrigid(2, 1, dtype=np.float64, perturb=0.1), [2, 3, 4]),
+    "curveFitting": ([3, 1], lambda: workloads.curve_fitting(3, dtype=np.float64), [0]),
+}
 
 
 @pytest.fixture(scope="module")
@@ -56,15 +66,15 @@ def _reference_spec(energy):
     return os.path.join(REFERENCE, "examples", energy, energy + ".t")
 
 
-@pytest.mark.parametrize("source", ["specs", "reference"])
+@pytest.mark.parametrize("source", ["specs", "reference", "specs-tiny"])
 @pytest.mark.parametrize("energy", sorted(CASES))
 def test_generated_code_matches_oracle_on_the_host(fe_probe, tmp_path, energy, source):
     """source = "specs": this repository's own statement of the energy; "reference": the reference's .t file itself, read
     where it lies (only when the reference tree is mounted) -- the oracle restates exactly that file"""
     from oracle.oracle import Oracle
-    dims, gen, upos = CASES[energy]
+    dims, gen, upos = (TINY if source == "specs-tiny" else CASES)[energy]
     host = gen()
-    spec = spec_path(energy) if source == "specs" else _reference_spec(energy)
+    spec = spec_path(energy) if source.startswith("specs") else _reference_spec(energy)
     if source == "reference" and not os.path.exists(spec):
         pytest.skip("reference tree not mounted")
     inc = tmp_path / "generated.inc"

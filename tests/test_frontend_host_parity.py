@@ -39,10 +39,35 @@ TINY = {
 
 
 @pytest.fixture(scope="module")
-def fe_probe(tmp_path_factory):
+def fe_probe(tmp_path_factory, frontend_obj):
     exe = tmp_path_factory.mktemp("fe") / "fe_probe"
-    subprocess.check_call([CXX, "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tools", "fe_probe.cpp"), os.path.join(ROOT, "opt_b200", "csrc", "frontend.cpp")])
+    subprocess.check_call([CXX, "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tools", "fe_probe.cpp"), frontend_obj])
     return str(exe)
+
+
+@pytest.fixture(scope="module")
+def frontend_obj(tmp_path_factory):
+    """frontend.cpp compiled once for the whole module: every harness below links it"""
+    obj = tmp_path_factory.mktemp("feobj") / "frontend.o"
+    subprocess.check_call([CXX, "-O1", "-std=c++17", "-c", "-o", str(obj), os.path.join(ROOT, "opt_b200", "csrc", "frontend.cpp")])
+    return str(obj)
+
+
+_HARNESS = {}   # (spec file, precision) -> compiled harness, shared by the cases that use the same generated code
+
+
+def _harness(fe_probe, frontend_obj, spec, dp, tmp_path_factory):
+    key = (os.path.abspath(spec), dp)
+    if key not in _HARNESS:
+        d = tmp_path_factory.mktemp("harness")
+        inc = d / "generated.inc"
+        out = subprocess.run([fe_probe, "--emit", str(inc), spec], capture_output=True, text=True)
+        assert out.returncode == 0 and inc.exists(), out.stdout + out.stderr
+        exe = d / "spec_eval_host"
+        subprocess.check_call([CXX, "-O1", "-std=c++17", f'-DGEN_SOURCE="{inc}"', "-DHOST_T=" + ("double" if dp else "float"), "-o", str(exe),
+                               os.path.join(ROOT, "tests", "host", "spec_eval_host.cpp"), frontend_obj])
+        _HARNESS[key] = str(exe)
+    return _HARNESS[key]
 
 
 def _write_params(host, d):
@@ -68,7 +93,7 @@ def _reference_spec(energy):
 
 @pytest.mark.parametrize("source", ["specs", "reference", "specs-tiny"])
 @pytest.mark.parametrize("energy", sorted(CASES))
-def test_generated_code_matches_oracle_on_the_host(fe_probe, tmp_path, energy, source):
+def test_generated_code_matches_oracle_on_the_host(fe_probe, frontend_obj, tmp_path_factory, tmp_path, energy, source):
     """source = "specs": this repository's own statement of the energy; "reference": the reference's .t file itself, read
     where it lies (only when the reference tree is mounted) -- the oracle restates exactly that file"""
     from oracle.oracle import Oracle
@@ -77,13 +102,8 @@ def test_generated_code_matches_oracle_on_the_host(fe_probe, tmp_path, energy, s
     spec = spec_path(energy) if source.startswith("specs") else _reference_spec(energy)
     if source == "reference" and not os.path.exists(spec):
         pytest.skip("reference tree not mounted")
-    inc = tmp_path / "generated.inc"
-    out = subprocess.run([fe_probe, "--emit", str(inc), spec], capture_output=True, text=True)
-    assert out.returncode == 0 and inc.exists(), out.stdout + out.stderr
-    exe = tmp_path / "spec_eval_host"
     dp = energy not in FP32
-    subprocess.check_call([CXX, "-O1", "-std=c++17", f'-DGEN_SOURCE="{inc}"', "-DHOST_T=" + ("double" if dp else "float"), "-o", str(exe), os.path.join(ROOT, "tests", "host", "spec_eval_host.cpp"),
-                           os.path.join(ROOT, "opt_b200", "csrc", "frontend.cpp")])
+    exe = _harness(fe_probe, frontend_obj, spec, dp, tmp_path_factory)
     data = tmp_path / "params"; data.mkdir()
     _write_params(host, str(data))
     res = tmp_path / "out.bin"
@@ -113,7 +133,7 @@ Energy(w * (X(G.a) - X(G.b) - 0.5 * T(G.a)))
 """
 
 
-def test_graph_over_a_2d_index_space_on_the_host(fe_probe, tmp_path):
+def test_graph_over_a_2d_index_space_on_the_host(fe_probe, frontend_obj, tmp_path_factory, tmp_path):
     """graph vertices of a 2-D index space are (d0, d1) int32 pairs (the reference's Index struct, o.t:355-387); the generated
     code, run on the CPU, must match a direct numpy statement of the energy"""
     W, H, E = 9, 7, 40
@@ -123,12 +143,7 @@ def test_graph_over_a_2d_index_space_on_the_host(fe_probe, tmp_path):
     b = np.stack([rng.integers(0, W, E), rng.integers(0, H, E)], -1).astype(np.int32)
     w = 0.7
     spec = tmp_path / "graph2d.t"; spec.write_text(GRAPH2D_SPEC)
-    inc = tmp_path / "generated.inc"
-    out = subprocess.run([fe_probe, "--emit", str(inc), str(spec)], capture_output=True, text=True)
-    assert out.returncode == 0 and inc.exists(), out.stdout + out.stderr
-    exe = tmp_path / "spec_eval_host"
-    subprocess.check_call([CXX, "-O1", "-std=c++17", f'-DGEN_SOURCE="{inc}"', "-o", str(exe), os.path.join(ROOT, "tests", "host", "spec_eval_host.cpp"),
-                           os.path.join(ROOT, "opt_b200", "csrc", "frontend.cpp")])
+    exe = _harness(fe_probe, frontend_obj, str(spec), True, tmp_path_factory)
     data = tmp_path / "params"; data.mkdir()
     _write_params([X.reshape(-1, 2), T.reshape(-1, 2), E, a, b, w], str(data))
     res = tmp_path / "out.bin"
@@ -149,7 +164,7 @@ def test_graph_over_a_2d_index_space_on_the_host(fe_probe, tmp_path):
 
 
 @pytest.mark.parametrize("energy", ["volumetric_mesh_deformation", "cotangent_mesh_smoothing", "embedded_mesh_deformation", "optical_flow", "intrinsic_image_decomposition"])
-def test_specs_without_an_oracle_energy_equal_the_reference_text(energy):
+def test_specs_without_an_oracle_energy_equal_the_reference_text(fe_probe, frontend_obj, energy):
     """the five example energies the oracle does not restate: specs/<energy>.t (this repository's own statement) and the reference's
     .t file must be the SAME energy -- both through the front end, generated code run on the CPU on identical random inputs built from
     the parameter table (tools/spec_equiv.py), cost / J^T F / diag(J^T J) equal in fp64.  Needs the reference tree."""
@@ -159,4 +174,4 @@ def test_specs_without_an_oracle_energy_equal_the_reference_text(energy):
     import importlib.util
     sp = importlib.util.spec_from_file_location("spec_equiv", os.path.join(ROOT, "tools", "spec_equiv.py"))
     mod = importlib.util.module_from_spec(sp); sp.loader.exec_module(mod)
-    assert mod.equivalent(spec_path(energy), ref, verbose=False)
+    assert mod.equivalent(spec_path(energy), ref, verbose=False, probe=fe_probe, frontend_obj=frontend_obj)

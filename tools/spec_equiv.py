@@ -76,12 +76,12 @@ def random_params(m, dims, rng, n_edges=37):
     return files
 
 
-def evaluate(probe, spec, files, dims, tmp, tag, fp32=False):
+def evaluate(probe, spec, files, dims, tmp, tag, fp32=False, frontend_obj=None):
     inc = os.path.join(tmp, f"gen_{tag}.inc")
     subprocess.check_call([probe, "--emit", inc, spec], stdout=subprocess.DEVNULL)
     exe = os.path.join(tmp, f"eval_{tag}")
     subprocess.check_call([CXX, "-O1", "-std=c++17", f'-DGEN_SOURCE="{inc}"', "-DHOST_T=" + ("float" if fp32 else "double"), "-o", exe, os.path.join(ROOT, "tests", "host", "spec_eval_host.cpp"),
-                           os.path.join(ROOT, "opt_b200", "csrc", "frontend.cpp")])
+                           frontend_obj or os.path.join(ROOT, "opt_b200", "csrc", "frontend.cpp")])
     data = os.path.join(tmp, f"data_{tag}"); os.makedirs(data, exist_ok=True)
     for k, a in files.items():
         np.ascontiguousarray(a).tofile(os.path.join(data, f"p{k}.bin"))
@@ -92,9 +92,10 @@ def evaluate(probe, spec, files, dims, tmp, tag, fp32=False):
     return float(r.stdout.split()[1]), np.fromfile(res, np.float64)
 
 
-def equivalent(a, b, dims=None, seed=0, verbose=True):
+def equivalent(a, b, dims=None, seed=0, verbose=True, probe=None, frontend_obj=None):
+    """probe / frontend_obj: prebuilt tools/fe_probe and frontend.o (the test suite builds them once); built here when absent"""
     with tempfile.TemporaryDirectory() as tmp:
-        probe = build_probe(tmp)
+        probe = probe or build_probe(tmp)
         ma, mb = meta(probe, a), meta(probe, b)
         if layout(ma) != layout(mb):
             if verbose:
@@ -103,8 +104,8 @@ def equivalent(a, b, dims=None, seed=0, verbose=True):
         dims = dims or [11, 7, 5][: ma["maxdim"] + 1]
         files = random_params(ma, dims, np.random.default_rng(seed))
         fp32 = single_precision(ma)
-        ca, va = evaluate(probe, a, files, dims, tmp, "a", fp32)
-        cb, vb = evaluate(probe, b, files, dims, tmp, "b", fp32)
+        ca, va = evaluate(probe, a, files, dims, tmp, "a", fp32, frontend_obj)
+        cb, vb = evaluate(probe, b, files, dims, tmp, "b", fp32, frontend_obj)
         tol = 1e-5 if fp32 else 1e-11
         ok = abs(ca - cb) <= tol * max(1.0, abs(ca)) and va.shape == vb.shape and np.abs(va - vb).max() <= tol * max(1.0, np.abs(va).max())
         if verbose:

@@ -55,13 +55,16 @@ def _compare(W, H, tile):
         assert np.abs(got[name] - ref[name]).max() <= 1e-3 * scale, name
 
 
-@pytest.mark.parametrize("W,H,tile", [(48, 40, "16x8"), (37, 29, "16x8"), (64, 64, "64x4"), (50, 33, "7x5")])
-def test_tile_variant_matches_per_step_loop(built, W, H, tile):
-    """runs in a child process: the library answers a CUDA error with exit(code) like the reference does, and an
-    unproven kernel must not be able to take the test session down with it"""
+CASES = [(48, 40, "16x8"), (37, 29, "16x8"), (64, 64, "64x4"), (50, 33, "7x5")]
+
+
+def test_tile_variant_matches_per_step_loop(built):
+    """runs in ONE child process: the library answers a CUDA error with exit(code) like the reference does, and an unproven kernel
+    must not be able to take the test session down with it"""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = f"import sys; sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r}); import test_gpu_zz_resident_tile as t; t._compare({W}, {H}, {tile!r}); print('TILE_OK')"
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
+    code = (f"import sys; sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r}); import test_gpu_zz_resident_tile as t\n"
+            + "\n".join(f"t._compare({W}, {H}, {tile!r}); print('case {W}x{H} tile {tile} ok')" for W, H, tile in CASES) + "\nprint('TILE_OK')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0 and "TILE_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])

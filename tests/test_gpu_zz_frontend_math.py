@@ -19,8 +19,7 @@ MATH_FNS = {   # name -> (numpy function, derivative, constant that keeps a*x + 
 }
 
 
-@pytest.mark.parametrize("fn", sorted(MATH_FNS))
-def test_math_function_values_and_derivatives(built, tmp_path, fn):
+def _check_math_function(tmp_path, fn):
     """every single-argument function of ad.t:747-763: the residual f(0.1 x + c) - y through front end + device dual
     numbers, cost and -J^T F against closed forms in numpy (fp64)"""
     import torch
@@ -58,7 +57,7 @@ end
 """
 
 
-def test_exclude_mask_may_change_between_steps(built, tmp_path):
+def _check_exclude_mask_may_change_between_steps(tmp_path):
     """the reference evaluates Exclude() in every kernel, so a caller may edit a mask image between two Opt_ProblemStep
     calls; the generic engine caches masked columns per solve and must notice (generic_engine.cuh k_geActiveChanged)"""
     import torch
@@ -88,3 +87,24 @@ def test_exclude_mask_may_change_between_steps(built, tmp_path):
     b.close()
     assert np.abs(XA - XB).max() <= 1e-12 * max(1.0, np.abs(XB).max())
     assert np.array_equal(XA[M2 != 0], X1[M2 != 0])            # pixels excluded by the NEW mask did not move in the second step
+
+
+def _run_in_child(body):
+    """the library answers a CUDA error with exit(code) like the reference does: first runs of new device paths happen in a child
+    process so that a surprise cannot take the pytest session down"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (f"import sys, pathlib, tempfile; sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+            "import test_gpu_zz_frontend_math as t\ntmp = pathlib.Path(tempfile.mkdtemp())\n" + body + "\nprint('CHILD_OK')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0 and "CHILD_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_math_function_values_and_derivatives(built):
+    _run_in_child("\n".join(f"t._check_math_function(tmp, {fn!r}); print('{fn} ok')" for fn in sorted(MATH_FNS)))
+
+
+def test_exclude_mask_may_change_between_steps(built):
+    _run_in_child("t._check_exclude_mask_may_change_between_steps(tmp)")

@@ -1109,14 +1109,17 @@ struct ImageWarpingOps : EnergyOps<T> {
     // 2-D tile variant (opt-in, OPTB_RESIDENT_TILE=WxH; chosen automatically for the multi-GPU form): own sequence/arrival
     // state because its grid size differs
     int tileW = 0, tileH = 0, tileGrid = 0, tileK = 0, tileAcross = 0; size_t tileSmem = 0; unsigned long long* tileWords = nullptr; unsigned long long tileSeq = 0;
-    bool tileMulti = false;
+    bool tileMulti = false; const void* tileChecked = nullptr;
     template <int KMAX, bool MULTI>
     bool launchTileK(const LaunchCtx& c, int L, const IWTileMulti<T>& M, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
         const void* fn = (const void*)k_iwPcgLoopTile<T, KMAX, MULTI>;
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileSmem) != cudaSuccess) { cudaGetLastError(); return false; }
-        int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 1024, tileSmem);
-        int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if ((long)occ * sms < tileGrid) return false;
+        if (tileChecked != fn) {   // once per kernel variant, not per launch
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileSmem) != cudaSuccess) { cudaGetLastError(); return false; }
+            int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 1024, tileSmem);
+            int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if ((long)occ * sms < tileGrid) return false;
+            tileChecked = fn;
+        }
         constexpr size_t llCount = 4 * (kMaxLLCtas + 1) + 1;
         if (!tileWords) { OPT_CUDA_CHECK(cudaMalloc((void**)&tileWords, sizeof(unsigned long long) * llCount)); OPT_CUDA_CHECK(cudaMemset(tileWords, 0, sizeof(unsigned long long) * llCount)); tileSeq = 0; }
         unsigned long long* arrivals = tileWords + 4 * (kMaxLLCtas + 1);

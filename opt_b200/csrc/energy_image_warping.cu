@@ -1159,7 +1159,7 @@ struct ImageWarpingOps : EnergyOps<T> {
             if (!found) return false;
         }
         tileW = a; tileH = b; tileAcross = (D.W + a - 1) / a; tileGrid = tileAcross * ((rows + b - 1) / b);
-        tileSmem = tileSmemFor(a, b, multi); tileK = (int)(((size_t)a * b + 1023) / 1024); tileMulti = multi;
+        tileSmem = tileSmemFor(a, b, multi); tileK = (int)(((size_t)a * b + 1023) / 1024); tileMulti = multi; tileChecked = nullptr;
         return true;
     }
     bool launchTile(const LaunchCtx& c, int L, const HaloPlan* haloZ, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {

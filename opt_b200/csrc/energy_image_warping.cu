@@ -1103,7 +1103,11 @@ struct ImageWarpingOps : EnergyOps<T> {
         unsigned long long* arrivals = llWords + 4 * (kMaxLLCtas + 1);
         unsigned long long k0 = resSeq; resSeq += 2ull * (unsigned long long)L;   // own sequence: the arrival counter counts gridDim per reduction
         void* args[] = { (void*)&D, (void*)&ws, (void*)&llWords, (void*)&arrivals, (void*)&k0, (void*)&L, (void*)&resR, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre };
-        OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)resGrid), dim3(1024), args, resSmem, c.stream));
+        const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3((unsigned)resGrid), dim3(1024), args, resSmem, c.stream);
+        if (le != cudaSuccess) {   // e.g. fewer SMs available than the device reports (MPS limits): nothing ran, use the per-step loop from now on
+            cudaGetLastError(); resSeq = k0; resR = -1;
+            return false;
+        }
         return true;
     }
     // 2-D tile variant (opt-in, OPTB_RESIDENT_TILE=WxH; chosen automatically for the multi-GPU form): own sequence/arrival
@@ -1128,7 +1132,12 @@ struct ImageWarpingOps : EnergyOps<T> {
         IWTileMulti<T> Mv = M;
         void* args[] = { (void*)&D, (void*)&ws, (void*)&tileWords, (void*)&arrivals, (void*)&k0, (void*)&L, (void*)&tileW, (void*)&tileH, (void*)&tileAcross, (void*)&Mv,
                          (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre };
-        OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)tileGrid), dim3(1024), args, tileSmem, c.stream));
+        const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3((unsigned)tileGrid), dim3(1024), args, tileSmem, c.stream);
+        if (le != cudaSuccess) {
+            if (MULTI) OPT_CUDA_CHECK(le);   // the other ranks are already inside the collective kernel: failing loudly is the only safe answer
+            cudaGetLastError(); tileSeq = k0; tileW = -1;
+            return false;
+        }
         return true;
     }
     size_t tileSmemFor(int a, int b, bool multi) const {

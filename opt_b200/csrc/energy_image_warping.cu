@@ -287,12 +287,6 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdlWait();
-    float beta = 0.f;
-    if (FUSE3) {
-        double drn, dro; loadScalars2(ws, rzNew, rzOld, drn, dro);
-        const float rn = (float)drn, ro = (float)dro;
-        if (ro > 0.f) beta = rn / ro;
-    }
     __syncthreads();
     // Multi-GPU (hp.nSeg > 0): this kernel is also the halo exchange.  The last CTA first stores this rank's
     // boundary rows of haloSrc (z when FUSE3, else p) into the neighbours' halo rows over NVLink and releases
@@ -337,6 +331,14 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
     }
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) { const int t = blockIdx.x + s * gridDim.x; if (t < numTiles) issue(t, s); }
+    }
+    // beta is awaited only now, with the first tiles already in flight: nothing staged above depends on it, and on several GPUs it
+    // arrives through the NVLink mailboxes a few microseconds after the kernel starts
+    float beta = 0.f;
+    if (FUSE3) {
+        double drn, dro; loadScalars2(ws, rzNew, rzOld, drn, dro);
+        const float rn = (float)drn, ro = (float)dro;
+        if (ro > 0.f) beta = rn / ro;
     }
     const float w2 = D.w * D.w, wf2 = D.wf * D.wf;
     const int lx = tid & (kTW - 1), ly0 = (tid >> 6) * kStrip;   // 256 threads = 64 columns x 4 strips of 4 rows
@@ -1050,6 +1052,7 @@ struct ImageWarpingOps : EnergyOps<T> {
     }
     ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); if (loopSync) cudaFree(loopSync); if (llWords) cudaFree(llWords); if (tileWords) cudaFree(tileWords); }
     const char* name() const override { return "image_warping"; }
+    unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(D); }
     int upperRows = 0, lowerRows = 0;
     bool setSlab(int ownedBegin, int ownedEnd, int up, int dn) override {
         if (ownedBegin < 0 || ownedEnd > D.H || ownedBegin >= ownedEnd || D.W % 4 != 0) return false;
@@ -1171,6 +1174,18 @@ struct ImageWarpingOps : EnergyOps<T> {
         tileSmem = tileSmemFor(a, b, multi); tileK = (int)(((size_t)a * b + 1023) / 1024); tileMulti = multi; tileChecked = nullptr;
         return true;
     }
+    bool pcgLoopMultiFits() override {   // asked once per connect, after setSlab(): tile shape + co-residency of all tiles
+        int dev = 0, coop = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (!coop || !chooseTile(true)) { tileW = -1; tileMulti = true; return false; }
+        const void* fn = tileK <= 2 ? (const void*)k_iwPcgLoopTile<T, 2, true> : (const void*)k_iwPcgLoopTile<T, 4, true>;
+        int occ = 0;
+        if (tileK > 4 || cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileSmem) != cudaSuccess) { cudaGetLastError(); tileW = -1; return false; }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 1024, tileSmem);
+        if ((long)occ * sms < tileGrid) { tileW = -1; return false; }
+        tileChecked = fn;
+        return true;
+    }
     bool launchTile(const LaunchCtx& c, int L, const HaloPlan* haloZ, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
         const bool multi = haloZ != nullptr;
         if (tileW == 0 || tileMulti != multi) { if (!chooseTile(multi)) { tileW = -1; tileMulti = multi; } }
@@ -1205,13 +1220,8 @@ struct ImageWarpingOps : EnergyOps<T> {
     LoopSync* loopSync = nullptr; unsigned long long loopSeq = 0; int gridLoop = 0; int coopOk = -1;
     bool pcgLoop(const LaunchCtx& c, int L, bool force, T* delta, T* r, T* z, T* p, T* p2, T* Ap, const T* pre, T** pFinal, const HaloPlan* haloZ) override {
         if (L <= 0) return false;
-        if (haloZ) {   // multi-GPU: only the tile kernel has a multi-rank form, and only on request (not yet run on hardware)
-            // NOTE: the ranks must all take the same branch (the kernel's reductions are collective).  The decision depends on the
-            // slab height only, so equal slabs (H divisible by the number of ranks -- bench.py, the tests) decide alike; with
-            // unequal slabs a rank that does not fit would fall back alone: make the decision collective before this becomes a default.
-            if (!force) return false;
-            int dev = 0, coop = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-            if (!coop || !launchTile(c, L, haloZ, delta, r, z, p, Ap, pre)) return false;
+        if (haloZ) {   // multi-GPU: the plan only gets here when EVERY rank answered pcgLoopMultiFits() with yes, so the launch is collective
+            if (!launchTile(c, L, haloZ, delta, r, z, p, Ap, pre)) { fprintf(stderr, "opt_b200: image_warping: the collective PCG-loop kernel could not be launched on this rank\n"); exit(4); }
             *pFinal = p;
             return true;
         }

@@ -6,8 +6,7 @@
 // vertex-CSR construction (stable cub radix sorts of the caller's index arrays, as in energy_arap.cu) and the deterministic
 // reductions of common.cuh.  Replaces, for this energy, the generated function map of the reference (o.t:2029-2460) and its
 // per-edge atomicAdd scatter (solverGPUGaussNewton.t:687-706).
-// STATUS: opt-in (OPTB_RNA_HAND=1).  The math is CPU-verified; the kernels were written after the round's GPU budget was
-// spent and have not run on hardware yet, so the generic engine stays the default for this energy.
+// Default for this energy (OPTB_GENERIC=1 selects the cached-Jacobian engine instead); parity: tests/test_gpu_generic_energies.py.
 #include <algorithm>
 #include <cub/cub.cuh>
 #include "solver.h"
@@ -111,6 +110,7 @@ struct RnaOps : EnergyOps<T> {
     }
     ~RnaOps() override { for (void* q : { (void*)D.pack, (void*)outStart, (void*)outNbr, (void*)inStart, (void*)inNbr, (void*)keysTmp, cubTemp }) if (q) cudaFree(q); }
     const char* name() const override { return "robust_nonrigid_alignment"; }
+    unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(D); }
     int grid() const { long g = ((long)D.N + kBlock - 1) / kBlock; long cap = (long)sms * 8; if (g > cap) g = cap; if (g > kMaxPartials) g = kMaxPartials; return g < 1 ? 1 : (int)g; }
     void bind(void** q) override {   // positions: robust_nonrigid_alignment.t:5-13
         D.wf = (T) * (const float*)q[0]; D.w = (T) * (const float*)q[1];

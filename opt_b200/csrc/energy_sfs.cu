@@ -10,8 +10,7 @@
 //   cost/modelCost, computeCtC                                                                 :580-592, :666-678, :616-622
 // Per PCG step the gather reads p, the 10 row coefficients and the flag byte of a pixel's neighbourhood (L1/L2 hits after
 // the first touch): ~53 B/pixel from HBM against the 208+ B/pixel of the cached-Jacobian engine this energy used before.
-// STATUS: opt-in (OPTB_SFS_HAND=1).  The math is CPU-verified; the kernels were written after the round's GPU budget was
-// spent and have not run on hardware yet, so the generic engine stays the default for this energy.
+// Default for this energy (OPTB_GENERIC=1 selects the cached-Jacobian engine instead); parity: tests/test_gpu_generic_energies.py.
 #include <type_traits>
 #include "solver.h"
 #include "sfs_device.cuh"
@@ -101,6 +100,7 @@ struct SfsOps : EnergyOps<T> {
     }
     ~SfsOps() override { cudaFree(P.B); cudaFree(P.dB); cudaFree(P.cR); cudaFree(P.cC); cudaFree(P.fl); }
     const char* name() const override { return "shape_from_shading"; }
+    unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(P); }
     void bind(void** q) override {   // positions: shape_from_shading.t:5-28 (all scalar Params are float, cast to opt_float on use, o.t:1699)
         auto f = [&](int k) { return (T) * (const float*)q[k]; };
         P.wp = (T)sqrt((double)f(0)); P.ws = (T)sqrt((double)f(1)); P.wg = (T)sqrt((double)f(2));

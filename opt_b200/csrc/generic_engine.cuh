@@ -336,6 +336,12 @@ struct GenericOpsBase : EnergyOps<T> {
         k_geSortValues<T><<<grid(nSlots), kBlock, 0, c.stream>>>(nSlots, srcS, val, valS);
     }
     void newSolve() override { structureValid = false; }
+    unsigned long long captureKey() const override {   // buffers bind()/linearise() may reallocate + the launch geometry of the row pass
+        const void* ptrs[] = { dLayout, val, colM, y, sliceStart, valS, rowS, active, F };
+        unsigned long long h = EnergyOps<T>::hashBytes(ptrs, sizeof(ptrs));
+        const long dims[] = { L.nRows, L.nEnt, (long)this->nUnknownsPadded, nSlots };
+        return EnergyOps<T>::hashBytes(dims, sizeof(dims), h);
+    }
     void pcgInit(const LaunchCtx& c, T* delta, T* r, T* pre, T* p, int rzSlot) override {
         linearise(c);
         k_geInit<T><<<grid(this->nUnknownsPadded), kBlock, 0, c.stream>>>((int)this->nUnknownsPadded, sliceStart, valS, rowS, F, active,

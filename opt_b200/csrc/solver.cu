@@ -14,6 +14,7 @@
 //   * PCGStep3 of iteration k is fused into PCGStep1 of iteration k+1 when the energy provides it.
 #include <cmath>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include "solver.h"
 #include "frontend.h"
@@ -61,21 +62,40 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, WindowRanges win
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
     pdlTrigger(); pdlWait();
     if (LM && ws.scalars[kFlags] != 0.0) return;
+    // The thread's first batch of loads is issued BEFORE alpha is awaited: none of the operands depends on it (they were all written
+    // by earlier kernels on this stream), and on several GPUs alpha = rz / p.Ap arrives through the NVLink mailboxes a few
+    // microseconds after the kernel starts -- that wait now overlaps the first HBM round trip instead of preceding it.
+    const long stride = (long)gridDim.x * kBlock;
+    long j = (long)blockIdx.x * kBlock + threadIdx.x;
+    V vd{}, vp{}, vr{}, vap{}, vpr{}, vb{};
+    long i = 0;
+    if (j < nVec) {
+        i = win.map(j);
+        vd = reinterpret_cast<const V*>(delta)[i]; vp = reinterpret_cast<const V*>(p)[i]; vr = reinterpret_cast<const V*>(r)[i];
+        vap = reinterpret_cast<const V*>(Ap)[i];
+        if (USEPRE) vpr = reinterpret_cast<const V*>(pre)[i];
+        if (LM) vb = reinterpret_cast<const V*>(b)[i];
+    }
     double dnum, dden; loadScalars2(ws, rzOld, kPAp, dnum, dden);
     const T num = (T)dnum, den = (T)dden;
     T alpha = T(0);
     if (den > T(0)) alpha = num / den;
     T accRz = T(0), accQ = T(0);
-    for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < nVec; j += (long)gridDim.x * kBlock) {
-        const long i = win.map(j);
+    while (j < nVec) {
         const bool mine = own.owns(i);
         T d[N], pp[N], rr[N], ap[N], pr[N], bb[N], zz[N];
-        unpack(reinterpret_cast<const V*>(delta)[i], d);
-        unpack(reinterpret_cast<const V*>(p)[i], pp);
-        unpack(reinterpret_cast<const V*>(r)[i], rr);
-        unpack(reinterpret_cast<const V*>(Ap)[i], ap);
-        if (USEPRE) unpack(reinterpret_cast<const V*>(pre)[i], pr);
-        if (LM) unpack(reinterpret_cast<const V*>(b)[i], bb);
+        unpack(vd, d); unpack(vp, pp); unpack(vr, rr); unpack(vap, ap);
+        if (USEPRE) unpack(vpr, pr);
+        if (LM) unpack(vb, bb);
+        const long iCur = i;
+        j += stride;
+        if (j < nVec) {   // next batch in flight while this one is computed and stored
+            i = win.map(j);
+            vd = reinterpret_cast<const V*>(delta)[i]; vp = reinterpret_cast<const V*>(p)[i]; vr = reinterpret_cast<const V*>(r)[i];
+            vap = reinterpret_cast<const V*>(Ap)[i];
+            if (USEPRE) vpr = reinterpret_cast<const V*>(pre)[i];
+            if (LM) vb = reinterpret_cast<const V*>(b)[i];
+        }
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             d[k] = d[k] + alpha * pp[k];
@@ -86,9 +106,9 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, WindowRanges win
                 if (LM) accQ += T(0.5) * (d[k] * (rr[k] + bb[k]));
             }
         }
-        reinterpret_cast<V*>(delta)[i] = pack(d);
-        reinterpret_cast<V*>(r)[i] = pack(rr);
-        if (mine) reinterpret_cast<V*>(z)[i] = pack(zz);   // halo entries of z belong to the neighbour's NVLink store (k_haloExchange)
+        reinterpret_cast<V*>(delta)[iCur] = pack(d);
+        reinterpret_cast<V*>(r)[iCur] = pack(rr);
+        if (mine) reinterpret_cast<V*>(z)[iCur] = pack(zz);   // halo entries of z belong to the neighbour's NVLink store (k_haloExchange)
     }
     gridReduceTo<kBlock>((double)accRz, ws, rzNew);
     if (LM) gridReduceTo<kBlock>((double)accQ, ws, kQ);
@@ -256,7 +276,8 @@ struct Plan : PlanBase {
     WindowRanges winVec{}, winScalar{};      // n == 0: stream the whole vectors
     long nVecWin() const { return winVec.n ? winVec.total : n / VecOf<T>::N; }
     // multi-GPU mailbox block (cudaMalloc'ed so it can be exported through CUDA IPC), see common.cuh CommView
-    struct CommBlock { unsigned long long words[kNumScalars][2][kMaxRanks][2]; unsigned long long haloFlags[2]; unsigned long long epoch[kNumScalars]; unsigned long long haloEpoch; };
+    struct CommBlock { unsigned long long words[kNumScalars][2][kMaxRanks][2]; unsigned long long haloFlags[2]; unsigned long long epoch[kNumScalars]; unsigned long long haloEpoch;
+                       unsigned long long fitFlags[kMaxRanks]; };   // fitFlags[r]: (connect generation << 2) | 1 (rank r cannot run the collective loop kernel) or 2 (it can)
     CommBlock* commBlock = nullptr;
     int world = 1, rank = 0;
     HaloPlan haloP{}, haloZ{};
@@ -269,7 +290,8 @@ struct Plan : PlanBase {
     cudaEvent_t evEntry = nullptr, evLoop0 = nullptr, evLoop1 = nullptr;
     int numSMs = 148;
     int gridStream = 0;          // CTAs for the streaming kernels
-    cudaGraphExec_t loopExec = nullptr; int loopExecIters = -1; bool loopExecFused = false;
+    int gridStep2 = 0;           // CTAs for PCGStep2 (co-resident count)
+    cudaGraphExec_t loopExec = nullptr; unsigned long long loopExecKey = 0; int graphBuilds = 0;
     bool useGraph = true, useFusion = true, usePdl = false;   // PDL measured slower here (early-resident dependents crowd the streaming kernels): opt-in via OPTB_PDL=1
     // nonlinear state (:994-1006)
     int nIter = 0;
@@ -301,6 +323,16 @@ struct Plan : PlanBase {
         long nVec = n / VecOf<T>::N;
         gridStream = (int)std::min<long>((nVec + kBlock - 1) / kBlock, (long)numSMs * 8);
         if (gridStream < 1) gridStream = 1;
+        {   // PCGStep2 keeps more registers than the 32 that 8 CTAs/SM would allow: size its grid to what is actually co-resident, so the
+            // grid-stride loop runs as ONE wave (a partial second wave of 2 CTAs per SM cannot saturate HBM)
+            const void* fn = lm ? (E->usePreconditioner ? (const void*)k_pcgStep2<T, true, true> : (const void*)k_pcgStep2<T, true, false>)
+                                : (E->usePreconditioner ? (const void*)k_pcgStep2<T, false, true> : (const void*)k_pcgStep2<T, false, false>);
+            int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBlock, 0);
+            if (occ < 1) occ = 1; if (occ > 8) occ = 8;
+            gridStep2 = (int)std::min<long>((nVec + kBlock - 1) / kBlock, (long)numSMs * occ);
+            if (gridStep2 < 1) gridStep2 = 1;
+            if (const char* e = getenv("OPTB_GRID_STEP2")) gridStep2 = std::max(1, std::min(atoi(e), kMaxPartials));   // experiments: also changes the summation order of r.z
+        }
         if (const char* s = getenv("OPTB_NO_GRAPH")) useGraph = atoi(s) == 0;
         if (const char* s = getenv("OPTB_NO_FUSION")) useFusion = atoi(s) == 0;
         if (const char* s = getenv("OPTB_PDL")) usePdl = atoi(s) != 0;
@@ -417,8 +449,30 @@ struct Plan : PlanBase {
             }
             winVec.n = winScalar.n = (int)wins.size();
         }
+        if (segs.size() > 4 || ranges.size() > 4) { fprintf(stderr, "opt_b200: at most 4 halo segments / owned ranges per rank are supported\n"); return -5; }
         if (loopExec) { cudaGraphExecDestroy(loopExec); loopExec = nullptr; }
+        // collective decision about the one-kernel PCG loop: every rank posts whether it can run it, into every rank's block;
+        // the first runLoop after this waits for all the answers (multiLoopAgreed)
+        ++connectGen; multiLoopState = -1;
+        const bool fits = persistentMode != 0 && !lm && !getenv("OPTB_NO_RESIDENT") && E->pcgLoopMultiFits();
+        const unsigned long long word = ((unsigned long long)connectGen << 2) | (fits ? 2ull : 1ull);
+        for (int r = 0; r < world; ++r) OPT_CUDA_CHECK(cudaMemcpy(&peerBlocks[r]->fitFlags[rank], &word, sizeof(word), cudaMemcpyDefault));
         return 0;
+    }
+    unsigned connectGen = 0; int multiLoopState = -1;   // -1: not resolved yet, 0: per-step loop on every rank, 1: collective loop kernel on every rank
+    bool multiLoopAgreed() {
+        if (multiLoopState >= 0) return multiLoopState == 1;
+        unsigned long long f[kMaxRanks];
+        for (int spin = 0; ; ++spin) {   // a peer may still be inside its own OptB200_PlanConnect
+            OPT_CUDA_CHECK(cudaMemcpy(f, commBlock->fitFlags, sizeof(f), cudaMemcpyDeviceToHost));
+            bool all = true, yes = true;
+            for (int r = 0; r < world; ++r) { if ((f[r] >> 2) != connectGen) all = false; else if ((f[r] & 3ull) != 2ull) yes = false; }
+            if (all) { multiLoopState = yes ? 1 : 0; break; }
+            if (spin > 60000) { fprintf(stderr, "opt_b200: rank %d: the other ranks never finished OptB200_PlanConnect\n", rank); exit(4); }
+            struct timespec ts = { 0, 1000000 }; nanosleep(&ts, nullptr);
+        }
+        if (verbosity > 1) printf("opt_b200: rank %d: PCG loop as one collective kernel: %s\n", rank, multiLoopState ? "yes" : "no");
+        return multiLoopState == 1;
     }
     CommBlock* peerBlocks[kMaxRanks] = {};
     unsigned long long* hostPeerTable[kMaxRanks] = {};
@@ -455,11 +509,11 @@ struct Plan : PlanBase {
     void launchStep2(int rzOld, int rzNew, T* p) {
         long nVec = n / VecOf<T>::N;
         if (lm) {
-            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
-            else k_pcgStep2<T, true, false><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStep2, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            else k_pcgStep2<T, true, false><<<gridStep2, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
         } else {
-            if (E->usePreconditioner) launchPdl(k_pcgStep2<T, false, true>, gridStream, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
-            else launchPdl(k_pcgStep2<T, false, false>, gridStream, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            if (E->usePreconditioner) launchPdl(k_pcgStep2<T, false, true>, gridStep2, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            else launchPdl(k_pcgStep2<T, false, false>, gridStep2, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
         }
         ++launches;
     }
@@ -517,7 +571,7 @@ struct Plan : PlanBase {
     void runLoop(int L) {
         bool fuse = loopFuses();
         OPT_CUDA_CHECK(cudaEventRecord(evLoop0, stream));
-        if (persistentMode != 0 && !lm && L > 0 && (world == 1 || persistentMode > 0)) {   // whole loop as one cooperative kernel where the energy offers it
+        if (persistentMode != 0 && !lm && L > 0 && (world == 1 || multiLoopAgreed())) {   // whole loop as one cooperative kernel where the energy offers it
             T* pf = nullptr;
             if (world > 1 && !pHaloFresh) { exchangeHalo(haloP, p); pHaloFresh = true; }   // the multi-rank form stages p's halo rows from memory
             if (E->pcgLoop(ctx(), L, persistentMode > 0, delta, r, z, p, p2, Ap, pre, &pf, world > 1 ? &haloZ : nullptr)) {
@@ -527,16 +581,28 @@ struct Plan : PlanBase {
             }
         }
         if (useGraph && L > 0) {
-            if (!loopExec || loopExecIters != L || loopExecFused != fuse) {
-                if (loopExec) { cudaGraphExecDestroy(loopExec); loopExec = nullptr; }
+            // The captured kernel nodes hold their arguments BY VALUE (weights, caller pointers, plan-owned buffers the energy may have
+            // reallocated in bind()/pcgInit(), q_tolerance, the reset period): re-capture whenever any of that differs from what the
+            // cached graph was built from.  Same topology => cudaGraphExecUpdate patches the node parameters in place (microseconds).
+            unsigned long long key = E->captureKey();
+            { const long v[] = { (long)L, (long)fuse, (long)sp.residual_reset_period, (long)world, (long)rank }; key = EnergyOps<T>::hashBytes(v, sizeof(v), key); }
+            key = EnergyOps<T>::hashValue(sp.q_tolerance, key);
+            key = EnergyOps<T>::hashValue(winVec, key); key = EnergyOps<T>::hashValue(ownVec, key);
+            if (!loopExec || loopExecKey != key) {
                 cudaGraph_t g;
                 int saved = launches;
                 OPT_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
                 emitLoop(L, fuse);
                 OPT_CUDA_CHECK(cudaStreamEndCapture(stream, &g));
-                OPT_CUDA_CHECK(cudaGraphInstantiate(&loopExec, g, 0));
+                bool updated = false;
+                if (loopExec) {
+                    cudaGraphExecUpdateResultInfo info{};
+                    if (cudaGraphExecUpdate(loopExec, g, &info) == cudaSuccess) updated = true;
+                    else { cudaGetLastError(); cudaGraphExecDestroy(loopExec); loopExec = nullptr; }
+                }
+                if (!updated) OPT_CUDA_CHECK(cudaGraphInstantiate(&loopExec, g, 0));
                 OPT_CUDA_CHECK(cudaGraphDestroy(g));
-                loopExecIters = L; loopExecFused = fuse;
+                loopExecKey = key; ++graphBuilds;
                 loopLaunchCount = launches - saved; launches = saved; loopPFinal = pFinal;
             }
             pFinal = loopPFinal;
@@ -762,8 +828,8 @@ static EnergyOps<T>* makeEnergy(const std::string& energy, const unsigned* dims)
     // OPTB_GENERIC=1 routes every energy (image_warping included) through the generic cached-Jacobian engine
     if (energy == "image_warping" && !getenv("OPTB_GENERIC")) return makeImageWarping<T>(dims);
     if (energy == "arap_mesh_deformation" && !getenv("OPTB_GENERIC")) return makeArapMesh<T>(dims);
-    if (energy == "robust_nonrigid_alignment" && getenv("OPTB_RNA_HAND") && !getenv("OPTB_GENERIC")) return makeRna<T>(dims);   // hand-written set, opt-in until it has run on hardware
-    if (energy == "shape_from_shading" && getenv("OPTB_SFS_HAND") && !getenv("OPTB_GENERIC")) return makeSfs<T>(dims);   // hand-written set, opt-in until it has run on hardware
+    if (energy == "robust_nonrigid_alignment" && !getenv("OPTB_GENERIC")) return makeRna<T>(dims);
+    if (energy == "shape_from_shading" && !getenv("OPTB_GENERIC")) return makeSfs<T>(dims);
     return makeGenericEnergy<T>(energy, dims);
 }
 

@@ -98,6 +98,10 @@ struct EnergyOps {
     virtual void modelCost(const LaunchCtx&, const T* /*delta*/) { unsupported("modelCost (LM)"); }
     // ComputedArray refresh (kernels.precompute, solverGPUGaussNewton.t:607-614)
     virtual void precompute(const LaunchCtx&) {}
+    // multi-GPU: can THIS rank run pcgLoop's multi-rank form for its slab (tile shape fits the shared memory, all tiles co-resident,
+    // cooperative launch available)?  Asked once per OptB200_PlanConnect, after setSlab(); the plan combines the answers of all ranks
+    // so that either every rank takes the collective kernel or none does.  After a "yes" a refusal inside pcgLoop is fatal.
+    virtual bool pcgLoopMultiFits() { return false; }
     // ---- multi-GPU slab decomposition.  The plan's dimensions describe the LOCAL domain =
     // owned slab rows + halo rows; [ownedBegin, ownedEnd) are the owned local rows, upperRows/lowerRows the
     // local row counts of the neighbouring ranks (0 = no neighbour).  Returns false if unsupported.
@@ -109,6 +113,17 @@ struct EnergyOps {
     virtual std::vector<std::pair<long, long>> processScalarRanges() const { return {}; }
     // called at every Opt_ProblemInit: graph indices / masks may have changed since the last solve
     virtual void newSolve() {}
+    // Fingerprint of everything the inner-loop kernels (applyJTJ / step3ApplyJTJ) receive BY VALUE or as launch geometry:
+    // weights, caller pointers, plan-owned buffers that bind()/pcgInit() may reallocate, residual counts.  The plan compares it
+    // (after pcgInit, when all of that is final for the step) with the fingerprint its captured PCG-loop graph was built from and
+    // re-captures on a mismatch -- the reference re-reads problemparams at every Init/Step (util.t:664-692).
+    virtual unsigned long long captureKey() const = 0;
+    static unsigned long long hashBytes(const void* data, size_t n, unsigned long long h = 1469598103934665603ull) {   // FNV-1a
+        const unsigned char* b = (const unsigned char*)data;
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+        return h;
+    }
+    template <class V> static unsigned long long hashValue(const V& v, unsigned long long h = 1469598103934665603ull) { return hashBytes(&v, sizeof(V), h); }
     virtual const char* name() const = 0;
     static void unsupported(const char* what) {
         fprintf(stderr, "opt_b200: %s is not implemented for this energy\n", what);
@@ -160,8 +175,8 @@ bool compileSpecToCubin(const fe::CompiledSpec& cs, bool doublePrecision, std::v
 // per-energy factories (energy_*.cu); return nullptr when the energy/precision is not built
 template <class T> EnergyOps<T>* makeImageWarping(const unsigned* dims);
 template <class T> EnergyOps<T>* makeArapMesh(const unsigned* dims);
-template <class T> EnergyOps<T>* makeSfs(const unsigned* dims);   // energy_sfs.cu (opt-in: OPTB_SFS_HAND=1)
-template <class T> EnergyOps<T>* makeRna(const unsigned* dims);   // energy_rna.cu (opt-in: OPTB_RNA_HAND=1)
+template <class T> EnergyOps<T>* makeSfs(const unsigned* dims);   // energy_sfs.cu
+template <class T> EnergyOps<T>* makeRna(const unsigned* dims);   // energy_rna.cu
 template <class T> EnergyOps<T>* makeGenericEnergy(const std::string& energy, const unsigned* dims);
 
 }  // namespace optb

@@ -10,15 +10,28 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def _setup(torch, dist):
+    """one rank per GPU over NCCL; with fewer GPUs than ranks (OPTB_SHARE_GPU=1, e.g. the driver's 1-GPU test box) the ranks share
+    GPUs -- CUDA IPC, the peer-memory mailboxes and the halo stores work the same between two processes on one device (the
+    processes time-slice, so it is slow) -- and torch.distributed's plumbing runs over gloo (NCCL refuses two ranks on one GPU)"""
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    ngpu = torch.cuda.device_count()
+    if os.environ.get("OPTB_SHARE_GPU") and ngpu < world:
+        torch.cuda.set_device(local % ngpu)
+        dist.init_process_group("gloo")
+        return rank, world, local, "cpu"
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, "cuda"
+
+
 def main_arap():
     """vertex-slab decomposition of arap_mesh_deformation vs the single-GPU solve"""
     import torch
     import torch.distributed as dist
     from opt_b200 import OptSolver, spec_path, workloads
     from opt_b200.distributed import VertexSlab, connect_plan
-    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world, local, flag_dev = _setup(torch, dist)
     nx, ny = int(sys.argv[2]), int(sys.argv[3]); kind = sys.argv[4] if len(sys.argv) > 4 else "gaussNewtonGPU"
     sp = {"nIterations": 3, "lIterations": 30}
     full = workloads.arap_mesh(nx, ny, n_handles=12)
@@ -46,7 +59,7 @@ def main_arap():
         print(f"multi_gpu_check ARAP world={world} {nx}x{ny} {kind} halo={slab.halo}: costs {costs[0]:.6f} -> {costs[-1]:.6f}; vs 1 GPU: cost rel {rel_c:.2e}, Offset {e_off:.2e}, Angle {e_ang:.2e}")
         print("  multi :", [f"{c:.6g}" for c in costs]); print("  single:", [f"{c:.6g}" for c in c1])
         ok = rel_c < 1e-4 and e_off < 1e-5 and e_ang < 2e-3 and len(costs) == len(c1)
-    flag = torch.tensor([1 if ok else 0], device="cuda")
+    flag = torch.tensor([1 if ok else 0], device=flag_dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
@@ -59,9 +72,7 @@ def main():
     import torch.distributed as dist
     from opt_b200 import OptSolver, spec_path, workloads
     from opt_b200.distributed import Slab, scatter_image_params, connect_plan, gather_owned_rows
-    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world, local, flag_dev = _setup(torch, dist)
     W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (128, 96)
     kind = sys.argv[3] if len(sys.argv) > 3 else "gaussNewtonGPU"
     sp = {"nIterations": 3, "lIterations": 40}
@@ -101,7 +112,7 @@ def main():
         print(f"  launches in the last step: {launches}")
         if max_launches > 0 and launches > max_launches:
             print(f"  expected at most {max_launches} launches: the persistent multi-GPU loop was not taken"); ok = False
-    flag = torch.tensor([1 if ok else 0], device="cuda")
+    flag = torch.tensor([1 if ok else 0], device=flag_dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)

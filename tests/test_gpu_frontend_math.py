@@ -4,9 +4,7 @@ round-end run; a surprise here must not hide the rest of the suite behind `-x`."
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first run on hardware is the round-end run (written after the round's GPU budget was "
-                                                     "spent); remove this mark once it has passed on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 MATH_FNS = {   # name -> (numpy function, derivative, constant that keeps a*x + c inside the domain)

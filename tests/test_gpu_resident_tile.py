@@ -9,9 +9,7 @@ import pytest
 
 from opt_b200 import workloads
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="k_iwPcgLoopTile has not been run on hardware yet (written after the round's GPU budget "
-                                                     "was spent); remove this mark once it has passed on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 @contextlib.contextmanager

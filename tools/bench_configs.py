@@ -46,13 +46,16 @@ def run(name, dims, spec, kind, host, dp, liters, steps=6, warmup=3, bytes_per_s
     s.close()
 
 
+ENGINE = " [generic engine]" if os.environ.get("OPTB_GENERIC") else ""
+
+
 def main():
     from opt_b200 import workloads
-    which = sys.argv[1:] or ["iw512", "sfs", "arap500k", "arap500k_generic", "rna"]   # also: sfs_hand, rna_hand (opt-in kernel sets)
+    which = sys.argv[1:] or ["iw512", "sfs", "arap500k", "arap500k_generic", "rna"]   # OPTB_GENERIC=1: everything on the cached-Jacobian engine
     if "iw512" in which:
         run("image_warping 512x512 fp32 GN", [512, 512], "image_warping", "gaussNewtonGPU", workloads.image_warping(512, 512), False, 400, bytes_per_step=188 * 512 * 512)
     if "sfs" in which:
-        run("shape_from_shading 640x480 fp32 LM (synthetic depth)", [640, 480], "shape_from_shading", "LMGPU", workloads.shape_from_shading(640, 480), False, 10, steps=10,
+        run("shape_from_shading 640x480 fp32 LM (synthetic depth)" + ENGINE, [640, 480], "shape_from_shading", "LMGPU", workloads.shape_from_shading(640, 480), False, 10, steps=10,
             bytes_per_step=90 * 640 * 480)
     nx = 708
     nv = nx * nx
@@ -67,21 +70,11 @@ def main():
             run(f"arap_mesh_deformation {nv} vertices / {ne} directed edges fp32 GN" + (" [generic engine]" if tag.endswith("generic") else ""), [nv], "arap_mesh_deformation",
                 "gaussNewtonGPU", workloads.clone_params(host), False, 100, bytes_per_step=396 * nv + 8 * ne)
             os.environ.pop("OPTB_GENERIC", None)
-    if "sfs_hand" in which:   # hand-written kernel set (energy_sfs.cu), opt-in until validated on hardware
-        os.environ["OPTB_SFS_HAND"] = "1"
-        run("shape_from_shading 640x480 fp32 LM (synthetic depth) [hand-written set]", [640, 480], "shape_from_shading", "LMGPU", workloads.shape_from_shading(640, 480), False, 10, steps=10,
-            bytes_per_step=90 * 640 * 480)
-        os.environ.pop("OPTB_SFS_HAND", None)
-    for tag in ("rna", "rna_hand"):
-        if tag not in which:
-            continue
+    if "rna" in which:
         n2 = 316
         host = workloads.robust_nonrigid(n2, n2, dtype=np.float64, perturb=0.05)   # perturbed: the unperturbed start converges inside the warm-up
-        if tag == "rna_hand":
-            os.environ["OPTB_RNA_HAND"] = "1"
-        run(f"robust_nonrigid_alignment {n2 * n2} vertices fp64 LM " + ("[hand-written set]" if tag == "rna_hand" else "[generic engine]"), [n2 * n2], "robust_nonrigid_alignment", "LMGPU",
+        run(f"robust_nonrigid_alignment {n2 * n2} vertices fp64 LM" + ENGINE, [n2 * n2], "robust_nonrigid_alignment", "LMGPU",
             host, True, 250, steps=4, warmup=1, bytes_per_step=1136 * n2 * n2 + 8 * host[8])
-        os.environ.pop("OPTB_RNA_HAND", None)
 
 
 if __name__ == "__main__":

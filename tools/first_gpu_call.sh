@@ -1,15 +1,20 @@
 #!/bin/bash
-# One gpurun call that answers everything ROUND2_CHECKLIST.md asks of a single B200:
+# One single-GPU gpurun call: the whole -m gpu suite (with xfail/xpass report), two ranks time-slicing ONE GPU through the
+# multi-rank paths (per-step loop and the collective one-kernel loop), the secondary configs, and the bench line.
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/first_gpu_call.sh'
-# Results land in gpurun_out/ (merged back): tests.txt (incl. which xfail-marked tests XPASSed), configs.jsonl, bench.json.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu -rxX 2>&1 | tail -60 > gpurun_out/tests.txt
+timeout 900 python -m pytest tests -q -m gpu -rxXs -x 2>&1 | tail -80 > gpurun_out/tests.txt
+tr() { python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port $1 tests/multi_gpu_check.py "${@:2}"; }
+{
+  echo "== shared GPU, per-step loop"; OPTB_SHARE_GPU=1 OPTB_PERSISTENT=0 timeout 300 tr 29611 128 96 gaussNewtonGPU 2>&1 | tail -8
+  echo "== shared GPU, collective loop kernel"; OPTB_SHARE_GPU=1 OPTB_TEST_MAX_LAUNCHES=12 timeout 300 tr 29612 128 96 gaussNewtonGPU 2>&1 | tail -8
+  echo "== shared GPU, collective loop kernel, 64x8 tiles"; OPTB_SHARE_GPU=1 OPTB_TEST_MAX_LAUNCHES=12 OPTB_RESIDENT_TILE=64x8 timeout 300 tr 29613 256 130 gaussNewtonGPU 2>&1 | tail -8
+} > gpurun_out/shared_gpu.txt 2>&1
 {
   timeout 300 python tools/bench_configs.py iw512 sfs arap500k
-  timeout 200 python tools/bench_configs.py sfs_hand
-  timeout 300 python tools/bench_configs.py rna rna_hand
-  OPTB_PERSISTENT=0 timeout 120 python tools/bench_configs.py iw512
-  OPTB_PERSISTENT=1 OPTB_RESIDENT_TILE=64x32 timeout 120 python tools/bench_configs.py iw512
+  OPTB_GENERIC=1 timeout 200 python tools/bench_configs.py sfs
+  timeout 300 python tools/bench_configs.py rna
+  OPTB_GENERIC=1 timeout 300 python tools/bench_configs.py rna
 } > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
 timeout 400 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -5 gpurun_out/tests.txt; grep -c config gpurun_out/configs.jsonl; cut -c1-200 gpurun_out/bench.json
+tail -5 gpurun_out/tests.txt; cat gpurun_out/shared_gpu.txt | grep -E "==|multi_gpu_check|launches|Error|error" | head -20; cut -c1-300 gpurun_out/bench.json

@@ -87,88 +87,208 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample_reference(rows=256, pcg_iters=4, target_seconds=0.0):
-    """kind "reference": matrix-free PCG steps built from the reference's OWN per-pixel functions (examples/image_warping/src/
-    WarpingSolverEquations.h: evalMinusJTFDevice, applyJTJDevice) compiled for the host into oracle/_ref/libref_iw.so
-    (oracle/ref_build.sh, oracle/ref_iw_shim.cpp ref_iw_pcg), OpenMP over the pixels, on a W_FULL x rows slab.
-    Returns None when the library is not there (it is built where /root/reference is mounted and travels with the snapshot)."""
-    import ctypes
-    import numpy as np
-    from opt_b200 import workloads
-    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libref_iw.so")
-    if not os.path.exists(so):
-        return None
-    L = ctypes.CDLL(so)
-    if not hasattr(L, "ref_iw_pcg"):
-        return None
-    L.ref_iw_pcg.restype = ctypes.c_double
-    host = workloads.image_warping(W_FULL, rows, seed=0, mask="none", n_constraints=3)
-    off, ang, ur, cons, m, wf, wr = host[0], host[1], host[2], host[3], host[4], host[5], host[6]
-    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    nt = ctypes.c_int(0); rz = ctypes.c_double(0)
-    t0 = time.time()
-    # the hand-written solver takes the UNSQUARED weights (its energy is sum w r^2, twice Opt's convention: oracle/ref_iw_shim.cpp)
-    call = lambda n: L.ref_iw_pcg(ctypes.c_int(W_FULL), ctypes.c_int(rows), fp(off), fp(ang), fp(ur), fp(m), fp(cons), ctypes.c_float(wf * wf), ctypes.c_float(wr * wr),
-                                  ctypes.c_int(n), ctypes.byref(nt), ctypes.byref(rz))
-    if target_seconds > 0:      # size the sample: a short calibration run, then enough iterations for about target_seconds of CPU work
-        cal = call(4)
-        pcg_iters = int(min(2000, max(pcg_iters, target_seconds / max(cal / 4, 1e-6))))
-    sec = call(pcg_iters)
-    wall = time.time() - t0
-    if not (sec > 0) or not np.isfinite(rz.value):
-        return None
-    full_rate = (pcg_iters / sec) * rows / H_FULL           # cost is linear in pixels
-    return {"value": full_rate, "unit": "PCG steps/s", "cores": int(nt.value), "kind": "reference",
-            "sample": f"the reference's own evalMinusJTFDevice/applyJTJDevice (WarpingSolverEquations.h, compiled for the host: oracle/_ref) in a matrix-free "
-                      f"PCG with OpenMP over the pixels, {W_FULL}x{rows} slab, {pcg_iters} PCG steps in {sec:.2f}s (wall incl. set-up {wall:.1f}s), "
-                      f"scaled by {rows}/{H_FULL} to the full image"}, wall
-
-
-def cpu_sample(steps=1, rows=256, pcg_iters=4, target_seconds=10.0):
-    """CPU baseline on a W_FULL x rows slab of the workload, PCG steps/s scaled to the full image: the reference's own equations on the
-    host when oracle/_ref is there (kind "reference"), else the CPU oracle (kind "port")"""
+def effective_cpus():
+    """cores this process may really use: the affinity mask, cut by the cgroup CPU quota (omp_get_max_threads() / nproc report every
+    core of the host, which oversubscribes a quota-limited container and made round 1's CPU numbers swing by 80x)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
-        ref = cpu_sample_reference(rows=rows, pcg_iters=max(pcg_iters, 8), target_seconds=target_seconds)
-    except Exception as e:      # a broken oracle/_ref must not take the bench line down: fall back to the port and say so
-        print(f"bench: reference CPU baseline unavailable ({type(e).__name__}: {e}); timing the oracle port instead", file=sys.stderr)
-        ref = None
-    if ref is not None:
-        return ref
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]           # cgroup v2
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())   # v1
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+CPU_ROWS, CPU_STEPS, CPU_REPEATS = 1024, 100, 3      # fixed sample: W_FULL x 1024 slab, 100 PCG steps, best of 3
+
+
+def _cpu_child(rows, steps, threads, repeats):
+    """runs in a fresh interpreter (no torch, no inherited OMP settings): see cpu_sample.  Prints one JSON object."""
+    import ctypes
     from opt_b200 import workloads
-    from oracle.oracle import Oracle, num_threads
+    out = {"kind": None}
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_iw.so")
     host = workloads.image_warping(W_FULL, rows, seed=0, mask="none", n_constraints=3)
-    o = Oracle("image_warping", "gaussNewtonGPU", [W_FULL, rows])
-    o.set_solver_parameter("nIterations", steps); o.set_solver_parameter("lIterations", pcg_iters)
+    if os.path.exists(so) and hasattr(ctypes.CDLL(so), "ref_iw_pcg"):
+        L = ctypes.CDLL(so)
+        L.ref_iw_pcg.restype = ctypes.c_double
+        off, ang, ur, cons, m, wf, wr = host[:7]
+        fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        secs = []
+        for _ in range(repeats):
+            x, a = off.copy(), ang.copy()
+            nt = ctypes.c_int(threads); rz = ctypes.c_double(0)
+            # the hand-written solver takes the UNSQUARED weights (its energy is sum w r^2, twice Opt's convention: oracle/ref_iw_shim.cpp)
+            sec = L.ref_iw_pcg(ctypes.c_int(W_FULL), ctypes.c_int(rows), fp(x), fp(a), fp(ur), fp(m), fp(cons), ctypes.c_float(wf * wf), ctypes.c_float(wr * wr),
+                               ctypes.c_int(steps), ctypes.byref(nt), ctypes.byref(rz))
+            if sec > 0 and np.isfinite(rz.value):
+                secs.append(sec)
+        if secs:
+            out = {"kind": "reference", "seconds": secs, "threads": int(nt.value), "steps": steps}
+    if out["kind"] is None:      # oracle/_ref is built where /root/reference is mounted and travels with the snapshot; without it: the oracle port
+        from oracle.oracle import Oracle, num_threads
+        secs = []
+        for _ in range(repeats):
+            o = Oracle("image_warping", "gaussNewtonGPU", [W_FULL, rows])
+            o.set_solver_parameter("nIterations", 1); o.set_solver_parameter("lIterations", steps)
+            hp = workloads.clone_params(host)
+            o.init(hp)
+            while o.step(hp):
+                pass
+            secs.append(o.get_scalar("secondsLinear") * steps / max(o.get_scalar("linearSteps"), 1))
+        out = {"kind": "port", "seconds": secs, "threads": num_threads(), "steps": steps}
+    print("CPU_SAMPLE " + json.dumps(out), flush=True)
+
+
+def cpu_sample(rows=CPU_ROWS, steps=CPU_STEPS, repeats=CPU_REPEATS):
+    """CPU baseline: PCG steps/s of the reference's own per-pixel equations (examples/image_warping/src/WarpingSolverEquations.h:
+    evalMinusJTFDevice, applyJTJDevice, compiled for the host into oracle/_ref/libref_iw.so by oracle/ref_build.sh; kind "reference")
+    in a matrix-free PCG with OpenMP over the pixels -- or of the CPU oracle (kind "port") when oracle/_ref is absent -- on a FIXED sample
+    (W_FULL x rows slab, `steps` PCG steps, best of `repeats`), scaled by rows/H_FULL to the full image (the cost is linear in the
+    pixel count).  Runs in a child interpreter with OMP_NUM_THREADS = the cores the cgroup/affinity really grant (torchrun exports
+    OMP_NUM_THREADS=1 to its workers), OMP_PROC_BIND=close, OMP_PLACES=cores."""
+    n = effective_cpus()
+    env = dict(os.environ)
+    env.update({"OMP_NUM_THREADS": str(n), "OMP_PROC_BIND": "close", "OMP_PLACES": "cores", "OMP_WAIT_POLICY": "active", "OMP_DYNAMIC": "false"})
     t0 = time.time()
-    o.init(host)
-    n = 0
-    while o.step(host):
-        n += 1
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-child", f"{rows},{steps},{n},{repeats}"], capture_output=True, text=True, env=env, timeout=900)
     wall = time.time() - t0
-    lin_s = o.get_scalar("secondsLinear"); lin_n = o.get_scalar("linearSteps")
-    slab_rate = lin_n / lin_s                       # PCG steps/s on the slab
-    full_rate = slab_rate * rows / H_FULL           # cost is linear in pixels
-    return {"value": full_rate, "unit": "PCG steps/s", "cores": num_threads(), "kind": "port",
-            "sample": f"oracle (C++/OpenMP, explicit-J CGNR-style PCG) on a {W_FULL}x{rows} slab, {int(lin_n)} PCG steps in {lin_s:.1f}s "
-                      f"(wall incl. linearisation {wall:.1f}s), scaled by {rows}/{H_FULL} to the full image"}, wall
+    rec = None
+    for line in r.stdout.splitlines():
+        if line.startswith("CPU_SAMPLE "):
+            rec = json.loads(line[len("CPU_SAMPLE "):])
+    if rec is None or not rec.get("seconds"):
+        raise RuntimeError("CPU baseline child failed: " + (r.stderr or r.stdout)[-500:])
+    best = min(rec["seconds"])
+    rate = (rec["steps"] / best) * rows / H_FULL
+    what = ("the reference's own evalMinusJTFDevice/applyJTJDevice (WarpingSolverEquations.h, compiled for the host: oracle/_ref) in a matrix-free PCG, OpenMP over the pixels"
+            if rec["kind"] == "reference" else "oracle port (C++/OpenMP, explicit-J PCG)")
+    return {"value": rate, "unit": "PCG steps/s", "cores": rec["threads"], "kind": rec["kind"],
+            "sample": f"{what}; fixed sample: {W_FULL}x{rows} slab, {rec['steps']} PCG steps, best of {len(rec['seconds'])} "
+                      f"({', '.join('%.2f' % x for x in rec['seconds'])} s), scaled by {rows}/{H_FULL} to the full image; "
+                      f"{rec['threads']} threads (affinity mask and cgroup quota), OMP_PROC_BIND=close"}, wall
+
+
+def parity_vs_n1(solver, slab, dev, host, W, H, liters, rank, world, checkpoints=(1, 3)):
+    """Evidence that the N-rank solve computes what the single-GPU solve computes (the driver's pytest box has one GPU, so the
+    multi-GPU pytest cases are skipped there; this record travels in the SCALE file instead).  All ranks solve `max(checkpoints)`
+    GN iterations of THE timed problem together; rank 0 then solves the same problem alone on its GPU with an unconnected plan, twice:
+    with the default launch geometry and with a different PCGStep2 grid (another summation order of r.z -- the same arithmetic, other
+    rounding).  The spread between those two single-GPU runs is the fp32 noise floor of this problem at this iteration count; the
+    N-rank result must lie within `factor` x that floor (plus an absolute floor) of the single-GPU result.
+    Reported per checkpoint: cost of both solves, relative cost difference, and the L2 distance of the unknowns relative to the L2 norm
+    of the update the solve has made so far (||X_k - X_0||) -- the same two quantities for the noise floor."""
+    import torch
+    import torch.distributed as dist
+    from opt_b200 import OptSolver, spec_path, workloads
+    from opt_b200.distributed import Slab
+    kmax = max(checkpoints)
+    rows = slab.g1 - slab.g0
+    maxrows = max(Slab(H, world, r).g1 - Slab(H, world, r).g0 for r in range(world))
+    x0 = [dev[0].clone(), dev[1].clone()]
+
+    def owned(t, ch):
+        v = t.view(slab.local_rows, W, ch)[slab.owned_begin:slab.owned_end]
+        pad = torch.zeros((maxrows, W, ch), device=t.device, dtype=t.dtype); pad[:rows] = v
+        return pad
+
+    def gather_full(t, ch):
+        mine = owned(t, ch).contiguous()
+        out = torch.empty((world,) + tuple(mine.shape), device=mine.device, dtype=mine.dtype)
+        dist.all_gather_into_tensor(out, mine)
+        parts = []
+        for r in range(world):
+            sr = Slab(H, world, r)
+            parts.append(out[r, :sr.g1 - sr.g0])
+        return torch.cat(parts, 0).reshape(H * W, ch)
+
+    solver.set_solver_parameters({"nIterations": kmax, "lIterations": liters})
+    solver.init(dev)
+    multi = {}
+    for k in range(1, kmax + 1):
+        solver.step(dev)
+        if k in checkpoints:
+            multi[k] = (solver.current_cost(), gather_full(dev[0], 2), gather_full(dev[1], 1))
+    torch.cuda.synchronize()
+    dev[0].copy_(x0[0]); dev[1].copy_(x0[1])          # the timed arms start from the original unknowns
+    rec = None
+    if rank == 0:
+        full = workloads.image_warping(W, H, seed=0, mask="none")
+
+        def single(env):
+            old = {k: os.environ.get(k) for k in env}
+            os.environ.update(env)
+            try:
+                d1 = workloads.to_device(workloads.clone_params(full))
+                s1 = OptSolver([W, H], spec_path("image_warping"), "gaussNewtonGPU")
+            finally:
+                for k, v in old.items():
+                    os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+            s1.set_solver_parameters({"nIterations": kmax, "lIterations": liters})
+            s1.init(d1)
+            out = {}
+            for k in range(1, kmax + 1):
+                s1.step(d1)
+                if k in checkpoints:
+                    out[k] = (s1.current_cost(), d1[0].clone().reshape(H * W, 2), d1[1].clone().reshape(H * W, 1))
+            torch.cuda.synchronize()
+            s1.close()
+            return out
+        ref = single({})
+        alt = single({"OPTB_GRID_STEP2": "333", "OPTB_PERSISTENT": "0"})      # other summation order, kernel-per-step loop
+        X0 = (torch.from_numpy(full[0]).cuda().reshape(H * W, 2), torch.from_numpy(full[1]).cuda().reshape(H * W, 1))
+
+        def dist_rel(a, b):
+            upd = float(torch.sqrt(((b[1] - X0[0]) ** 2).sum() + ((b[2] - X0[1]) ** 2).sum()))
+            d = float(torch.sqrt(((a[1] - b[1]) ** 2).sum() + ((a[2] - b[2]) ** 2).sum()))
+            return d / max(upd, 1e-30)
+        factor, floor_cost, floor_x = 8.0, 1e-5, 1e-4
+        rec = {"reference": "single-GPU solve of the same problem on rank 0 (unconnected plan)", "gn_iterations": list(checkpoints), "checks": [],
+               "tolerance": f"|cost_N - cost_1|/cost_1 <= max({floor_cost:g}, {factor:g} x noise) and ||X_N - X_1||/||X_1 - X_0|| <= max({floor_x:g}, {factor:g} x noise), "
+                            "noise = the same quantity between two single-GPU solves that differ only in the summation order of r.z (PCGStep2 grid 333 CTAs, per-step loop)"}
+        ok = True
+        for k in checkpoints:
+            c_rel = abs(multi[k][0] - ref[k][0]) / max(abs(ref[k][0]), 1e-30); x_rel = dist_rel(multi[k], ref[k])
+            n_c = abs(alt[k][0] - ref[k][0]) / max(abs(ref[k][0]), 1e-30); n_x = dist_rel(alt[k], ref[k])
+            good = c_rel <= max(floor_cost, factor * n_c) and x_rel <= max(floor_x, factor * n_x)
+            ok = ok and good
+            rec["checks"].append({"after_gn_iterations": k, "cost_n": multi[k][0], "cost_1": ref[k][0], "cost_rel_diff": c_rel, "unknowns_rel_diff": x_rel,
+                                  "noise_cost_rel_diff": n_c, "noise_unknowns_rel_diff": n_x, "ok": good})
+        rec["ok"] = ok
+    dist.barrier()
+    return rec
+
+
+def workload_string(W, H, liters):
+    return f"image_warping {W}x{H} fp32 GN (BASELINE.json headline), lIterations={liters}, step = 1 GN iteration"
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU arithmetic for the path on the host cores (see cpu_sample); every step is one
+    bounded sample of the same workload.  Under torchrun only rank 0 works."""
     if rank != 0:
         return
     samples, t_all = [], time.time()
-    for _ in range(args.warmup + args.steps):
-        cb, wall = cpu_sample(steps=1, rows=512, pcg_iters=20)
+    for _ in range(max(args.warmup, 0) + max(args.steps, 1)):
+        cb, wall = cpu_sample(repeats=1)
         samples.append(cb)
-        if time.time() - t_all > 240:
+        if time.time() - t_all > 200:
             break
     timed = samples[min(args.warmup, len(samples) - 1):]
-    rate = statistics.median([s["value"] for s in timed])
+    rate = max(s["value"] for s in timed)          # best sample, like the in-line cpu_baseline (best of 3)
     cb = dict(timed[-1]); cb["value"] = rate
+    cb["sample"] += f"; this arm: best of {len(timed)} timed samples ({', '.join('%.1f' % s['value'] for s in timed)} steps/s)"
     line = {"impl": "reference", "metric": "pcg_steps_per_s", "value": rate, "unit": "PCG steps/s", "n_gpus": args.gpus,
-            "steps": len(timed), "warmup": args.warmup, "ms_per_step": 1000.0 * L_ITERS / rate, "higher_is_better": True,
+            "steps": len(timed), "warmup": args.warmup, "ms_per_step": 1000.0 * args.liters / rate, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"image_warping {W_FULL}x{H_FULL} fp32 GN, lIterations={L_ITERS}", "note": "reference arm on host cores (cpu_baseline.kind says which code: the reference's own equations from oracle/_ref, else the oracle port); bounded slab sample scaled to the full image"},
+            "config": {"workload": workload_string(args.size, args.size, args.liters),
+                       "note": "reference arm on host cores (cpu_baseline.kind says which code: the reference's own equations from oracle/_ref, else the oracle port); each step is one bounded slab sample scaled to the full image"},
             "cpu_baseline": cb, "e2e": {"value": rate, "unit": "PCG steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -183,7 +303,11 @@ def main():
     ap.add_argument("--liters", type=int, default=L_ITERS)
     ap.add_argument("--size", type=int, default=W_FULL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-child", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_child:
+        _cpu_child(*[int(v) for v in args.cpu_child.split(",")])
+        return
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -216,6 +340,13 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ multi-GPU result vs the single-GPU result (N > 1)
+    parity = None
+    if world > 1:
+        parity = parity_vs_n1(solver, slab, dev, host, W, H, args.liters, rank, world)
+        total = args.warmup + args.steps
+        solver.set_solver_parameters({"nIterations": total + 1, "lIterations": args.liters})
 
     # ------------------------------------------------------------------ device-resident arm
     solver.init(dev)
@@ -292,7 +423,7 @@ def main():
         line = {
             "metric": "pcg_steps_per_s", "value": value, "unit": "PCG steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"image_warping {W}x{H} fp32 GN (BASELINE.json headline), lIterations={args.liters}, step = 1 GN iteration",
+            "config": {"workload": workload_string(W, H, args.liters),
                        "parallelism": "single GPU" if world == 1 else f"{world} row slabs of {W}x{slab.g1 - slab.g0} (+1 halo row per neighbour), NVLink peer-memory halo exchange + scalar mailboxes",
                        "l2": "inputs larger than L2 (live PCG vectors ~%.0f MB per rank)" % (W * Hr * 4 * 3 * 7 / 1e6) if W * Hr * 84 > 126e6 else "per-rank working set %.0f MB fits the 126 MB L2 (no flush between steps: the solver itself streams >= 7 vectors per PCG step)" % (W * Hr * 4 * 3 * 7 / 1e6),
                        "final_cost": final_cost},
@@ -308,8 +439,10 @@ def main():
                                       "frac": BYTES_PCG_STEP * W * (slab.g1 - slab.g0) / (loop_step_us * 1e-6) / 1e9 / peak},
                          "kernels_ms": prof},
         }
+        if parity is not None:
+            line["parity_vs_n1"] = parity
         if not args.no_cpu_baseline and world == 1:
-            cb, _ = cpu_sample(steps=1, rows=1024, pcg_iters=40)
+            cb, _ = cpu_sample()
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:

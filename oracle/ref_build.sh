@@ -15,3 +15,6 @@ fi
 if [ ! -f "$HERE/_ref/libref_arap.so" ] || [ "$HERE/ref_arap_shim.cpp" -nt "$HERE/_ref/libref_arap.so" ]; then
   $CXX $FLAGS -I"$REF/examples/arap_mesh_deformation/src" -o "$HERE/_ref/libref_arap.so" "$HERE/ref_arap_shim.cpp"
 fi
+if [ ! -f "$HERE/_ref/libref_sfs.so" ] || [ "$HERE/ref_sfs_shim.cpp" -nt "$HERE/_ref/libref_sfs.so" ]; then
+  $CXX $FLAGS -I"$REF/examples/shape_from_shading/src" -o "$HERE/_ref/libref_sfs.so" "$HERE/ref_sfs_shim.cpp"
+fi

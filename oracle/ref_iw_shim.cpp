@@ -52,11 +52,25 @@ void ref_iw_applyjtj(int W, int H, float2* x, float* A, float2* urshape, float* 
 // optimised away and the caller can see that it converges).
 double ref_iw_pcg(int W, int H, float2* x, float* A, float2* urshape, float* mask, float2* constraints, float weightFit, float weightReg,
                   int steps, int* threads, double* rzOut) {
+    // *threads > 0 on entry: use exactly that many OpenMP threads (the caller passes the cores its cgroup / affinity mask really
+    // grants: omp_get_max_threads() reports every core of the host, 128 on a box whose container may run on 16)
+#ifdef _OPENMP
+    if (threads && *threads > 0) omp_set_num_threads(*threads);
+#endif
     const int N = W * H;
     SolverInput in; in.N = N; in.width = W; in.height = H; in.d_constraints = constraints;
     SolverParameters pr; pr.weightFitting = weightFit; pr.weightRegularizer = weightReg; pr.nNonLinearIterations = 0; pr.nLinIterations = 0;
-    std::vector<float2> delta(N), r(N), z(N), p(N), Ap(N), pre(N);
-    std::vector<float> deltaA(N), rA(N), zA(N), pA(N), ApA(N), preA(N);
+    // work vectors: allocated untouched and first written inside the parallel loops below (first-touch page placement follows the
+    // static schedule every later loop uses)
+    struct Buf2 { float2* v; explicit Buf2(size_t n) : v((float2*)malloc(n * sizeof(float2))) {} ~Buf2() { free(v); } float2* data() { return v; } float2& operator[](size_t i) { return v[i]; } };
+    struct Buf1 { float* v; explicit Buf1(size_t n) : v((float*)malloc(n * sizeof(float))) {} ~Buf1() { free(v); } float* data() { return v; } float& operator[](size_t i) { return v[i]; } };
+    Buf2 delta(N), r(N), z(N), p(N), Ap(N), pre(N);
+    Buf1 deltaA(N), rA(N), zA(N), pA(N), ApA(N), preA(N);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < N; ++i) {
+        delta[i] = r[i] = z[i] = p[i] = Ap[i] = pre[i] = make_float2(0, 0);
+        deltaA[i] = rA[i] = zA[i] = pA[i] = ApA[i] = preA[i] = 0.f;
+    }
     SolverState st{}; st.d_x = x; st.d_A = A; st.d_urshape = urshape; st.d_mask = mask; st.d_delta = delta.data(); st.d_deltaA = deltaA.data();
     st.d_precondioner = pre.data(); st.d_precondionerA = preA.data(); st.d_p = p.data(); st.d_pA = pA.data();
     int nt = 1;

@@ -1,0 +1,92 @@
+"""Problem set-ups of the reference's example programs, built from their own input FILES through opt_b200.io -- the part of
+examples/*/src/main.cpp + CombinedSolver.h that turns files into the positional parameter table of the .t spec (host numpy here;
+workloads.to_device makes the CUDA-tensor form).  Same constants as the reference apps; what they do with mLib/OpenMesh/LodePNG is
+done with the minimal readers of include/OptB200IO.h."""
+import os
+
+import numpy as np
+
+from . import io
+
+FIXTURES = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "fixtures")
+
+
+def image_warping_from_files(mask_png, constraints_file, alpha=1.0, downsample=1, dtype=np.float32, w_fit=100.0, w_reg=0.01):
+    """examples/image_warping/src/main.cpp:55-108 + CombinedSolver.h:125-207: Mask = red channel of <name>_mask.png (0 = active),
+    UrShape = Offset0 = pixel grid, Angle0 = 0, Constraints = -1 except the marker pixels (moved towards their targets by `alpha`,
+    the continuation parameter of preNonlinearSolve) and the image border (pinned to itself); weights passed as square roots.
+    Returns (params, (W, H))."""
+    m = io.read_png(mask_png)[::downsample, ::downsample, 0].astype(dtype)
+    H, W = m.shape
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H))
+    ur = np.stack([xs, ys], -1).astype(dtype).reshape(-1, 2).copy()
+    rows = [list(r // downsample) for r in io.read_pair_constraints(constraints_file)]
+    for y in range(H):
+        for x in range(W):
+            if y == 0 or x == 0 or y == H - 1 or x == W - 1:
+                rows.append([x, y, x, y])
+    cons = -np.ones((W * H, 2), dtype)
+    for x, y, tx, ty in rows:
+        if m[y, x] == 0:
+            cons[y * W + x] = [(1.0 - alpha) * x + alpha * tx, (1.0 - alpha) * y + alpha * ty]
+    return [ur.copy(), np.zeros(W * H, dtype), ur, cons, m.reshape(-1).copy(), float(np.sqrt(np.float32(w_fit))), float(np.sqrt(np.float32(w_reg)))], (W, H)
+
+
+def shape_from_shading_from_files(prefix, dtype=np.float32):
+    """examples/shape_from_shading/src/SFSSolverInput.h:22-73 + main.cpp:21-28: four .imagedump files and the parameter dump under
+    `prefix` (e.g. .../shape_from_shading/default); the unknown starts from <prefix>_initialUnknown, the row / column edge masks are
+    the two halves of <prefix>_maskEdgeMap.  Returns (params, (W, H))."""
+    X = io.read_imagedump(prefix + "_initialUnknown.imagedump"); D = io.read_imagedump(prefix + "_targetDepth.imagedump")
+    Im = io.read_imagedump(prefix + "_targetIntensity.imagedump"); E = io.read_imagedump(prefix + "_maskEdgeMap.imagedump", clamp_infinity=False)
+    P = io.read_sfs_parameters(prefix + ".SFSSolverParameters")
+    H, W = X.shape
+    e = E.reshape(-1)
+    eR, eC = e[:W * H].copy(), e[W * H:2 * W * H].copy()
+    scal = [P["weightFitting"], P["weightRegularizer"], P["weightShading"], P["fx"], P["fy"], P["ux"], P["uy"]] + [float(v) for v in P["lightingCoefficients"]]
+    c = lambda a: np.ascontiguousarray(a.reshape(-1).astype(dtype))
+    return [float(v) for v in scal] + [c(X), c(D), c(Im), eR, eC], (W, H)
+
+
+def sqrt3_subdivide(v, faces):
+    """One step of Kobbelt's sqrt(3) subdivision of a closed triangle mesh -- what the reference app applies to its input once
+    before solving (OpenMesh::Subdivider::Uniform::Sqrt3T, examples/arap_mesh_deformation/src/main.cpp:60-73; the marker file indexes
+    the SUBDIVIDED mesh): a new vertex at every face centroid (index N + f), old vertices relaxed towards the mean of their old
+    neighbours with weight (4 - 2 cos(2 pi / n)) / 9, every old edge flipped to connect the two adjacent centroids."""
+    v = np.asarray(v, np.float64); faces = np.asarray(faces, np.int64)
+    N, F = len(v), len(faces)
+    nbrs = [set() for _ in range(N)]
+    edge_faces = {}
+    for f, (a, b, c) in enumerate(faces):
+        for x, y in ((a, b), (b, c), (c, a)):
+            nbrs[x].add(y); nbrs[y].add(x)
+            edge_faces.setdefault((min(x, y), max(x, y)), []).append((f, x, y))
+    cent = v[faces].mean(1)
+    newv = np.empty((N + F, 3))
+    for i in range(N):
+        n = len(nbrs[i]); w = (4.0 - 2.0 * np.cos(2.0 * np.pi / n)) / 9.0
+        newv[i] = (1.0 - w) * v[i] + w * v[list(nbrs[i])].mean(0)
+    newv[N:] = cent
+    newf = []
+    for (lo, hi), fl in edge_faces.items():
+        if len(fl) != 2:
+            raise ValueError("sqrt3_subdivide: closed manifold triangle mesh expected")
+        (f1, x, y), (f2, _, _) = fl                      # in f1 the edge runs x -> y
+        newf.append([x, N + f2, N + f1]); newf.append([y, N + f1, N + f2])
+    return newv.astype(np.float32), np.asarray(newf, np.int32)
+
+
+def arap_from_files(mesh_file, marker_file, alpha=1.0, dtype=np.float32, w_fit=4.0, w_reg=1.0, subdivisions=1):
+    """examples/arap_mesh_deformation/src/main.cpp:37-75,:93-96 + CombinedSolver.h:58-62,:90-148,:150-172: the mesh is subdivided
+    once (sqrt3), Offset0 = UrShape = its vertices, Angle0 = 0, Constraints = -inf except the marker vertices (moved from their rest
+    position towards the marker position by `alpha`), graph = one directed edge per (vertex, neighbour).  Returns (params, N)."""
+    v, faces = io.read_mesh(mesh_file)
+    for _ in range(subdivisions):
+        v, faces = sqrt3_subdivide(v, faces)
+    pos, _, idx = io.read_markers(marker_file)
+    N = len(v)
+    cons = np.full((N, 3), -np.inf, dtype)
+    for k, vi in enumerate(idx):
+        cons[vi] = (1.0 - alpha) * v[vi] + alpha * pos[k]
+    head, tail = io.mesh_neighbour_edges(v, faces)
+    c = lambda a: np.ascontiguousarray(a.astype(dtype))
+    return [float(np.sqrt(np.float32(w_fit))), float(np.sqrt(np.float32(w_reg))), c(v), np.zeros((N, 3), dtype), c(v), cons, int(len(head)), head, tail], N

@@ -195,7 +195,10 @@ __device__ __forceinline__ double orderedStridedSum(const double* part, unsigned
 // partial -> partials[slot][blockIdx]; last CTA sums gridDim.x partials in order -> scalars[slot].
 // Must be called by all threads of all CTAs of the launch exactly once per slot.
 template <int NT>
-__device__ __forceinline__ void gridReduceTo(double v, const ReduceWorkspace& ws, int slot) {
+__device__ __forceinline__ void gridReduceTo(double v, const ReduceWorkspace& ws, int slot, unsigned long long* const* releaseFlags = nullptr) {
+    // releaseFlags != nullptr (multi-GPU, the kernel stored halo data into neighbours' memory over NVLink before calling this): every
+    // CTA's arrival is preceded by a SYSTEM-scope fence, and the last CTA -- which has then observed every CTA's arrival -- releases
+    // releaseFlags[0..1] (the neighbours' "halo arrived" words, nullptr = no neighbour) with the halo sequence number of this step.
     __shared__ double s_warp[NT / 32];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -208,7 +211,7 @@ __device__ __forceinline__ void gridReduceTo(double v, const ReduceWorkspace& ws
         if (lane == 0) {
             double* part = ws.partials + (size_t)slot * kMaxPartials;
             part[blockIdx.x] = t;
-            __threadfence();
+            if (releaseFlags) __threadfence_system(); else __threadfence();
             unsigned int prev = atomicAdd(ws.counters + slot, 1u);
             s_last = (prev == gridDim.x - 1);
         }
@@ -231,6 +234,14 @@ __device__ __forceinline__ void gridReduceTo(double v, const ReduceWorkspace& ws
                 if (ws.comm.world <= 1) ws.scalars[slot] = u;
             }
             if (ws.comm.world > 1) publishScalarWarp(ws, slot, u);
+            if (releaseFlags) {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_system();
+                    const unsigned long long e = haloEpochNow(ws);
+                    for (int d = 0; d < 2; ++d) if (releaseFlags[d]) stReleaseSys(releaseFlags[d], e);
+                }
+            }
         }
     }
     __syncthreads();   // s_warp / s_last reusable by a second call in the same kernel

@@ -19,7 +19,7 @@ __device__ __forceinline__ double rnaGuardedInvert(double v) { double s = 1.0 + 
 
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_rnaPack(RnaData<T> D) {
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < D.N; v += gridDim.x * kBlock) D.pack[v] = rnaMakePack(D, v);
+    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) D.pack[v] = rnaMakePack(D, v);
 }
 template <class T> __device__ __forceinline__ void rnaStore(T* vec, const RnaData<T>& D, int v, const RnaOut<T>& q) {
     const long o = 3L * v, a = D.offA + 3L * v;
@@ -30,10 +30,11 @@ template <class T>
 __global__ void __launch_bounds__(kBlock) k_rnaInit(RnaData<T> D, ReduceWorkspace ws, int rzSlot, int usePre, T* __restrict__ delta, T* __restrict__ r,
                                                     T* __restrict__ pre, T* __restrict__ p) {
     T acc = T(0);
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < D.N; v += gridDim.x * kBlock) {
-        const RnaOut<T> g = rnaGather<T, 1>(D, v, nullptr), d = rnaGather<T, 2>(D, v, nullptr);
+    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
         RnaOut<T> rr, pr, pp, zero;
         zero.O = RnaV3<T>{ T(0), T(0), T(0) }; zero.A = zero.O; zero.g = T(0);
+        if (v < D.lo || v >= D.hi) { rnaStore(delta, D, v, zero); rnaStore(r, D, v, zero); rnaStore(pre, D, v, zero); continue; }   // halo vertex: its p arrives from the owner
+        const RnaOut<T> g = rnaGather<T, 1>(D, v, nullptr), d = rnaGather<T, 2>(D, v, nullptr);
         rr.O = RnaV3<T>{ -g.O.x, -g.O.y, -g.O.z }; rr.A = RnaV3<T>{ -g.A.x, -g.A.y, -g.A.z }; rr.g = -g.g;
         // graph problems: PCGInit1_Finish order -- invert first, then the UsePreconditioner(false) override (:406-410)
         pr.O = RnaV3<T>{ rnaGuardedInvert(d.O.x), rnaGuardedInvert(d.O.y), rnaGuardedInvert(d.O.z) };
@@ -50,7 +51,8 @@ __global__ void __launch_bounds__(kBlock) k_rnaInit(RnaData<T> D, ReduceWorkspac
 template <class T, bool LM>
 __global__ void __launch_bounds__(kBlock) k_rnaApplyJTJ(RnaData<T> D, ReduceWorkspace ws, int dotSlot, const T* __restrict__ x, T* __restrict__ out, const T* __restrict__ CtC) {
     T acc = T(0);
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < D.N; v += gridDim.x * kBlock) {
+    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
+        if (v < D.lo || v >= D.hi) { RnaOut<T> zero; zero.O = RnaV3<T>{ T(0), T(0), T(0) }; zero.A = zero.O; zero.g = T(0); rnaStore(out, D, v, zero); continue; }
         RnaOut<T> o = rnaGather<T, 0>(D, v, x);
         const long a0 = 3L * v, a1 = D.offA + 3L * v, a2 = D.offG + v;
         const RnaV3<T> xO{ x[a0], x[a0 + 1], x[a0 + 2] }, xA{ x[a1], x[a1 + 1], x[a1 + 2] }; const T xg = x[a2];
@@ -67,13 +69,13 @@ __global__ void __launch_bounds__(kBlock) k_rnaApplyJTJ(RnaData<T> D, ReduceWork
 template <class T, bool MODEL>
 __global__ void __launch_bounds__(kBlock) k_rnaCost(RnaData<T> D, ReduceWorkspace ws, int slot, const T* __restrict__ delta) {
     T acc = T(0);
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < D.N; v += gridDim.x * kBlock) acc += rnaCostAt<T, MODEL>(D, v, delta);
+    for (int v = D.lo + blockIdx.x * kBlock + threadIdx.x; v < D.hi; v += gridDim.x * kBlock) acc += rnaCostAt<T, MODEL>(D, v, delta);
     gridReduceTo<kBlock>((double)acc, ws, slot);
 }
 // PCGComputeCtC (+_Graph), :616-622, :739-744: CtC = diag(J^T J) / radius
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_rnaCtC(RnaData<T> D, T* __restrict__ CtC, T invRadius) {
-    for (int v = blockIdx.x * kBlock + threadIdx.x; v < D.N; v += gridDim.x * kBlock) {
+    for (int v = D.lo + blockIdx.x * kBlock + threadIdx.x; v < D.hi; v += gridDim.x * kBlock) {
         RnaOut<T> d = rnaGather<T, 2>(D, v, nullptr);
         d.O.x *= invRadius; d.O.y *= invRadius; d.O.z *= invRadius; d.A.x *= invRadius; d.A.y *= invRadius; d.A.z *= invRadius; d.g *= invRadius;
         rnaStore(CtC, D, v, d);
@@ -95,7 +97,7 @@ struct RnaOps : EnergyOps<T> {
     bool csrValid = false, packValid = false;
     int sms = 148;
     RnaOps(const unsigned* dims) {
-        D.N = (int)dims[0];
+        D.N = (int)dims[0]; D.lo = D.wlo = 0; D.hi = D.whi = D.N;
         this->unknowns.resize(3);
         this->unknowns[0].elements = D.N; this->unknowns[0].channels = 3;   // Offset
         this->unknowns[1].elements = D.N; this->unknowns[1].channels = 3;   // Angle
@@ -111,7 +113,7 @@ struct RnaOps : EnergyOps<T> {
     ~RnaOps() override { for (void* q : { (void*)D.pack, (void*)outStart, (void*)outNbr, (void*)inStart, (void*)inNbr, (void*)keysTmp, cubTemp }) if (q) cudaFree(q); }
     const char* name() const override { return "robust_nonrigid_alignment"; }
     unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(D); }
-    int grid() const { long g = ((long)D.N + kBlock - 1) / kBlock; long cap = (long)sms * 8; if (g > cap) g = cap; if (g > kMaxPartials) g = kMaxPartials; return g < 1 ? 1 : (int)g; }
+    int grid() const { long g = ((long)(D.whi - D.wlo) + kBlock - 1) / kBlock; long cap = (long)sms * 8; if (g > cap) g = cap; if (g > kMaxPartials) g = kMaxPartials; return g < 1 ? 1 : (int)g; }
     void bind(void** q) override {   // positions: robust_nonrigid_alignment.t:5-13
         D.wf = (T) * (const float*)q[0]; D.w = (T) * (const float*)q[1];
         this->unknowns[0].user = q[2]; this->unknowns[1].user = q[3]; this->unknowns[2].user = q[4];
@@ -122,6 +124,29 @@ struct RnaOps : EnergyOps<T> {
         nEdges = n; v0 = (const int*)q[9]; v1 = (const int*)q[10];
     }
     void newSolve() override { csrValid = false; }   // the caller may have rewritten the index arrays in place
+    // ---- multi-GPU: 1-D decomposition of the (locality-ordered) vertex index, as energy_arap.cu: every rank binds the GLOBAL arrays, owns
+    // the vertices [ownedBegin, ownedEnd) and keeps `up` / `dn` halo vertices beyond them (the graph's index bandwidth)
+    int haloUp = 0, haloDn = 0;
+    bool setSlab(int ownedBegin, int ownedEnd, int up, int dn) override {
+        if (ownedBegin < 0 || ownedEnd > D.N || ownedBegin >= ownedEnd || ownedBegin % 4 || (ownedEnd % 4 && ownedEnd != D.N) || up % 4 || dn % 4) return false;
+        if (ownedBegin - up < 0 || ownedEnd + dn > D.N || up > ownedEnd - ownedBegin || dn > ownedEnd - ownedBegin) return false;
+        D.lo = ownedBegin; D.hi = ownedEnd; D.wlo = ownedBegin - up; D.whi = ownedEnd + dn; haloUp = up; haloDn = dn;
+        return true;
+    }
+    std::vector<typename EnergyOps<T>::HaloSegment> haloSegments() const override {
+        std::vector<typename EnergyOps<T>::HaloSegment> s;   // vectors are global-size on every rank: destination offsets equal source offsets
+        if (haloUp > 0) { s.push_back({ 3L * D.lo, 3L * D.lo, 3L * haloUp, 0 }); s.push_back({ D.offA + 3L * D.lo, D.offA + 3L * D.lo, 3L * haloUp, 0 }); s.push_back({ D.offG + D.lo, D.offG + D.lo, (long)haloUp, 0 }); }
+        if (haloDn > 0) {
+            s.push_back({ 3L * (D.hi - haloDn), 3L * (D.hi - haloDn), 3L * haloDn, 1 }); s.push_back({ D.offA + 3L * (D.hi - haloDn), D.offA + 3L * (D.hi - haloDn), 3L * haloDn, 1 });
+            s.push_back({ D.offG + (D.hi - haloDn), D.offG + (D.hi - haloDn), (long)haloDn, 1 });
+        }
+        return s;
+    }
+    std::vector<std::pair<long, long>> ownedScalarRanges() const override { return { { 3L * D.lo, 3L * D.hi }, { D.offA + 3L * D.lo, D.offA + 3L * D.hi }, { D.offG + D.lo, D.offG + D.hi } }; }
+    std::vector<std::pair<long, long>> processScalarRanges() const override {
+        if (D.wlo == 0 && D.whi == D.N) return {};
+        return { { 3L * D.wlo, 3L * D.whi }, { D.offA + 3L * D.wlo, D.offA + 3L * D.whi }, { D.offG + D.wlo, D.offG + D.whi } };
+    }
     void buildCsr(cudaStream_t st) {
         if (csrValid) return;
         if (nEdges > capE) {

@@ -42,6 +42,7 @@ struct RnaData {
     long offA, offG;             // Angle / RobustWeights blocks inside the flat PCG vectors (Offset block starts at 0)
     RnaPack<T>* pack;
     const int *outStart, *outNbr, *inStart, *inNbr;   // vertex-CSR neighbour lists (out: edges v->b, in: edges c->v)
+    int lo, hi, wlo, whi;        // multi-GPU (kernels only): owned vertices [lo,hi) and the window incl. halo [wlo,whi); single GPU: [0,N)
 };
 
 RNA_HD void rnaSinCos(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }

@@ -12,6 +12,7 @@
 //     (:1093-1102, a blocking D2H per PCG step in the reference) is evaluated on the device and turns
 //     the remaining captured kernels into no-ops.
 //   * PCGStep3 of iteration k is fused into PCGStep1 of iteration k+1 when the energy provides it.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <ctime>
@@ -45,10 +46,35 @@ struct OwnedRanges {
 };
 
 // Multi-GPU with replicated (global-size) vectors (graph energies): the part of the flat vectors this rank has to
-// stream at all = owned entries + halo entries, as up to two contiguous windows.  n == 0: everything.
+// stream at all = owned entries + halo entries, as up to two contiguous windows (one per unknown array).  n == 0: everything.
 struct WindowRanges {
-    long lo[2], len[2]; long total; int n;
-    __device__ __forceinline__ long map(long j) const { return n == 0 ? j : (j < len[0] ? lo[0] + j : lo[1] + (j - len[0])); }
+    long lo[3], len[3]; long total; int n;
+    __device__ __forceinline__ long map(long j) const {
+        if (n == 0 || j < len[0]) return n == 0 ? j : lo[0] + j;
+        j -= len[0];
+        return (n < 3 || j < len[1]) ? lo[1] + j : lo[2] + (j - len[1]);
+    }
+};
+
+// Multi-GPU, halo of z without a separate exchange kernel: PCGStep2 stores the z it computes for entries inside this rank's boundary
+// segments ALSO into the neighbour's halo entries (NVLink peer stores), and its reduction's last CTA releases the neighbours' flags;
+// PCGStep3 forms p on the owned entries first and waits for the incoming flag only before it touches the halo entries.
+template <class T> struct ZPush {
+    int n;                                   // 0: disabled
+    long lo[kMaxHaloSegs], hi[kMaxHaloSegs], shift[kMaxHaloSegs];   // boundary segments in VecOf<T>::N-wide units; destination index = i + shift
+    T* dst[kMaxHaloSegs];                    // the neighbour's z vector
+    unsigned long long* peerFlag[2];         // neighbours' "halo arrived" words (nullptr: no neighbour on that side)
+};
+struct HaloWait {
+    int n;                                   // 0: disabled
+    long lo[8], len[8], total;               // halo entries inside the streamed window, VecOf<T>::N-wide units
+    unsigned long long* flag[2];             // my "halo arrived" words, written by the upper / lower neighbour (nullptr: none)
+    __device__ __forceinline__ long map(long j) const {
+        long i = -1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { if (k < n && i < 0) { if (j < len[k]) i = lo[k] + j; else j -= len[k]; } }
+        return i;
+    }
 };
 
 // ------------------------------------------------------------------------------------ PCGStep2
@@ -58,7 +84,7 @@ template <class T, bool LM, bool USEPRE>
 __global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, WindowRanges win, ReduceWorkspace ws, OwnedRanges own, int rzOld, int rzNew,
                                                      T* __restrict__ delta, const T* __restrict__ p, T* __restrict__ r,
                                                      const T* __restrict__ Ap, const T* __restrict__ pre,
-                                                     const T* __restrict__ b, T* __restrict__ z) {
+                                                     const T* __restrict__ b, T* __restrict__ z, ZPush<T> push) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
     pdlTrigger(); pdlWait();
     if (LM && ws.scalars[kFlags] != 0.0) return;
@@ -108,9 +134,15 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, WindowRanges win
         }
         reinterpret_cast<V*>(delta)[iCur] = pack(d);
         reinterpret_cast<V*>(r)[iCur] = pack(rr);
-        if (mine) reinterpret_cast<V*>(z)[iCur] = pack(zz);   // halo entries of z belong to the neighbour's NVLink store (k_haloExchange)
+        if (mine) {   // halo entries of z belong to the neighbour's NVLink store
+            reinterpret_cast<V*>(z)[iCur] = pack(zz);
+            if (push.n) {
+#pragma unroll
+                for (int k = 0; k < kMaxHaloSegs; ++k) if (k < push.n && iCur >= push.lo[k] && iCur < push.hi[k]) reinterpret_cast<V*>(push.dst[k])[iCur + push.shift[k]] = pack(zz);
+            }
+        }
     }
-    gridReduceTo<kBlock>((double)accRz, ws, rzNew);
+    gridReduceTo<kBlock>((double)accRz, ws, rzNew, push.n ? push.peerFlag : nullptr);
     if (LM) gridReduceTo<kBlock>((double)accQ, ws, kQ);
 }
 
@@ -164,7 +196,8 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2SecondHalf(long nVec, Window
 // ------------------------------------------------------------------------------------ PCGStep3
 // :537-550.  beta = rz_new / rz_old (guarded), p = z + beta p
 template <class T, bool LM>
-__global__ void __launch_bounds__(kBlock) k_pcgStep3(long nVec, WindowRanges win, ReduceWorkspace ws, int rzNew, int rzOld, const T* __restrict__ z, T* __restrict__ p) {
+__global__ void __launch_bounds__(kBlock) k_pcgStep3(long nVec, WindowRanges win, ReduceWorkspace ws, int rzNew, int rzOld, const T* __restrict__ z, T* __restrict__ p,
+                                                     OwnedRanges own, HaloWait hw) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
     pdlTrigger(); pdlWait();
     if (LM && ws.scalars[kFlags] != 0.0) return;
@@ -172,13 +205,32 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep3(long nVec, WindowRanges win
     const T rn = (T)drn, ro = (T)dro;
     T beta = T(0);
     if (ro > T(0)) beta = rn / ro;
-    for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < nVec; j += (long)gridDim.x * kBlock) {
-        const long i = win.map(j);
+    auto one = [&](long i) {
         T zz[N], pp[N];
         unpack(reinterpret_cast<const V*>(z)[i], zz); unpack(reinterpret_cast<const V*>(p)[i], pp);
 #pragma unroll
         for (int k = 0; k < N; ++k) pp[k] = zz[k] + beta * pp[k];
         reinterpret_cast<V*>(p)[i] = pack(pp);
+    };
+    for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < nVec; j += (long)gridDim.x * kBlock) {
+        const long i = win.map(j);
+        if (hw.n && !own.owns(i)) continue;      // halo entries: second pass, once the neighbours' z has arrived
+        one(i);
+    }
+    if (hw.n) {
+        if (threadIdx.x == 0) {
+            const unsigned long long e = haloEpochNow(ws);
+            for (int d = 0; d < 2; ++d) if (hw.flag[d]) { while (ldAcquireSys(hw.flag[d]) < e) {} }
+        }
+        __syncthreads();
+        for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < hw.total; j += (long)gridDim.x * kBlock) {
+            const long i = hw.map(j);
+            T zz[N], pp[N];   // z was written by another GPU: read it past L1
+            unpack(__ldcg(reinterpret_cast<const V*>(z) + i), zz); unpack(reinterpret_cast<const V*>(p)[i], pp);
+#pragma unroll
+            for (int k = 0; k < N; ++k) pp[k] = zz[k] + beta * pp[k];
+            reinterpret_cast<V*>(p)[i] = pack(pp);
+        }
     }
 }
 
@@ -281,6 +333,7 @@ struct Plan : PlanBase {
     CommBlock* commBlock = nullptr;
     int world = 1, rank = 0;
     HaloPlan haloP{}, haloZ{};
+    ZPush<T> zPush{}; HaloWait zWait{};   // in-kernel halo of z (Step2 pushes, Step3 waits); n == 0: not available, use k_haloExchange
     HaloPlan* dHaloP = nullptr; HaloPlan* dHaloZ = nullptr;       // device copies (kernels take them by pointer)
     unsigned long long** dPeerTable = nullptr;
     std::vector<void*> ipcOpened;
@@ -417,8 +470,8 @@ struct Plan : PlanBase {
         auto segs = E->haloSegments();
         auto fill = [&](HaloPlan& hp, void* up, void* dn) {
             hp = HaloPlan{};
-            hp.nSeg = (int)segs.size();
-            for (int i = 0; i < hp.nSeg && i < 4; ++i) { hp.srcOff[i] = segs[i].srcOff; hp.dstOff[i] = segs[i].dstOff; hp.len[i] = segs[i].len; hp.dir[i] = segs[i].dir; }
+            hp.nSeg = (int)std::min<size_t>(segs.size(), (size_t)kMaxHaloSegs);
+            for (int i = 0; i < hp.nSeg && i < kMaxHaloSegs; ++i) { hp.srcOff[i] = segs[i].srcOff; hp.dstOff[i] = segs[i].dstOff; hp.len[i] = segs[i].len; hp.dir[i] = segs[i].dir; }
             hp.peerVec[0] = up; hp.peerVec[1] = dn;
             // my data lands in the upper neighbour as "from below" (its haloFlags[1]) and in the lower neighbour as "from above" (its haloFlags[0])
             hp.peerFlag[0] = up ? &peerBlocks[rank - 1]->haloFlags[1] : nullptr;
@@ -441,7 +494,7 @@ struct Plan : PlanBase {
         auto wins = E->processScalarRanges();
         winVec = WindowRanges{}; winScalar = WindowRanges{};
         if (!wins.empty()) {
-            if (wins.size() > 2) { fprintf(stderr, "opt_b200: at most two process windows supported\n"); return -4; }
+            if (wins.size() > 3) { fprintf(stderr, "opt_b200: at most three process windows supported\n"); return -4; }
             for (size_t i = 0; i < wins.size(); ++i) {
                 if (wins[i].first % VecOf<T>::N || wins[i].second % VecOf<T>::N) { fprintf(stderr, "opt_b200: process window not vector aligned\n"); return -3; }
                 winScalar.lo[i] = wins[i].first; winScalar.len[i] = wins[i].second - wins[i].first; winScalar.total += winScalar.len[i];
@@ -449,7 +502,8 @@ struct Plan : PlanBase {
             }
             winVec.n = winScalar.n = (int)wins.size();
         }
-        if (segs.size() > 4 || ranges.size() > 4) { fprintf(stderr, "opt_b200: at most 4 halo segments / owned ranges per rank are supported\n"); return -5; }
+        buildZPush(segs, ranges, wins, upZ, dnZ);
+        if (segs.size() > (size_t)kMaxHaloSegs || ranges.size() > 4) { fprintf(stderr, "opt_b200: at most %d halo segments / 4 owned ranges per rank are supported\n", kMaxHaloSegs); return -5; }
         if (loopExec) { cudaGraphExecDestroy(loopExec); loopExec = nullptr; }
         // collective decision about the one-kernel PCG loop: every rank posts whether it can run it, into every rank's block;
         // the first runLoop after this waits for all the answers (multiLoopAgreed)
@@ -458,6 +512,38 @@ struct Plan : PlanBase {
         const unsigned long long word = ((unsigned long long)connectGen << 2) | (fits ? 2ull : 1ull);
         for (int r = 0; r < world; ++r) OPT_CUDA_CHECK(cudaMemcpy(&peerBlocks[r]->fitFlags[rank], &word, sizeof(word), cudaMemcpyDefault));
         return 0;
+    }
+    // Step2-push / Step3-wait form of the z halo: needs every boundary segment and every halo range aligned to the vector width
+    template <class Segs, class Ranges, class Wins>
+    void buildZPush(const Segs& segs, const Ranges& ranges, const Wins& wins, void* upZ, void* dnZ) {
+        constexpr long NV = VecOf<T>::N;
+        zPush = ZPush<T>{}; zWait = HaloWait{};
+        if (getenv("OPTB_NO_ZPUSH") || segs.empty() || segs.size() > (size_t)kMaxHaloSegs || (!upZ && !dnZ)) return;
+        ZPush<T> zp{}; HaloWait hw{};
+        for (auto& sg : segs) {
+            void* dst = sg.dir == 0 ? upZ : dnZ;
+            if (!dst) continue;
+            if (sg.srcOff % NV || sg.dstOff % NV || sg.len % NV) return;
+            zp.lo[zp.n] = sg.srcOff / NV; zp.hi[zp.n] = (sg.srcOff + sg.len) / NV; zp.shift[zp.n] = (sg.dstOff - sg.srcOff) / NV; zp.dst[zp.n] = (T*)dst; ++zp.n;
+        }
+        zp.peerFlag[0] = haloZ.peerFlag[0]; zp.peerFlag[1] = haloZ.peerFlag[1];
+        // halo entries = streamed entries (the windows, or the whole vectors) that are not owned
+        std::vector<std::pair<long, long>> span;
+        if (wins.empty()) span.push_back({ 0, n }); else for (auto& w : wins) span.push_back({ w.first, w.second });
+        std::vector<std::pair<long, long>> own(ranges.begin(), ranges.end());
+        std::sort(own.begin(), own.end());
+        for (auto sp2 : span) {
+            long at = sp2.first;
+            for (auto& o : own) {
+                if (o.second <= at || o.first >= sp2.second) continue;
+                if (o.first > at) { if (hw.n >= 8 || at % NV || o.first % NV) return; hw.lo[hw.n] = at / NV; hw.len[hw.n] = (o.first - at) / NV; hw.total += hw.len[hw.n]; ++hw.n; }
+                at = std::max(at, o.second);
+            }
+            if (at < sp2.second) { if (hw.n >= 8 || at % NV || sp2.second % NV) return; hw.lo[hw.n] = at / NV; hw.len[hw.n] = (sp2.second - at) / NV; hw.total += hw.len[hw.n]; ++hw.n; }
+        }
+        hw.flag[0] = upZ ? haloZ.myFlag[0] : nullptr; hw.flag[1] = dnZ ? haloZ.myFlag[1] : nullptr;
+        if (zp.n == 0 || hw.n == 0) return;
+        zPush = zp; zWait = hw;
     }
     unsigned connectGen = 0; int multiLoopState = -1;   // -1: not resolved yet, 0: per-step loop on every rank, 1: collective loop kernel on every rank
     bool multiLoopAgreed() {
@@ -506,21 +592,23 @@ struct Plan : PlanBase {
     }
 
     // ---- one PCG iteration, launched on `stream` (captured into the loop graph or issued directly)
-    void launchStep2(int rzOld, int rzNew, T* p) {
+    void launchStep2(int rzOld, int rzNew, T* p, bool pushZ = false) {
+        const ZPush<T> zp = pushZ ? zPush : ZPush<T>{};
         long nVec = n / VecOf<T>::N;
         if (lm) {
-            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStep2, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
-            else k_pcgStep2<T, true, false><<<gridStep2, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStep2, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp);
+            else k_pcgStep2<T, true, false><<<gridStep2, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp);
         } else {
-            if (E->usePreconditioner) launchPdl(k_pcgStep2<T, false, true>, gridStep2, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
-            else launchPdl(k_pcgStep2<T, false, false>, gridStep2, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z);
+            if (E->usePreconditioner) launchPdl(k_pcgStep2<T, false, true>, gridStep2, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp);
+            else launchPdl(k_pcgStep2<T, false, false>, gridStep2, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp);
         }
         ++launches;
     }
-    void launchStep3(int rzNew, int rzOld, T* p) {
+    void launchStep3(int rzNew, int rzOld, T* p, bool waitZ = false) {
+        const HaloWait hw = waitZ ? zWait : HaloWait{};
         long nVec = n / VecOf<T>::N;
-        if (lm) k_pcgStep3<T, true><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, rzNew, rzOld, z, p);
-        else launchPdl(k_pcgStep3<T, false>, gridStream, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, rzNew, rzOld, (const T*)z, p);
+        if (lm) k_pcgStep3<T, true><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, rzNew, rzOld, z, p, ownVec, hw);
+        else launchPdl(k_pcgStep3<T, false>, gridStream, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, rzNew, rzOld, (const T*)z, p, ownVec, hw);
         ++launches;
     }
     // Emits iterations [0, L).  rz slot convention: iteration l reads rz[l&1] as "old", writes rz[(l+1)&1].
@@ -551,14 +639,17 @@ struct Plan : PlanBase {
                 if (E->usePreconditioner) k_pcgStep2SecondHalf<T, true><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzNew, delta, r, Adelta, pre, b, z);
                 else k_pcgStep2SecondHalf<T, false><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzNew, delta, r, Adelta, pre, b, z);
                 ++launches;
-            } else {
+            }
+            const bool step3Fused = fuse && !lm && l + 1 < L;   // Step3 of this iteration runs inside the next Step1
+            const bool zInStep2 = world > 1 && zPush.n > 0 && !reset && !step3Fused;   // Step2 pushes z's boundary entries, the standalone Step3 waits for them
+            if (!reset) {
                 tBeginFine("PCGStep2");
-                launchStep2(rzOld, rzNew, cur);
+                launchStep2(rzOld, rzNew, cur, zInStep2);
                 tEndFine();
             }
-            if (!(kernelHalo && fuse && l + 1 < L)) exchangeHalo(haloZ, z);   // neighbours need z on my boundary rows for their p = z + beta p
-            if (fuse && !lm && l + 1 < L) pending = true;   // defer Step3 into the next Step1
-            else { tBeginFine("PCGStep3"); launchStep3(rzNew, rzOld, cur); tEndFine(); }
+            if (!zInStep2 && !(kernelHalo && step3Fused)) exchangeHalo(haloZ, z);   // neighbours need z on my boundary rows for their p = z + beta p
+            if (step3Fused) pending = true;   // defer Step3 into the next Step1
+            else { tBeginFine("PCGStep3"); launchStep3(rzNew, rzOld, cur, zInStep2); tEndFine(); }
             if (lm) { k_lmZeta<T><<<1, 1, 0, stream>>>(ws, l, (T)sp.q_tolerance); ++launches; }
         }
         pFinal = cur;

@@ -42,10 +42,11 @@ struct UnknownArray {
 // boundary rows; peerVec are the neighbours' copies of the same vector (CUDA IPC), flags live in the
 // ranks' mailbox blocks.  Used either by the stand-alone k_haloExchange or from inside an energy's
 // J^T J kernel (push at kernel start, wait only before tiles that touch halo rows).
+constexpr int kMaxHaloSegs = 6;          // unknown arrays x 2 directions (robust_nonrigid_alignment: Offset, Angle, RobustWeights)
 struct HaloPlan {
     int nSeg;
-    long srcOff[4], dstOff[4], len[4];   // in scalars
-    int dir[4];                          // 0 = to the upper neighbour, 1 = to the lower neighbour
+    long srcOff[kMaxHaloSegs], dstOff[kMaxHaloSegs], len[kMaxHaloSegs];   // in scalars
+    int dir[kMaxHaloSegs];               // 0 = to the upper neighbour, 1 = to the lower neighbour
     void* peerVec[2];                    // neighbour's copy of the vector being exchanged (nullptr: no neighbour)
     unsigned long long* peerFlag[2];     // neighbour's "halo arrived from me" flag
     unsigned long long* myFlag[2];       // my flags, written by the upper / lower neighbour

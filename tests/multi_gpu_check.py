@@ -65,9 +65,54 @@ def main_arap():
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
 
+def main_rna():
+    """vertex-slab decomposition of robust_nonrigid_alignment (fp64, LM: BASELINE.json config 5) vs the single-GPU solve"""
+    import torch
+    import torch.distributed as dist
+    from opt_b200 import OptSolver, spec_path, workloads
+    from opt_b200.distributed import VertexSlab, connect_plan
+    rank, world, local, flag_dev = _setup(torch, dist)
+    nx, ny = int(sys.argv[2]), int(sys.argv[3]); kind = sys.argv[4] if len(sys.argv) > 4 else "LMGPU"
+    dp = (sys.argv[5] if len(sys.argv) > 5 else "f64") == "f64"
+    sp = {"nIterations": 3, "lIterations": 30}
+    full = workloads.robust_nonrigid(nx, ny, dtype=np.float64 if dp else np.float32, perturb=0.05)
+    N = nx * ny
+    slab = VertexSlab(N, world, rank, full[9], full[10])
+    dev = workloads.to_device(workloads.clone_params(full))           # every rank binds the global arrays
+    s = OptSolver([N], spec_path("robust_nonrigid_alignment"), kind, double_precision=dp)
+    connect_plan(s, slab)
+    s.set_solver_parameters(sp)
+    s.init(dev); costs = [s.current_cost()]
+    while s.step(dev):
+        costs.append(s.current_cost())
+    torch.cuda.synchronize()
+    got = [slab.gather(dev[k].cpu().numpy()) for k in (2, 3, 4)]
+    ok = True
+    if rank == 0:
+        ref = workloads.to_device(workloads.clone_params(full))
+        s1 = OptSolver([N], spec_path("robust_nonrigid_alignment"), kind, double_precision=dp); s1.set_solver_parameters(sp)
+        s1.init(ref); c1 = [s1.current_cost()]
+        while s1.step(ref):
+            c1.append(s1.current_cost())
+        want = [ref[k].cpu().numpy() for k in (2, 3, 4)]
+        rel_c = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(costs, c1)) if len(costs) == len(c1) else float("inf")
+        errs = [float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12)) for a, b in zip(got, want)]
+        print(f"multi_gpu_check RNA world={world} {nx}x{ny} {kind} {'f64' if dp else 'f32'} halo={slab.halo}: costs {costs[0]:.8f} -> {costs[-1]:.8f}; vs 1 GPU: cost rel {rel_c:.2e}, "
+              f"Offset {errs[0]:.2e}, Angle {errs[1]:.2e}, RobustWeights {errs[2]:.2e}")
+        print("  multi :", [f"{c:.8g}" for c in costs]); print("  single:", [f"{c:.8g}" for c in c1])
+        tol = (1e-9, 1e-8) if dp else (1e-4, 2e-3)
+        ok = rel_c < tol[0] and max(errs) < tol[1] and len(costs) == len(c1)
+    flag = torch.tensor([1 if ok else 0], device=flag_dev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "arap":
         return main_arap()
+    if len(sys.argv) > 1 and sys.argv[1] == "rna":
+        return main_rna()
     import torch
     import torch.distributed as dist
     from opt_b200 import OptSolver, spec_path, workloads

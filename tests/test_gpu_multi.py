@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("world,args", [(2, ["128", "96", "gaussNewtonGPU"]), (2, ["256", "130", "LMGPU"]), (4, ["192", "64", "gaussNewtonGPU"]),
-                                        (2, ["arap", "48", "40", "gaussNewtonGPU"]), (2, ["arap", "36", "50", "LMGPU"]), (4, ["arap", "32", "96", "gaussNewtonGPU"])])
+                                        (2, ["arap", "48", "40", "gaussNewtonGPU"]), (2, ["arap", "36", "50", "LMGPU"]), (4, ["arap", "32", "96", "gaussNewtonGPU"]),
+                                        (2, ["rna", "40", "48", "LMGPU", "f64"]), (2, ["rna", "36", "50", "gaussNewtonGPU", "f32"]), (4, ["rna", "32", "96", "LMGPU", "f64"])])
 def test_slab_solve_matches_single_gpu(built, world, args):
     import torch
     if torch.cuda.device_count() < world:

@@ -13,7 +13,7 @@ timeout 500 python -m pytest tests/test_gpu_multi.py tests/test_gpu_zz_multi_per
   echo "== 2048^2 on 2 ranks (per-step loop: the slab does not fit on chip)"
   timeout 300 $TR --master-port 29623 bench.py --gpus 2 --steps 8 --warmup 3
   echo "== arap 500k on 1 and 2 ranks"
-  timeout 200 python tools/bench_arap_multi.py 2>&1 | tail -3
-  timeout 200 $TR --master-port 29624 tools/bench_arap_multi.py 2>&1 | tail -3
+  timeout 200 python tools/bench_graph_multi.py 2>&1 | tail -3
+  timeout 200 $TR --master-port 29624 tools/bench_graph_multi.py 2>&1 | tail -3
 } > gpurun_out/bench_2gpu.txt 2>&1
 tail -6 gpurun_out/tests_2gpu.txt; grep -E "^==|\"value\"" gpurun_out/bench_2gpu.txt | cut -c1-400

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJ(IWData<T> D, ReduceWorksp
 #define IW_STRIP 4
 #endif
 constexpr int kTW = 64, kTH = IW_TH, kStages = IW_STAGES, kStrip = IW_STRIP;
-// TMA rule (measured, tools/scratch/tma_probe.cu): the innermost box coordinate must start on a 16-byte
+// TMA rule (measured, tools/tma_probe.cu): the innermost box coordinate must start on a 16-byte
 // boundary, so 2-channel rows are staged from pixel x0-2 and 1-channel rows from pixel x0-4.
 constexpr int kRowO = 2 * (kTW + 4);      // floats per staged row of a 2-channel image (pixels x0-2 .. x0+TW+1)
 constexpr int kRowA = kTW + 8;            // floats per staged row of a 1-channel image (pixels x0-4 .. x0+TW+3)
@@ -1097,7 +1097,7 @@ struct ImageWarpingOps : EnergyOps<T> {
             if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resSmem) != cudaSuccess) { cudaGetLastError(); return false; }
             int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 1024, resSmem);
             int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            if ((long)occ * sms < resGrid) return false;
+            if ((long)occ * sms < resGrid) { resR = -1; return false; }   // does not fit this device: remember, do not ask again every step
             resChecked = KMAX;
         }
         ReduceWorkspace ws = c.ws;

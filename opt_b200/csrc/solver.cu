@@ -254,14 +254,18 @@ template <class T> __global__ void __launch_bounds__(kBlock) k_copy(long n, T* _
 // PCGFinalizeDiagonal (:631-664).  `pre` holds guardedInvert(diag) from PCGInit1 on entry (0 on
 // excluded/padding entries, which stay inert), the true LM preconditioner on exit.
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, WindowRanges win, ReduceWorkspace ws, OwnedRanges own, int rzSlot, T* __restrict__ CtC, const T* __restrict__ SSq,
+__global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, WindowRanges win, ReduceWorkspace ws, OwnedRanges own, int rzSlot, T* __restrict__ CtC, T* __restrict__ SSq,
                                                                T* __restrict__ pre, const T* __restrict__ r, T* __restrict__ b, T* __restrict__ p,
                                                                const T* __restrict__ delta, T radius, T minDiag, T maxDiag) {
     T accD = T(0), accQ = T(0);
     for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < n; j += (long)gridDim.x * kBlock) {
         const long i = win.map(j);
+        // active NOW = PCGInit1 left a non-zero guardedInvert(diag) in pre (0 on excluded / padding / halo-of-nothing entries).  SSq is saved
+        // at the first nonlinear iteration only (:1038-1041); an unknown whose Exclude() mask cleared later gets its scale now.
+        const T preIn = pre[i];
         T ssq = SSq[i];
-        if (ssq > T(0)) {
+        if (preIn > T(0) && !(ssq > T(0))) { ssq = preIn; SSq[i] = ssq; }
+        if (preIn > T(0) && ssq > T(0)) {
             T unclamped = CtC[i];
             T invS = T(1) / ssq;
             T clampMul = invS / radius;
@@ -340,11 +344,13 @@ struct Plan : PlanBase {
     double* hScalars = nullptr;  // pinned mirror
     cudaStream_t stream = nullptr, userStream = nullptr;
     bool ownStream = true;
-    cudaEvent_t evEntry = nullptr, evLoop0 = nullptr, evLoop1 = nullptr;
+    cudaEvent_t evEntry = nullptr, evLoop0 = nullptr, evLoop1 = nullptr, evCost = nullptr, evExit = nullptr;
+    mutable bool costPending = false, loopMsPending = false;   // GN steps do not wait for their own cost: resolved on demand
     int numSMs = 148;
     int gridStream = 0;          // CTAs for the streaming kernels
     int gridStep2 = 0;           // CTAs for PCGStep2 (co-resident count)
     cudaGraphExec_t loopExec = nullptr; unsigned long long loopExecKey = 0; int graphBuilds = 0;
+    bool asyncSteps = true;      // GN: Opt_ProblemStep returns without waiting for its cost (OPTB_SYNC_STEPS=1: block like the reference)
     bool useGraph = true, useFusion = true, usePdl = false;   // PDL measured slower here (early-resident dependents crowd the streaming kernels): opt-in via OPTB_PDL=1
     // nonlinear state (:994-1006)
     int nIter = 0;
@@ -372,6 +378,7 @@ struct Plan : PlanBase {
         OPT_CUDA_CHECK(cudaMallocHost((void**)&hScalars, sizeof(double) * kNumScalars));
         OPT_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         OPT_CUDA_CHECK(cudaEventCreateWithFlags(&evEntry, cudaEventDisableTiming));
+        OPT_CUDA_CHECK(cudaEventCreateWithFlags(&evCost, cudaEventDisableTiming)); OPT_CUDA_CHECK(cudaEventCreateWithFlags(&evExit, cudaEventDisableTiming));
         OPT_CUDA_CHECK(cudaEventCreate(&evLoop0)); OPT_CUDA_CHECK(cudaEventCreate(&evLoop1));
         long nVec = n / VecOf<T>::N;
         gridStream = (int)std::min<long>((nVec + kBlock - 1) / kBlock, (long)numSMs * 8);
@@ -390,6 +397,7 @@ struct Plan : PlanBase {
         if (const char* s = getenv("OPTB_NO_FUSION")) useFusion = atoi(s) == 0;
         if (const char* s = getenv("OPTB_PDL")) usePdl = atoi(s) != 0;
         persistentMode = -1; if (const char* s = getenv("OPTB_PERSISTENT")) persistentMode = atoi(s) != 0 ? 1 : 0;
+        if (const char* s = getenv("OPTB_SYNC_STEPS")) asyncSteps = atoi(s) == 0;
         // The reference's harness always asks for the timing table (examples/shared/OptSolver.h:47-48), so the flag alone must
         // not cost the fast path: by default the table has one row per REGION (PCGInit1, the whole PCG loop, update, cost);
         // OPTB_TIMING_TABLE=1 switches to one row per kernel by issuing the per-step kernels individually.
@@ -404,7 +412,7 @@ struct Plan : PlanBase {
         for (void* q : ipcOpened) cudaIpcCloseMemHandle(q);
         cudaFree(commBlock); cudaFree(dHaloP); cudaFree(dHaloZ); cudaFree(dPeerTable);
         cudaFree(ws.partials); cudaFree(ws.counters); cudaFree(ws.scalars); cudaFreeHost(hScalars);
-        cudaEventDestroy(evEntry); cudaEventDestroy(evLoop0); cudaEventDestroy(evLoop1);
+        cudaEventDestroy(evEntry); cudaEventDestroy(evLoop0); cudaEventDestroy(evLoop1); cudaEventDestroy(evCost); cudaEventDestroy(evExit);
         if (ownStream) cudaStreamDestroy(stream);
         delete E;
     }
@@ -424,14 +432,35 @@ struct Plan : PlanBase {
     void setStream(cudaStream_t s) override { userStream = s; }
     void setMaxLinearIterations(int k) override { maxLinIters = k; }
     int launchesLastStep() const override { return launches; }
-    float pcgLoopMsLastStep() const override { return loopMs; }
+    float pcgLoopMsLastStep() const override {
+        if (loopMsPending) { OPT_CUDA_CHECK(cudaEventSynchronize(evLoop1)); float ms = 0; OPT_CUDA_CHECK(cudaEventElapsedTime(&ms, evLoop0, evLoop1)); const_cast<Plan*>(this)->loopMs = ms; loopMsPending = false; }
+        return loopMs;
+    }
     long numUnknowns() const override { return n; }
     int unknownLayout(int maxArrays, long* offsets, long* elements, int* channels) const override {
         int k = 0;
         for (auto& u : E->unknowns) { if (k < maxArrays) { offsets[k] = u.offset; elements[k] = u.elements; channels[k] = u.channels; } ++k; }
         return k;
     }
-    double currentCost() const override { return (double)prevCost; }
+    double currentCost() const override { const_cast<Plan*>(this)->resolveCost(); return (double)prevCost; }
+    // Gauss-Newton takes no decision from the cost, so Opt_ProblemStep does not wait for it (the reference blocks on a D2H copy per
+    // nonlinear iteration, solverGPUGaussNewton.t:790-797): the value lands in pinned memory behind an event and is picked up by
+    // Opt_ProblemCurrentCost, by the next verbose print, or when the solve ends.
+    void resolveCost() {
+        if (!costPending) return;
+        OPT_CUDA_CHECK(cudaEventSynchronize(evCost));
+        prevCost = (T)hScalars[kCost]; costPending = false;
+    }
+    void computeCostAsync() {
+        E->cost(ctx()); ++launches;
+        if (world > 1) { k_finalizeScalars<<<1, 32, 0, stream>>>(ws, (1u << kRz0) | (1u << kRz1) | (1u << kPAp) | (1u << kCost) | (1u << kModelCost) | (1u << kQ)); ++launches; }
+        OPT_CUDA_CHECK(cudaMemcpyAsync(hScalars, ws.scalars, sizeof(double) * kNumScalars, cudaMemcpyDeviceToHost, stream));
+        OPT_CUDA_CHECK(cudaEventRecord(evCost, stream));
+        costPending = true;
+        // whatever the caller queues next on ITS stream (default: the NULL stream) comes after this step's work
+        OPT_CUDA_CHECK(cudaEventRecord(evExit, stream));
+        OPT_CUDA_CHECK(cudaStreamWaitEvent(userStream, evExit, 0));
+    }
 
     // order our stream after whatever the caller queued on its stream (default: the legacy NULL stream,
     // which is what the reference runs on, util.t:828)
@@ -568,6 +597,7 @@ struct Plan : PlanBase {
         k_haloExchange<T><<<1, 1024, 0, stream>>>(&hp == &haloP ? dHaloP : dHaloZ, ws, vec); ++launches;
     }
     void readScalars() {
+        resolveCost();
         if (world > 1) { k_finalizeScalars<<<1, 32, 0, stream>>>(ws, (1u << kRz0) | (1u << kRz1) | (1u << kPAp) | (1u << kCost) | (1u << kModelCost) | (1u << kQ)); ++launches; }
         OPT_CUDA_CHECK(cudaMemcpyAsync(hScalars, ws.scalars, sizeof(double) * kNumScalars, cudaMemcpyDeviceToHost, stream));
         OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -582,6 +612,7 @@ struct Plan : PlanBase {
         E->bind(params);
         E->newSolve();
         enter();
+        if (costPending || loopMsPending) { OPT_CUDA_CHECK(cudaStreamSynchronize(stream)); resolveCost(); }
         nIter = 0; finished = false; reported = false; launches = 0;
         if (timingOn) { OPT_CUDA_CHECK(cudaStreamSynchronize(stream)); dropTimedLaunches(); }   // a previous solve that was abandoned before it finished
         trust_region_radius = (T)sp.trust_region_radius; radius_decrease_factor = (T)sp.radius_decrease_factor;
@@ -753,7 +784,11 @@ struct Plan : PlanBase {
 
     int step(void** params) override {   // :1016-1177
         E->bind(params);
-        if (finished || !(nIter < sp.nIterations)) { if (!reported) { finishSolve(); reported = true; } finished = true; return 0; }
+        if (finished || !(nIter < sp.nIterations)) {
+            if (costPending || loopMsPending) { OPT_CUDA_CHECK(cudaStreamSynchronize(stream)); resolveCost(); }   // the solve ends with all of its work complete, like the reference
+            if (!reported) { finishSolve(); reported = true; }
+            finished = true; return 0;
+        }
         enter();
         launches = 0;
         LaunchCtx c = ctx();
@@ -786,10 +821,17 @@ struct Plan : PlanBase {
         }
         tEnd();
         E->precompute(c);
+        if (!lm && verbosity == 0 && !timingOn && asyncSteps) {   // GN: nothing below needs the cost on the host
+            resolveCost();          // the previous step's value, before its pinned slot is reused
+            computeCostAsync();
+            loopMsPending = true;
+            ++nIter;
+            return 1;
+        }
         tBegin("computeCost");
         T newCost = computeCost();
         tEnd();    // syncs; hScalars also carries the model cost and the loop timing is complete
-        OPT_CUDA_CHECK(cudaEventElapsedTime(&loopMs, evLoop0, evLoop1));
+        OPT_CUDA_CHECK(cudaEventElapsedTime(&loopMs, evLoop0, evLoop1)); loopMsPending = false;
         int ret = 1;
         if (lm) {   // :1119-1157
             T model_cost = (T)hScalars[kModelCost];

@@ -11,6 +11,7 @@
 // Per PCG step the gather reads p, the 10 row coefficients and the flag byte of a pixel's neighbourhood (L1/L2 hits after
 // the first touch): ~53 B/pixel from HBM against the 208+ B/pixel of the cached-Jacobian engine this energy used before.
 // Default for this energy (OPTB_GENERIC=1 selects the cached-Jacobian engine instead); parity: tests/test_gpu_generic_energies.py.
+#include <algorithm>
 #include <type_traits>
 #include "solver.h"
 #include "sfs_device.cuh"
@@ -66,6 +67,91 @@ __global__ void __launch_bounds__(kBlock) k_sfsApplyJTJ(SfsData<T> P, ReduceWork
     }
     if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
 }
+// PCGStep1, tiled: the same operator as k_sfsApplyJTJ in two passes over a 32x8 tile held in shared memory.  The one-pass gather
+// re-forms every row's  y = row . p  once per unknown that row touches (5x for the shading rows, 5x3 for the smoothness rows): ~260
+// L1/L2 loads per pixel per PCG step, which is what bounds it (46 us per step at 640x480, measured).  Here p (tile + 2-pixel ring),
+// then the five row values and the ten shading-row coefficients of every row centre in tile + 1-pixel ring are staged once; the gather
+// for unknown u reads them from shared memory.  HBM/L2 traffic per pixel: p, 10 coefficients, the flag byte, out (+CtC).
+// Same products in the same order as sfsGather<T, 0> (rows with a zero coefficient contribute an exact 0 instead of being skipped).
+constexpr int kSfsTW = 32, kSfsTH = 8;
+constexpr int kSfsRW = kSfsTW + 2, kSfsRH = kSfsTH + 2, kSfsPW = kSfsTW + 4, kSfsPH = kSfsTH + 4;
+static_assert(kSfsTW * kSfsTH == kBlock, "one thread per tile pixel");
+template <class T, bool LM>
+__global__ void __launch_bounds__(kBlock) k_sfsApplyJTJTiled(SfsData<T> P, ReduceWorkspace ws, int dotSlot, const T* __restrict__ x, T* __restrict__ out,
+                                                             const T* __restrict__ CtC, int tilesX, int numTiles) {
+    __shared__ T sp[kSfsPH][kSfsPW];
+    __shared__ T sy[5][kSfsRH][kSfsRW];        // yR, yC, yS.x, yS.y, yS.z of the row centred at the cell
+    __shared__ T sc[10][kSfsRH][kSfsRW];       // cR[0..4], cC[0..4] of the row centred at the cell
+    const long N = (long)P.W * P.H;
+    const int tid = threadIdx.x, tx = tid % kSfsTW, ty = tid / kSfsTW;
+    T acc = T(0);
+    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        const int x0 = (tile % tilesX) * kSfsTW, y0 = (tile / tilesX) * kSfsTH;
+        __syncthreads();   // the previous tile's gather is done with the staging buffers
+        for (int c = tid; c < kSfsPH * kSfsPW; c += kBlock) {
+            const int ly = c / kSfsPW, lx = c - ly * kSfsPW, gx = x0 - 2 + lx, gy = y0 - 2 + ly;
+            sp[ly][lx] = (gx >= 0 && gx < P.W && gy >= 0 && gy < P.H) ? x[(long)gy * P.W + gx] : T(0);
+        }
+        __syncthreads();
+        for (int c = tid; c < kSfsRH * kSfsRW; c += kBlock) {
+            const int ly = c / kSfsRW, lx = c - ly * kSfsRW, gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+            T y[5] = { T(0), T(0), T(0), T(0), T(0) }, co[10] = { T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0) };
+            if (gx >= 0 && gx < P.W && gy >= 0 && gy < P.H) {
+                const long ci = (long)gy * P.W + gx;
+                const unsigned f = P.fl[ci];
+                if (f & kSfsInner) {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const T* coef = t == 0 ? P.cR : P.cC;
+#pragma unroll
+                        for (int m = 0; m < 5; ++m) {
+                            const T am = coef[(long)m * N + ci];
+                            co[t * 5 + m] = am;
+                            y[t] += am * sp[ly + 1 + sfsDy(t, m)][lx + 1 + sfsDx(t, m)];
+                        }
+                    }
+                }
+                if (f & kSfsFlat) {
+#pragma unroll
+                    for (int comp = 0; comp < 3; ++comp)
+#pragma unroll
+                        for (int m = 0; m < 5; ++m) y[2 + comp] += sfsCoefS(P, gx, gy, comp, m) * sp[ly + 1 + sfsDy(2, m)][lx + 1 + sfsDx(2, m)];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sy[k][ly][lx] = y[k];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) sc[k][ly][lx] = co[k];
+        }
+        __syncthreads();
+        const int px = x0 + tx, py = y0 + ty;
+        if (px < P.W && py < P.H) {
+            const long u = (long)py * P.W + px;
+            T o = T(0);
+            if (P.fl[u] & kSfsIncluded) {
+                const T xi = sp[ty + 2][tx + 2];
+                o = P.wp * (P.wp * xi);                                                       // r_p
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {                                             // u is dependency k of the row centred at u - offset_k
+                        const int cy = ty + 1 - sfsDy(t, k), cx = tx + 1 - sfsDx(t, k);
+                        o += sc[t * 5 + k][cy][cx] * sy[t][cy][cx];
+                    }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const int cy = ty + 1 - sfsDy(2, k), cx = tx + 1 - sfsDx(2, k);
+#pragma unroll
+                    for (int comp = 0; comp < 3; ++comp) o += sfsCoefS(P, px - sfsDx(2, k), py - sfsDy(2, k), comp, k) * sy[2 + comp][cy][cx];
+                }
+                if (LM) o += CtC[u] * xi;
+                acc += xi * o;
+            }
+            out[u] = o;
+        }
+    }
+    if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
+}
 template <class T, bool MODEL>
 __global__ void __launch_bounds__(kBlock) k_sfsCost(SfsData<T> P, ReduceWorkspace ws, int slot, const T* __restrict__ delta) {
     const long N = (long)P.W * P.H;
@@ -97,7 +183,13 @@ struct SfsOps : EnergyOps<T> {
         int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         long g = (N + kBlock - 1) / kBlock; if (g > (long)sms * 8) g = (long)sms * 8; if (g > kMaxPartials) g = kMaxPartials; if (g < 1) g = 1;
         grid = (int)g;
+        tilesX = (P.W + kSfsTW - 1) / kSfsTW; numTiles = tilesX * ((P.H + kSfsTH - 1) / kSfsTH);
+        int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_sfsApplyJTJTiled<T, true>, kBlock, 0);
+        if (occ < 1) occ = 1;
+        gridTiled = (int)std::min<long>(std::min<long>(numTiles, (long)sms * occ), kMaxPartials);
+        tiled = !getenv("OPTB_SFS_NO_TILED");   // the one-pass gather (A/B measurements)
     }
+    int tilesX = 0, numTiles = 0, gridTiled = 1; bool tiled = true;
     ~SfsOps() override { cudaFree(P.B); cudaFree(P.dB); cudaFree(P.cR); cudaFree(P.cC); cudaFree(P.fl); }
     const char* name() const override { return "shape_from_shading"; }
     unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(P); }
@@ -118,6 +210,11 @@ struct SfsOps : EnergyOps<T> {
         k_sfsInit<T><<<grid, kBlock, 0, c.stream>>>(P, this->usePreconditioner ? 1 : 0, c.ws, rzSlot, delta, r, pre, p);
     }
     void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot, const HaloPlan*) override {
+        if (tiled) {
+            if (CtC) k_sfsApplyJTJTiled<T, true><<<gridTiled, kBlock, 0, c.stream>>>(P, c.ws, dotSlot, x, out, CtC, tilesX, numTiles);
+            else k_sfsApplyJTJTiled<T, false><<<gridTiled, kBlock, 0, c.stream>>>(P, c.ws, dotSlot, x, out, nullptr, tilesX, numTiles);
+            return;
+        }
         if (CtC) k_sfsApplyJTJ<T, true><<<grid, kBlock, 0, c.stream>>>(P, c.ws, dotSlot, x, out, CtC);
         else k_sfsApplyJTJ<T, false><<<grid, kBlock, 0, c.stream>>>(P, c.ws, dotSlot, x, out, nullptr);
     }

@@ -55,11 +55,15 @@ def _k_steps(energy, kind, dims, host, k, tol=3e-4, names=("delta", "r", "p", "A
     for q in (s, o):
         q.set_solver_parameter("nIterations", 1); q.set_solver_parameter("lIterations", 50)
         q.set_max_linear_iterations(k)
+    r0max = float(np.abs(o.eval_jtf(ref)[1]).max())          # |J^T F|_inf: the scale the residual recurrence cancels from
     s.init(dev); o.init(ref)
     s.step(dev); o.step(ref)
     for name in names:
         a = s.read_vector(name); b = _flat(s, o.get_vector(name))
-        assert np.abs(a - b).max() <= tol * max(1e-30, np.abs(b).max()), (name, k)
+        # relative to the vector's own inf-norm; r (and Ap) are differences of terms of size |J^T F|, so once PCG has reduced r by
+        # orders of magnitude (cat512: 8e3 -> 0.2 in 7 steps) the fp32 floor is a few ulp of THAT scale, not of |r|
+        floor = 5e-6 * r0max if name in ("r", "Ap_X") else 0.0
+        assert np.abs(a - b).max() <= max(tol * max(1e-30, np.abs(b).max()), floor), (name, k, float(np.abs(a - b).max()), float(np.abs(b).max()), r0max)
     s.close()
 
 
@@ -118,6 +122,32 @@ def test_image_warping_tile_geometry(built, W, H):
         finally:
             for kk, v in old.items():
                 os.environ.pop(kk, None) if v is None else os.environ.__setitem__(kk, v)
+
+
+@pytest.mark.parametrize("W,H", [(45, 37), (70, 19), (32, 8), (33, 9), (5, 4)])
+@pytest.mark.parametrize("dp", [False, True])
+def test_shape_from_shading_tile_geometry(built, W, H, dp):
+    """the tiled J^T J kernel (32x8 tiles in shared memory) on sizes that cut tiles on both axes, and against the one-pass gather"""
+    from opt_b200 import OptSolver, spec_path
+    from oracle.oracle import Oracle
+    host = workloads.shape_from_shading(W, H, dtype=np.float64 if dp else np.float32)
+    s = OptSolver([W, H], spec_path("shape_from_shading"), "LMGPU", double_precision=dp)
+    o = Oracle("shape_from_shading", "LMGPU", [W, H], double_precision=dp)
+    dev = workloads.to_device(host)
+    x = np.random.default_rng(W * H).normal(size=W * H).astype(host[16].dtype)
+    xf = _flat(s, x)
+    out, dot = s.apply_jtj(dev, xf)
+    ref = _flat(s, o.apply_jtj(host, x))
+    assert np.abs(out - ref).max() <= (1e-11 if dp else 5e-5) * max(1.0, np.abs(ref).max())
+    s.close()
+    os.environ["OPTB_SFS_NO_TILED"] = "1"
+    try:
+        s2 = OptSolver([W, H], spec_path("shape_from_shading"), "LMGPU", double_precision=dp)
+    finally:
+        os.environ.pop("OPTB_SFS_NO_TILED", None)
+    out2, dot2 = s2.apply_jtj(dev, xf)
+    assert np.abs(out - out2).max() <= (1e-13 if dp else 1e-6) * max(1.0, np.abs(ref).max())     # same products, same order
+    s2.close()
 
 
 def test_shape_from_shading_shipped_fixture(built):

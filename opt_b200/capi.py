@@ -1,4 +1,4 @@
-"""ctypes binding of libOpt.so (include/Opt.h, include/OptB200.h).  Plain C ABI, no torch types."""
+"""ctypes binding of libOpt.so (include/Opt.h, include/OptB200.h, include/OptB200Examples.h).  Plain C ABI, no torch types."""
 import ctypes
 import os
 
@@ -44,6 +44,13 @@ SYMBOLS = [
     ("OptB200_FrontendCompile", ctypes.c_int, [_CP, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
     ("OptB200_PlanCommHandles", ctypes.c_int, [_VP, _VP, ctypes.c_int]),
     ("OptB200_PlanConnect", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    # include/OptB200Examples.h: the example harnesses' per-outer-iteration pre-steps on the device
+    ("OptB200_ImageWarpingConstraints", ctypes.c_int, [_VP, _VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_int, ctypes.c_float, ctypes.c_int, _VP]),
+    ("OptB200_ArapConstraints", ctypes.c_int, [_VP, _VP, ctypes.c_int, _VP, _VP, ctypes.c_int, ctypes.c_float, ctypes.c_int, _VP]),
+    ("OptB200_VertexNormals", ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, _VP, ctypes.c_int, _VP, _VP]),
+    ("OptB200_PointGridCreate", _VP, [_VP, ctypes.c_int, ctypes.c_float, _VP]),
+    ("OptB200_PointGridFree", None, [_VP]),
+    ("OptB200_RnaCorrespondences", ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_int, _VP]),
 ]
 
 

@@ -90,3 +90,68 @@ def arap_from_files(mesh_file, marker_file, alpha=1.0, dtype=np.float32, w_fit=4
     head, tail = io.mesh_neighbour_edges(v, faces)
     c = lambda a: np.ascontiguousarray(a.astype(dtype))
     return [float(np.sqrt(np.float32(w_fit))), float(np.sqrt(np.float32(w_reg))), c(v), np.zeros((N, 3), dtype), c(v), cons, int(len(head)), head, tail], N
+
+
+# ------------------------------------------------------------------------------------------------ per-outer-iteration pre-steps on the GPU
+# (include/OptB200Examples.h; thin wrappers over torch CUDA tensors -- device memory plumbing only)
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _dp(t):
+    import torch
+    return 1 if t.dtype == torch.float64 else 0
+
+
+def image_warping_constraints_gpu(constraints, mask, W, H, rows, alpha):
+    """setConstraintImage(alpha) on the device: `constraints` (W*H*2) is rewritten in place from the marker rows (n x 4 int32 CUDA tensor)"""
+    from . import capi
+    rc = capi.lib().OptB200_ImageWarpingConstraints(_ptr(constraints), _ptr(mask), W, H, _ptr(rows), int(rows.shape[0]), float(alpha), _dp(constraints), None)
+    if rc != 0:
+        raise capi.OptError(f"OptB200_ImageWarpingConstraints failed ({rc})")
+
+
+def arap_constraints_gpu(constraints, current, idx, targets, alpha):
+    from . import capi
+    rc = capi.lib().OptB200_ArapConstraints(_ptr(constraints), _ptr(current), int(current.shape[0]), _ptr(idx), _ptr(targets), int(idx.shape[0]), float(alpha), _dp(constraints), None)
+    if rc != 0:
+        raise capi.OptError(f"OptB200_ArapConstraints failed ({rc})")
+
+
+def vertex_normals_gpu(positions, faces):
+    import torch
+    from . import capi
+    out = torch.empty((positions.shape[0], 3), dtype=torch.float32, device=positions.device)
+    rc = capi.lib().OptB200_VertexNormals(_ptr(positions), _dp(positions), int(positions.shape[0]), _ptr(faces), int(faces.shape[0]), _ptr(out), None)
+    if rc != 0:
+        raise capi.OptError(f"OptB200_VertexNormals failed ({rc})")
+    return out
+
+
+class PointGrid:
+    """search structure over the target vertices of robust_nonrigid_alignment (replaces the harness's nanoflann k-d tree)"""
+
+    def __init__(self, target_pos, cell_size):
+        from . import capi
+        self.L = capi.lib(); self.tp = target_pos
+        self.h = self.L.OptB200_PointGridCreate(_ptr(target_pos), int(target_pos.shape[0]), float(cell_size), None)
+        if not self.h:
+            raise capi.OptError("OptB200_PointGridCreate failed")
+
+    def close(self):
+        if self.h:
+            self.L.OptB200_PointGridFree(self.h); self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def correspondences(self, target_normals, source_pos, source_normals, constraints, constraint_normals, robust_weights, prev_constraints,
+                        position_threshold, cos_normal_threshold=0.7, max_k=20):
+        """setConstraints of the harness: fills constraints / constraint_normals / robust_weights in place, returns the number of changed constraints"""
+        from . import capi
+        rc = self.L.OptB200_RnaCorrespondences(self.h, _ptr(self.tp), _ptr(target_normals), _ptr(source_pos), _ptr(source_normals), int(source_pos.shape[0]),
+                                               float(position_threshold), float(cos_normal_threshold), int(max_k), _ptr(constraints), _ptr(constraint_normals),
+                                               _ptr(robust_weights), _ptr(prev_constraints), _dp(source_pos), None)
+        if rc < 0:
+            raise capi.OptError(f"OptB200_RnaCorrespondences failed ({rc})")
+        return rc

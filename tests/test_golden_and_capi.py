@@ -35,7 +35,7 @@ def test_oracle_reproduces_golden(built, name):
 
 def _declared_symbols():
     names = []
-    for h in ("Opt.h", "OptB200.h"):
+    for h in ("Opt.h", "OptB200.h", "OptB200Examples.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names += re.findall(r"\b(Opt(?:B200)?_[A-Za-z]+)\s*\(", src)
@@ -55,6 +55,18 @@ def test_library_exports_every_declared_symbol(built):
     for n in declared:
         assert re.search(rf"\bT {n}\b", nm), n
     assert b"sm_100a" in L.OptB200_Version()
+
+
+def test_io_library_exports_every_declared_symbol(built):
+    """include/OptB200IO.h <-> opt_b200/lib/libOptIO.so"""
+    from opt_b200 import io
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "OptB200IO.h")).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(OptIO_[A-Za-z]+)\s*\(", src)))
+    assert len(declared) >= 14
+    L = io.lib()
+    nm = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "opt_b200", "lib", "libOptIO.so")], text=True)
+    for n in declared:
+        assert hasattr(L, n) and re.search(rf"\bT {n}\b", nm), n
 
 
 def test_struct_layout_matches_reference_header():

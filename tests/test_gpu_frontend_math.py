@@ -95,7 +95,7 @@ def _run_in_child(body):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = (f"import sys, pathlib, tempfile; sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
-            "import test_gpu_zz_frontend_math as t\ntmp = pathlib.Path(tempfile.mkdtemp())\n" + body + "\nprint('CHILD_OK')\n")
+            "import test_gpu_frontend_math as t\ntmp = pathlib.Path(tempfile.mkdtemp())\n" + body + "\nprint('CHILD_OK')\n")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0 and "CHILD_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
 

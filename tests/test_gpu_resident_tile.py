@@ -62,7 +62,7 @@ def test_tile_variant_matches_per_step_loop(built):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = (f"import sys; sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r}); import test_gpu_zz_resident_tile as t\n"
+    code = (f"import sys; sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r}); import test_gpu_resident_tile as t\n"
             + "\n".join(f"t._compare({W}, {H}, {tile!r}); print('case {W}x{H} tile {tile} ok')" for W, H, tile in CASES) + "\nprint('TILE_OK')\n")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0 and "TILE_OK" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])

@@ -4,7 +4,7 @@
 #   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/gpu2_call.sh'
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1"
-timeout 500 python -m pytest tests/test_gpu_multi.py tests/test_gpu_zz_multi_persistent.py -q -rxXs 2>&1 | tail -40 > gpurun_out/tests_2gpu.txt
+timeout 500 python -m pytest tests/test_gpu_multi.py tests/test_gpu_multi_persistent.py -q -rxXs 2>&1 | tail -40 > gpurun_out/tests_2gpu.txt
 {
   echo "== 1024^2 on 2 ranks, collective loop kernel (default when it fits)"
   timeout 200 $TR --master-port 29621 bench.py --gpus 2 --size 1024 --steps 6 --warmup 3

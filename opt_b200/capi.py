@@ -55,7 +55,8 @@ SYMBOLS = [
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libOpt.so")
+    # OPTB_LIBOPT: an alternative build of the same library (kernel-variant A/B runs, tools/build_variants.sh); never a fallback
+    return os.environ.get("OPTB_LIBOPT") or os.path.join(_HERE, "lib", "libOpt.so")
 
 
 def lib():

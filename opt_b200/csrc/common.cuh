@@ -385,9 +385,10 @@ __device__ __forceinline__ double gridAllReduceLL(double v, unsigned long long* 
 // identical; the last CTA of each rank then publishes the RANK's partial to every rank's NVLink mailbox (slot `slot`,
 // sequence k, sender = this rank -- the wire format of publishScalar) instead of a local result slot, and warp 0 of every CTA
 // polls the `world` senders of its own mailbox (one lane per word, as loadScalars2) and adds them in rank order, so every
-// CTA of every rank obtains the bitwise-identical sum.  releaseData additionally makes this CTA's earlier stores -- local
-// ones AND NVLink stores into a neighbour's memory -- visible to every rank after the call (system-scope fences).
-// NOT yet run on hardware (written after the round's GPU budget was spent).
+// CTA of every rank obtains the bitwise-identical sum.  releaseData makes this CTA's earlier LOCAL global stores visible to
+// the other CTAs of this rank after the call (device-scope fences, as in gridAllReduceLL).  Data for OTHER ranks must not rely
+// on this call: it travels as self-validating LL words (llStore / llLoad below) -- a system-scope fence per CTA on each side
+// of the reduction cost ~10 us per PCG step when it was done that way (measured on 2 B200s: 26.9 us per step).
 template <int NT>
 __device__ __forceinline__ double gridAllReduceLLMulti(double v, unsigned long long* words, unsigned long long* arrivals, unsigned long long k, bool releaseData,
                                                        const CommView& comm, int slot) {
@@ -409,7 +410,7 @@ __device__ __forceinline__ double gridAllReduceLLMulti(double v, unsigned long l
         const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
         if (lane < 2) stVolatileU64(row + 2 * blockIdx.x + lane, ((lane ? (bits >> 32) : (bits & 0xffffffffull)) << 32) | seq);
         if (lane == 0) {
-            if (releaseData) __threadfence_system();
+            if (releaseData) __threadfence();
             const unsigned long long prev = atomicAdd(arrivals, 1ull);
             s_last = (prev + 1ull == (unsigned long long)gridDim.x * k);
         }
@@ -431,7 +432,7 @@ __device__ __forceinline__ double gridAllReduceLLMulti(double v, unsigned long l
             for (unsigned i = lane; i < gridDim.x; i += 32) u += s_part[i];   // fixed order
             u = warpSum(u);
             const unsigned long long bits = (unsigned long long)__double_as_longlong(u);
-            if (releaseData) __threadfence_system();
+            if (releaseData) __threadfence();
             if (lane < 2 * comm.world)   // lane = 2 * destination rank + word
                 stVolatileU64(comm.peerWords[lane >> 1] + mailboxWord(slot, k, comm.rank) + (lane & 1), (((lane & 1) ? (bits >> 32) : (bits & 0xffffffffull)) << 32) | seq);
         }
@@ -450,13 +451,39 @@ __device__ __forceinline__ double gridAllReduceLLMulti(double v, unsigned long l
             const unsigned lo = __shfl_sync(0xffffffffu, payload, 2 * r), hi = __shfl_sync(0xffffffffu, payload, 2 * r + 1);
             sum += __longlong_as_double((long long)((unsigned long long)lo | ((unsigned long long)hi << 32)));
         }
-        if (lane == 0) { if (releaseData) __threadfence_system(); s_val = sum; }
+        if (lane == 0) { if (releaseData) __threadfence(); s_val = sum; }
     }
     __syncthreads();
     const double out = s_val;
     __syncthreads();
     return out;
 }
+
+// Self-validating data words for peer memory (NCCL-LL style): an opt_float travels as one (float) or two (double) 8-byte words, each
+// payload32 | sequence32, written with a single 8-byte store.  The reader polls the word itself until it carries the expected
+// sequence -- no flag, no fence on either side; the sequence only grows, so a stale word is never mistaken for a new one.
+__device__ __forceinline__ void llStore(unsigned long long* slot, float v, unsigned seq) {
+    stVolatileU64(slot, ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)seq);
+}
+__device__ __forceinline__ void llStore(unsigned long long* slot, double v, unsigned seq) {   // slot[0], slot[1]
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    stVolatileU64(slot, ((bits & 0xffffffffull) << 32) | (unsigned long long)seq);
+    stVolatileU64(slot + 1, ((bits >> 32) << 32) | (unsigned long long)seq);
+}
+__device__ __forceinline__ void llLoad(const unsigned long long* slot, unsigned seq, float& out) {
+    unsigned long long w, spins = 0;
+    do { w = ldVolatileU64(slot); if (++spins > (1ull << 26)) __trap(); } while ((unsigned)(w & 0xffffffffull) != seq);   // a lost rank is a bug: fail, do not hang
+    out = __uint_as_float((unsigned)(w >> 32));
+}
+__device__ __forceinline__ void llLoad(const unsigned long long* slot, unsigned seq, double& out) {
+    unsigned long long w0, w1, spins = 0;
+    do { w0 = ldVolatileU64(slot); w1 = ldVolatileU64(slot + 1); if (++spins > (1ull << 26)) __trap(); } while ((unsigned)(w0 & 0xffffffffull) != seq || (unsigned)(w1 & 0xffffffffull) != seq);
+    out = __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
+}
+template <class T> struct LLWords;
+template <> struct LLWords<float> { static constexpr int N = 1; };
+template <> struct LLWords<double> { static constexpr int N = 2; };
+constexpr size_t kPeerScratchBytes = 1u << 20;   // per-plan scratch behind the mailbox block, reachable by the peers (LL halo rows of the loop kernel)
 
 // Programmatic dependent launch (PDL): a kernel launched with launchPdl may begin while its predecessor on the stream
 // is still draining; it must call pdlWait() before touching anything the predecessor wrote.  Kernels call

@@ -713,7 +713,11 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopResident(IWData<T> D, Redu
 // last owned row also store their edge row of z into the neighbour's halo row over NVLink; the reductions span all ranks
 // (gridAllReduceLLMulti); and because the per-step path keeps X consistent on halo rows by recomputing delta there
 // (DESIGN.md section 6), boundary tiles accumulate delta for their ring row too ("shadow delta", sH*).
-template <class T> struct IWTileMulti { T* zUp; T* zDn; long upO, upA, dnO, dnA; };   // neighbour z vectors (nullptr: none) and where my edge rows land in them
+// Rank boundary of the collective loop kernel: z of my first / last owned row travels to the neighbouring rank as LL words (llStore /
+// llLoad, common.cuh) in that rank's peer scratch: 3 scalars per pixel (Offset.x, Offset.y, Angle) at word index (3 x + c) * LLWords<T>::N.
+// toUp / toDn: where I write (the upper neighbour's "from below" row / the lower neighbour's "from above" row; nullptr: no neighbour);
+// fromUp / fromDn: my own two rows, written by the neighbours.
+template <class T> struct IWTileMulti { unsigned long long* toUp; unsigned long long* toDn; const unsigned long long* fromUp; const unsigned long long* fromDn; };
 constexpr int kLoopMailboxSlot = 8;   // spare scalar slot of CommBlock::words used by the persistent loop's own sequence numbers
 template <class T, int KMAX, bool MULTI>
 __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long* arrivals,
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWo
     unsigned char* sF = reinterpret_cast<unsigned char*>(sQa + nCap);
     // MULTI: shadow delta of the ring row above (side 0) / below (side 1) when that row belongs to a neighbouring rank
     T* sH = reinterpret_cast<T*>(smemRaw + (((size_t)(nRing * 7 + nCap * 5) * sizeof(T) + nCap + 15) / 16) * 16);   // [2 sides][3 planes][tw]
-    const bool shadowUp = MULTI && M.zUp != nullptr && ty0 == D.y0, shadowDn = MULTI && M.zDn != nullptr && ty0 + thE == D.y1;
+    const bool shadowUp = MULTI && M.toUp != nullptr && ty0 == D.y0, shadowDn = MULTI && M.toDn != nullptr && ty0 + thE == D.y1;
     if (MULTI) for (int c = tid; c < 6 * tw; c += NT) sH[c] = T(0);
     const Vec2<T>* pO = reinterpret_cast<const Vec2<T>*>(p);
     for (int c = tid; c < (thE + 2) * pw; c += NT) {              // ring-included planes; cells outside the image are zero
@@ -759,7 +763,7 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWo
                 sF[c] = D.flags[i];
                 const Vec2<T> dO = reinterpret_cast<const Vec2<T>*>(delta)[i]; dx[q] = dO.x; dy[q] = dO.y; da[q] = delta[D.offA + i];
                 edge[q] = (ly == 0 || ly == thE - 1 || lx == 0 || lx == twE - 1);
-                if (MULTI) { pushUp[q] = M.zUp != nullptr && ty0 + ly == D.y0; pushDn[q] = M.zDn != nullptr && ty0 + ly == D.y1 - 1; }
+                if (MULTI) { pushUp[q] = M.toUp != nullptr && ty0 + ly == D.y0; pushDn[q] = M.toDn != nullptr && ty0 + ly == D.y1 - 1; }
             }
         }
     }
@@ -790,7 +794,12 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWo
                 const int gx = tx0 - 1 + lc, gy = ty0 - 1 + lr;
                 if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
                     const long j = (long)gy * W + gx;
-                    const Vec2<T> zo = ldcgV(reinterpret_cast<const Vec2<T>*>(z) + j); const T zaa = ldcgT(z + D.offA + j);
+                    Vec2<T> zo; T zaa;
+                    const unsigned long long* ll = !MULTI ? nullptr : ((gy == D.y0 - 1 && M.fromUp) ? M.fromUp : ((gy == D.y1 && M.fromDn) ? M.fromDn : nullptr));
+                    if (ll) {   // the row belongs to the neighbouring rank: its z arrives as LL words carrying this phase's sequence number
+                        const unsigned long long* w = ll + (size_t)3 * gx * LLWords<T>::N;
+                        llLoad(w, (unsigned)k, zo.x); llLoad(w + LLWords<T>::N, (unsigned)k, zo.y); llLoad(w + 2 * LLWords<T>::N, (unsigned)k, zaa);
+                    } else { zo = ldcgV(reinterpret_cast<const Vec2<T>*>(z) + j); zaa = ldcgT(z + D.offA + j); }
                     const int cc = lr * pw + lc;
                     sPx[cc] = zo.x + beta * sPx[cc]; sPy[cc] = zo.y + beta * sPy[cc]; sPa[cc] = zaa + beta * sPa[cc];
                 }
@@ -850,10 +859,11 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWo
                 zx[q] = qo * rx; zy[q] = qo * ry; za[q] = sQa[c] * ra;
                 acc += zx[q] * rx; acc += zy[q] * ry; acc += za[q] * ra;
                 if (edge[q]) { stcgV(reinterpret_cast<Vec2<T>*>(z) + giOf[q], Vec2<T>{ zx[q], zy[q] }); stcgT(z + D.offA + giOf[q], za[q]); }
-                if (MULTI && (pushUp[q] || pushDn[q])) {   // my edge row is the neighbouring rank's halo row: store it there over NVLink
-                    const long x = giOf[q] % W;
-                    if (pushUp[q]) { M.zUp[M.upO + 2 * x] = zx[q]; M.zUp[M.upO + 2 * x + 1] = zy[q]; M.zUp[M.upA + x] = za[q]; }
-                    if (pushDn[q]) { M.zDn[M.dnO + 2 * x] = zx[q]; M.zDn[M.dnO + 2 * x + 1] = zy[q]; M.zDn[M.dnA + x] = za[q]; }
+                if (MULTI && (pushUp[q] || pushDn[q])) {   // my edge row is the neighbouring rank's halo row: LL words over NVLink, no fence
+                    const size_t x = (size_t)(giOf[q] % W);
+                    const unsigned seq = (unsigned)(k + 1ull);   // = k after the reduction below: what the reader's phase A will expect
+                    if (pushUp[q]) { unsigned long long* w = M.toUp + 3 * x * LLWords<T>::N; llStore(w, zx[q], seq); llStore(w + LLWords<T>::N, zy[q], seq); llStore(w + 2 * LLWords<T>::N, za[q], seq); }
+                    if (pushDn[q]) { unsigned long long* w = M.toDn + 3 * x * LLWords<T>::N; llStore(w, zx[q], seq); llStore(w + LLWords<T>::N, zy[q], seq); llStore(w + 2 * LLWords<T>::N, za[q], seq); }
                 }
             }
         }
@@ -1174,7 +1184,10 @@ struct ImageWarpingOps : EnergyOps<T> {
         tileSmem = tileSmemFor(a, b, multi); tileK = (int)(((size_t)a * b + 1023) / 1024); tileMulti = multi; tileChecked = nullptr;
         return true;
     }
+    void* scratchMine = nullptr; void* scratchUp = nullptr; void* scratchDn = nullptr;
+    void setPeerScratch(void* mine, void* up, void* dn) override { scratchMine = mine; scratchUp = up; scratchDn = dn; }
     bool pcgLoopMultiFits() override {   // asked once per connect, after setSlab(): tile shape + co-residency of all tiles
+        if ((size_t)2 * 3 * D.W * LLWords<T>::N * sizeof(unsigned long long) > kPeerScratchBytes) return false;   // two LL rows must fit the peer scratch
         int dev = 0, coop = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (!coop || !chooseTile(true)) { tileW = -1; tileMulti = true; return false; }
@@ -1191,11 +1204,13 @@ struct ImageWarpingOps : EnergyOps<T> {
         if (tileW == 0 || tileMulti != multi) { if (!chooseTile(multi)) { tileW = -1; tileMulti = multi; } }
         if (tileW < 0) return false;
         IWTileMulti<T> M{};
-        if (multi) {   // where my first / last owned row lands in the neighbours' z vectors: the destinations of haloSegments()
-            M.zUp = (T*)haloZ->peerVec[0]; M.zDn = (T*)haloZ->peerVec[1];
-            const long W = D.W;
-            M.upO = 2 * W * (upperRows - 1); M.upA = alignUp64(2 * W * upperRows) + W * (upperRows - 1);
-            M.dnO = 0; M.dnA = alignUp64(2 * W * lowerRows);
+        if (multi) {   // LL rows in the peer scratch areas: row 0 of a rank's scratch = data from its upper neighbour, row 1 = from its lower neighbour
+            const size_t rowWords = (size_t)3 * D.W * LLWords<T>::N;
+            unsigned long long* mine = (unsigned long long*)scratchMine;
+            M.fromUp = haloZ->peerVec[0] ? mine : nullptr; M.fromDn = haloZ->peerVec[1] ? mine + rowWords : nullptr;
+            M.toUp = haloZ->peerVec[0] ? (unsigned long long*)scratchUp + rowWords : nullptr;    // I am my upper neighbour's lower neighbour
+            M.toDn = haloZ->peerVec[1] ? (unsigned long long*)scratchDn : nullptr;
+            if ((haloZ->peerVec[0] && !scratchUp) || (haloZ->peerVec[1] && !scratchDn) || !mine) return false;
             return tileK <= 2 ? launchTileK<2, true>(c, L, M, delta, r, z, p, Ap, pre) : launchTileK<4, true>(c, L, M, delta, r, z, p, Ap, pre);
         }
         return tileK <= 2 ? launchTileK<2, false>(c, L, M, delta, r, z, p, Ap, pre) : launchTileK<4, false>(c, L, M, delta, r, z, p, Ap, pre);

@@ -372,8 +372,8 @@ struct Plan : PlanBase {
         OPT_CUDA_CHECK(cudaMalloc((void**)&ws.scalars, sizeof(double) * kNumScalars));
         OPT_CUDA_CHECK(cudaMemset(ws.counters, 0, sizeof(unsigned) * kNumScalars));
         OPT_CUDA_CHECK(cudaMemset(ws.scalars, 0, sizeof(double) * kNumScalars));
-        OPT_CUDA_CHECK(cudaMalloc((void**)&commBlock, sizeof(CommBlock)));
-        OPT_CUDA_CHECK(cudaMemset(commBlock, 0, sizeof(CommBlock)));
+        OPT_CUDA_CHECK(cudaMalloc((void**)&commBlock, sizeof(CommBlock) + kPeerScratchBytes));   // mailboxes, then the peer scratch area
+        OPT_CUDA_CHECK(cudaMemset(commBlock, 0, sizeof(CommBlock) + kPeerScratchBytes));
         ws.comm.world = 1; ws.comm.rank = 0;
         OPT_CUDA_CHECK(cudaMallocHost((void**)&hScalars, sizeof(double) * kNumScalars));
         OPT_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -532,6 +532,8 @@ struct Plan : PlanBase {
             winVec.n = winScalar.n = (int)wins.size();
         }
         buildZPush(segs, ranges, wins, upZ, dnZ);
+        E->setPeerScratch((void*)(commBlock + 1), (rank > 0 && upperRows > 0) ? (void*)(peerBlocks[rank - 1] + 1) : nullptr,
+                          (rank + 1 < world && lowerRows > 0) ? (void*)(peerBlocks[rank + 1] + 1) : nullptr);
         if (segs.size() > (size_t)kMaxHaloSegs || ranges.size() > 4) { fprintf(stderr, "opt_b200: at most %d halo segments / 4 owned ranges per rank are supported\n", kMaxHaloSegs); return -5; }
         if (loopExec) { cudaGraphExecDestroy(loopExec); loopExec = nullptr; }
         // collective decision about the one-kernel PCG loop: every rank posts whether it can run it, into every rank's block;

@@ -103,6 +103,9 @@ struct EnergyOps {
     // cooperative launch available)?  Asked once per OptB200_PlanConnect, after setSlab(); the plan combines the answers of all ranks
     // so that either every rank takes the collective kernel or none does.  After a "yes" a refusal inside pcgLoop is fatal.
     virtual bool pcgLoopMultiFits() { return false; }
+    // multi-GPU: kPeerScratchBytes of zero-initialised device memory of this rank and of its upper / lower neighbour (nullptr: none), mapped
+    // through CUDA IPC at OptB200_PlanConnect -- for data the energy's collective kernels exchange as self-validating LL words
+    virtual void setPeerScratch(void* /*mine*/, void* /*upper*/, void* /*lower*/) {}
     // ---- multi-GPU slab decomposition.  The plan's dimensions describe the LOCAL domain =
     // owned slab rows + halo rows; [ownedBegin, ownedEnd) are the owned local rows, upperRows/lowerRows the
     // local row counts of the neighbouring ranks (0 = no neighbour).  Returns false if unsupported.

@@ -15,6 +15,8 @@ timeout 300 python tools/bench_graph_multi.py --workload rna1m > gpurun_out/rna1
   done
 } > gpurun_out/variants.txt 2>&1
 timeout 400 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+# per-rank problem sizes of the 2/4/8-GPU runs on ONE GPU, no communication: what the per-step loop costs without the sync points
+for sz in "2048 1024" "2048 512" "2048 256"; do set -- $sz; timeout 200 python tools/bench_slab_single.py $1 $2 >> gpurun_out/slab_single.jsonl 2>> gpurun_out/bench.err; done
 OPTB_BENCH_SERIAL_E2E=1 timeout 400 python bench.py --no-cpu-baseline > gpurun_out/bench_serial_e2e.json 2>> gpurun_out/bench.err
 # ncu: launch list of the bench command, then full captures of the dominant kernels
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 400 --csv --log-file gpurun_out/r2_launches_iw2048.csv python bench.py --steps 2 --warmup 3 --liters 40 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1

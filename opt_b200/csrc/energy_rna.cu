@@ -81,6 +81,20 @@ __global__ void __launch_bounds__(kBlock) k_rnaCtC(RnaData<T> D, T* __restrict__
         rnaStore(CtC, D, v, d);
     }
 }
+// graph symmetry test (as energy_arap.cu): every out-neighbour b of v must list v among ITS out-neighbours with the same multiplicity
+static __global__ void k_rnaSymmetric(int N, const int* __restrict__ outStart, const int* __restrict__ outNbr, const int* __restrict__ inStart, int* __restrict__ notSymmetric) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < N; v += gridDim.x * blockDim.x) {
+        bool ok = (outStart[v + 1] - outStart[v]) == (inStart[v + 1] - inStart[v]);
+        for (int k = outStart[v]; ok && k < outStart[v + 1]; ++k) {
+            const int b = outNbr[k];
+            int cnt = 0, mine = 0;
+            for (int q = outStart[b]; q < outStart[b + 1]; ++q) cnt += outNbr[q] == v;
+            for (int q = outStart[v]; q < outStart[v + 1]; ++q) mine += outNbr[q] == b;
+            ok = cnt == mine;
+        }
+        if (!ok) *notSymmetric = 1;
+    }
+}
 static __global__ void k_rnaCsrStart(int nE, const int* __restrict__ sortedKeys, int N, int* __restrict__ start) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= nE; t += gridDim.x * blockDim.x) {
         const int k = t < nE ? sortedKeys[t] : N, kp = t > 0 ? sortedKeys[t - 1] : -1;
@@ -163,6 +177,13 @@ struct RnaOps : EnergyOps<T> {
         cub::DeviceRadixSort::SortPairs(cubTemp, cubBytes, v1, keysTmp, v0, inNbr, nEdges, 0, endBit, st);
         k_rnaCsrStart<<<g, 256, 0, st>>>(nEdges, keysTmp, D.N, inStart);
         D.outStart = outStart; D.outNbr = outNbr; D.inStart = inStart; D.inNbr = inNbr;
+        // symmetric graphs (every mesh the reference app builds lists both directions of an edge, OptGraph.h:64-75) take the merged loop of
+        // the J^T J gather: one neighbour visit serves the edge and its reverse
+        int* flag = keysTmp;   // the sort keys are no longer needed
+        OPT_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+        k_rnaSymmetric<<<g, 256, 0, st>>>(D.N, outStart, outNbr, inStart, flag);
+        int ns = 1; OPT_CUDA_CHECK(cudaMemcpyAsync(&ns, flag, sizeof(int), cudaMemcpyDeviceToHost, st)); OPT_CUDA_CHECK(cudaStreamSynchronize(st));
+        D.symmetric = (ns == 0 && !getenv("OPTB_RNA_NO_SYMMETRIC")) ? 1 : 0;
         csrValid = true;
     }
     // the pack depends on the current unknowns: refreshed wherever the reference refreshes its linearisation

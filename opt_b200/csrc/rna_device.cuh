@@ -43,6 +43,7 @@ struct RnaData {
     RnaPack<T>* pack;
     const int *outStart, *outNbr, *inStart, *inNbr;   // vertex-CSR neighbour lists (out: edges v->b, in: edges c->v)
     int lo, hi, wlo, whi;        // multi-GPU (kernels only): owned vertices [lo,hi) and the window incl. halo [wlo,whi); single GPU: [0,N)
+    int symmetric;               // every edge (a,b) has its reverse (b,a) with the same multiplicity: the in-list of a vertex equals its out-list
 };
 
 RNA_HD void rnaSinCos(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }
@@ -117,9 +118,19 @@ template <class T, int MODE> RNA_HD RnaOut<T> rnaGather(const RnaData<T>& D, int
             }
             aO.x += y.x; aO.y += y.y; aO.z += y.z;
             aA.x -= rnaDot(c0, y); aA.y -= rnaDot(c1, y); aA.z -= rnaDot(c2, y);
+            if (MODE == 0 && D.symmetric) {   // the reverse edge b -> v exists: its term needs the same neighbour data (one gather instead of two)
+                const RnaRot<T> Rb(sb_);
+                const RnaV3<T> pAb = rnaLd3(vec + D.offA, b), pOb = rnaLd3(vec, b);
+                const RnaV3<T> dr{ -d.x, -d.y, -d.z };                       // U_b - U_v
+                const RnaV3<T> Rdr = Rb.apply(dr);
+                RnaV3<T> e0, e1, e2; Rb.columns(dr, Rdr, e0, e1, e2);
+                aO.x -= (pOb.x - pOv.x) - (e0.x * pAb.x + e1.x * pAb.y + e2.x * pAb.z);
+                aO.y -= (pOb.y - pOv.y) - (e0.y * pAb.x + e1.y * pAb.y + e2.y * pAb.z);
+                aO.z -= (pOb.z - pOv.z) - (e0.z * pAb.x + e1.z * pAb.y + e2.z * pAb.z);
+            }
         }
     }
-    for (int k = D.inStart[v]; k < D.inStart[v + 1]; ++k) {            // edges c -> v: O_v enters with the opposite sign
+    for (int k = (MODE == 0 && D.symmetric) ? D.inStart[v + 1] : D.inStart[v]; k < D.inStart[v + 1]; ++k) {            // edges c -> v: O_v enters with the opposite sign
         if (MODE == 2) { aO.x += T(1); continue; }
         const int c = D.inNbr[k];
         const RnaPack<T> sc = D.pack[c];

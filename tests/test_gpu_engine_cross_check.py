@@ -13,10 +13,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _child(body, tag):
+def _child(body, tag, switch="OPTB_GENERIC"):
     code = ("import os, sys\n"
             f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
-            "os.environ['OPTB_GENERIC'] = '1'\n"
+            f"os.environ[{switch!r}] = '1'\n"
             "import test_gpu_generic_energies as g\n" + body + f"\nprint({tag!r})\n")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and tag in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
@@ -30,6 +30,16 @@ def test_generic_engine_matches_oracle(built, energy, kinds):
         for kind in kinds:
             lines.append(f"g.test_solve_parity(None, {energy!r}, {kind!r}, {dp})")
     _child("\n".join(lines), "GENERIC_OK")
+
+
+def test_rna_unmerged_gather_matches_oracle(built):
+    """robust_nonrigid_alignment's J^T J gather merges an edge with its reverse when the graph is symmetric (every mesh the reference
+    app builds); OPTB_RNA_NO_SYMMETRIC=1 keeps the two-loop form that arbitrary graphs take -- both must match the oracle"""
+    lines = []
+    for dp in (False, True):
+        lines.append(f"g.test_kernel_parity(None, 'robust_nonrigid_alignment', {dp})")
+        lines.append(f"g.test_solve_parity(None, 'robust_nonrigid_alignment', 'LMGPU', {dp})")
+    _child("\n".join(lines), "UNMERGED_OK", switch="OPTB_RNA_NO_SYMMETRIC")
 
 
 def test_hand_written_and_generic_agree(built):

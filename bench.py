@@ -437,13 +437,15 @@ def main():
         # (same ordering as the ncu launch list, profiles/r1_ncu_iw2048.md); algorithmic bytes per SURVEY 8(d)
         loop_kernels = {"PCGStep2": BYTES_STEP2, "PCGStep3+PCGStep1(fused)": BYTES_STEP1 + BYTES_STEP3, "PCGStep1": BYTES_STEP1}
         cands = [k for k in ("PCGStep2", "PCGStep3+PCGStep1(fused)") if k in prof] or [k for k in ("PCGStep1",) if k in prof]
-        traffic = None
+        traffic, traffic_src = None, None
         if cands:
             dom_name = max(cands, key=lambda k: prof[k])
             dom_bytes, dom_ms = loop_kernels[dom_name] * pixels, prof[dom_name]
-            tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-            if os.path.exists(tp) and W == W_FULL and H == H_FULL:
-                traffic = json.load(open(tp)).get(dom_name)
+            for tf in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):      # DRAM bytes per launch from the committed ncu --set full capture
+                tp = os.path.join(ROOT, "profiles", tf)
+                if os.path.exists(tp) and W == W_FULL and H == H_FULL and json.load(open(tp)).get(dom_name):
+                    traffic = json.load(open(tp)).get(dom_name); traffic_src = f"profiles/{tf} (ncu --set full capture of this kernel at this size; not measured in this run)"
+                    break
         else:                               # multi-GPU: no per-kernel replay; report the PCG step as the unit
             dom_name, dom_bytes, dom_ms = "PCG step (all kernels, rank 0 slab)", BYTES_PCG_STEP * W * (slab.g1 - slab.g0), loop_step_us * 1e-3
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
@@ -459,7 +461,7 @@ def main():
                     "ms_per_step": e2e_ms / ksteps, "what": "per step: pinned host inputs -> H2D, Opt_ProblemInit + one Opt_ProblemStep via the C ABI, unknowns -> D2H; copies on their own streams, double-buffered, overlapping the neighbouring steps' kernels" + (" (serial order forced)" if serial else "")},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": traffic,
+                         "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
                          "pcg_step": {"algorithmic_bytes_per_gpu": BYTES_PCG_STEP * W * (slab.g1 - slab.g0), "us_in_timed_region": loop_step_us,
                                       "achieved": BYTES_PCG_STEP * W * (slab.g1 - slab.g0) / (loop_step_us * 1e-6) / 1e9,

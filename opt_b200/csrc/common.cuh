@@ -247,6 +247,61 @@ __device__ __forceinline__ void gridReduceTo(double v, const ReduceWorkspace& ws
     __syncthreads();   // s_warp / s_last reusable by a second call in the same kernel
 }
 
+// Two sums with ONE arrival round (PCGStep2 of LM produces r.z and q together): same per-slot partial layout and summation order as
+// two gridReduceTo calls, so the values are bitwise the same; returns true in every thread of the CTA that finished the reduction, whose
+// thread 0 also receives the two LOCAL sums (single GPU: the reduced values).
+template <int NT>
+__device__ __forceinline__ bool gridReduceTo2(double v0, double v1, const ReduceWorkspace& ws, int slot0, int slot1, unsigned long long* const* releaseFlags,
+                                              double* out0, double* out1) {
+    __shared__ double s_warp2[2][NT / 32];
+    __shared__ bool s_last2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v0 = warpSum(v0); v1 = warpSum(v1);
+    if (lane == 0) { s_warp2[0][wid] = v0; s_warp2[1][wid] = v1; }
+    __syncthreads();
+    if (wid == 0) {
+        double t0 = lane < NT / 32 ? s_warp2[0][lane] : 0.0, t1 = lane < NT / 32 ? s_warp2[1][lane] : 0.0;
+        t0 = warpSum(t0); t1 = warpSum(t1);
+        if (lane == 0) {
+            ws.partials[(size_t)slot0 * kMaxPartials + blockIdx.x] = t0;
+            ws.partials[(size_t)slot1 * kMaxPartials + blockIdx.x] = t1;
+            if (releaseFlags) __threadfence_system(); else __threadfence();
+            unsigned int prev = atomicAdd(ws.counters + slot0, 1u);
+            s_last2 = (prev == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    const bool last = s_last2;
+    if (last) {
+        __threadfence();
+        double t0 = orderedStridedSum<NT>(ws.partials + (size_t)slot0 * kMaxPartials, gridDim.x);
+        double t1 = orderedStridedSum<NT>(ws.partials + (size_t)slot1 * kMaxPartials, gridDim.x);
+        t0 = warpSum(t0); t1 = warpSum(t1);
+        if (lane == 0) { s_warp2[0][wid] = t0; s_warp2[1][wid] = t1; }
+        __syncthreads();
+        if (wid == 0) {
+            double u0 = lane < NT / 32 ? s_warp2[0][lane] : 0.0, u1 = lane < NT / 32 ? s_warp2[1][lane] : 0.0;
+            u0 = warpSum(u0); u1 = warpSum(u1);
+            if (lane == 0) {
+                ws.counters[slot0] = 0u;
+                if (ws.comm.world <= 1) { ws.scalars[slot0] = u0; ws.scalars[slot1] = u1; }
+                if (out0) *out0 = u0; if (out1) *out1 = u1;
+            }
+            if (ws.comm.world > 1) { publishScalarWarp(ws, slot0, u0); publishScalarWarp(ws, slot1, u1); }
+            if (releaseFlags) {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_system();
+                    const unsigned long long e = haloEpochNow(ws);
+                    for (int d = 0; d < 2; ++d) if (releaseFlags[d]) stReleaseSys(releaseFlags[d], e);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    return last;
+}
+
 // ------------------------------------------------------------------ persistent-kernel reductions
 // State of the grid-wide all-reduce used by the persistent PCG-loop kernels (cooperative launch: all CTAs are
 // co-resident).  One object per plan; `k` is a sequence number that only ever grows (the host hands every launch a

@@ -111,11 +111,15 @@ __global__ void __launch_bounds__(kBlock) k_sfsApplyJTJTiled(SfsData<T> P, Reduc
                         }
                     }
                 }
-                if (f & kSfsFlat) {
+                if (f & kSfsFlat) {   // the 15 coefficients need 3 + 3 divisions, not 15 x 2 (sfsCoefS divides per call)
+                    const T ax[3] = { sfsAx(P, gx - 1), sfsAx(P, gx), sfsAx(P, gx + 1) }, ay[3] = { sfsAy(P, gy - 1), sfsAy(P, gy), sfsAy(P, gy + 1) };
 #pragma unroll
-                    for (int comp = 0; comp < 3; ++comp)
-#pragma unroll
-                        for (int m = 0; m < 5; ++m) y[2 + comp] += sfsCoefS(P, gx, gy, comp, m) * sp[ly + 1 + sfsDy(2, m)][lx + 1 + sfsDx(2, m)];
+                    for (int m = 0; m < 5; ++m) {
+                        const T pm = sp[ly + 1 + sfsDy(2, m)][lx + 1 + sfsDx(2, m)];
+                        y[2] += sfsCoefFromA(P, ax[1 + sfsDx(2, m)], m) * pm;
+                        y[3] += sfsCoefFromA(P, ay[1 + sfsDy(2, m)], m) * pm;
+                        y[4] += sfsCoefFromA(P, T(1), m) * pm;
+                    }
                 }
             }
 #pragma unroll
@@ -138,11 +142,13 @@ __global__ void __launch_bounds__(kBlock) k_sfsApplyJTJTiled(SfsData<T> P, Reduc
                         const int cy = ty + 1 - sfsDy(t, k), cx = tx + 1 - sfsDx(t, k);
                         o += sc[t * 5 + k][cy][cx] * sy[t][cy][cx];
                     }
+                const T axu = sfsAx(P, px), ayu = sfsAy(P, py);   // dependency k of the row centred at u - offset_k is u itself: one factor pair per pixel
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
                     const int cy = ty + 1 - sfsDy(2, k), cx = tx + 1 - sfsDx(2, k);
-#pragma unroll
-                    for (int comp = 0; comp < 3; ++comp) o += sfsCoefS(P, px - sfsDx(2, k), py - sfsDy(2, k), comp, k) * sy[2 + comp][cy][cx];
+                    o += sfsCoefFromA(P, axu, k) * sy[2][cy][cx];
+                    o += sfsCoefFromA(P, ayu, k) * sy[3][cy][cx];
+                    o += sfsCoefFromA(P, T(1), k) * sy[4][cy][cx];
                 }
                 if (LM) o += CtC[u] * xi;
                 acc += xi * o;

@@ -140,10 +140,14 @@ template <class T> SFS_HD T sfsFP(const SfsData<T>& P, long c) { return (P.fl[c]
 template <class T> SFS_HD T sfsFR(const SfsData<T>& P, long c) { return (P.fl[c] & kSfsInner) ? P.wg * ((P.B[c] - P.B[c + 1]) * T(P.eR[c])) : T(0); }
 template <class T> SFS_HD T sfsFC(const SfsData<T>& P, long c) { return (P.fl[c] & kSfsInner) ? P.wg * ((P.B[c] - P.B[c + P.W]) * T(P.eC[c])) : T(0); }
 // coefficient of the k-th dependency (order sfsDepsS) in component comp of the r_s row centred at (x, y); zero row unless flat
+// back-projection factor of pixel column qx / row qy (P(c) = (ax d, ay d, d)), and the row coefficient built from it
+template <class T> SFS_HD T sfsAx(const SfsData<T>& P, int qx) { return (T(qx) - P.ux) / P.fx; }
+template <class T> SFS_HD T sfsAy(const SfsData<T>& P, int qy) { return (T(qy) - P.uy) / P.fy; }
+template <class T> SFS_HD T sfsCoefFromA(const SfsData<T>& P, T a, int k) { return k == 0 ? P.ws * (T(4) * a) : -(P.ws * a); }
 template <class T> SFS_HD T sfsCoefS(const SfsData<T>& P, int x, int y, int comp, int k) {
     const int qx = x + sfsDx(2, k), qy = y + sfsDy(2, k);
-    const T a = comp == 0 ? (T(qx) - P.ux) / P.fx : (comp == 1 ? (T(qy) - P.uy) / P.fy : T(1));
-    return k == 0 ? P.ws * (T(4) * a) : -(P.ws * a);
+    const T a = comp == 0 ? sfsAx(P, qx) : (comp == 1 ? sfsAy(P, qy) : T(1));
+    return sfsCoefFromA(P, a, k);
 }
 template <class T> SFS_HD T sfsFS(const SfsData<T>& P, int x, int y, int comp) {   // value of r_s,comp centred at (x, y)
     const long c = (long)y * P.W + x;

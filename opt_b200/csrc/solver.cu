@@ -84,7 +84,7 @@ template <class T, bool LM, bool USEPRE>
 __global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, WindowRanges win, ReduceWorkspace ws, OwnedRanges own, int rzOld, int rzNew,
                                                      T* __restrict__ delta, const T* __restrict__ p, T* __restrict__ r,
                                                      const T* __restrict__ Ap, const T* __restrict__ pre,
-                                                     const T* __restrict__ b, T* __restrict__ z, ZPush<T> push) {
+                                                     const T* __restrict__ b, T* __restrict__ z, ZPush<T> push, int zetaIter, T zetaTol) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
     pdlTrigger(); pdlWait();
     if (LM && ws.scalars[kFlags] != 0.0) return;
@@ -142,8 +142,20 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2(long nVec, WindowRanges win
             }
         }
     }
-    gridReduceTo<kBlock>((double)accRz, ws, rzNew, push.n ? push.peerFlag : nullptr);
-    if (LM) gridReduceTo<kBlock>((double)accQ, ws, kQ);
+    if (!LM) { gridReduceTo<kBlock>((double)accRz, ws, rzNew, push.n ? push.peerFlag : nullptr); return; }
+    // LM: r.z and q in one arrival round; on a single GPU the CTA that finishes the reduction also takes the zeta early-out decision
+    // (:1093-1102) -- the reduced q is in its hands -- instead of a one-thread kernel per PCG step.  The flag records the breaking
+    // iteration (1 + l): PCGStep3 of THAT iteration still runs (the reference updates p before it tests zeta), everything later is a no-op.
+    __shared__ double s_q;
+    double q1 = 0.0;
+    const bool last = gridReduceTo2<kBlock>((double)accRz, (double)accQ, ws, rzNew, kQ, push.n ? push.peerFlag : nullptr, nullptr, &s_q);
+    if (last && zetaIter >= 0 && threadIdx.x == 0) {
+        q1 = s_q;
+        const T Q1 = (T)q1, Q0 = (T)ws.scalars[kQPrev];
+        const T zeta = T(zetaIter + 1) * (Q1 - Q0) / Q1;
+        if (zeta < zetaTol) ws.scalars[kFlags] = 1.0 + zetaIter;
+        ws.scalars[kQPrev] = (double)Q1;
+    }
 }
 
 // PCGStep2_1stHalf (:491-503): delta += alpha p
@@ -197,10 +209,10 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep2SecondHalf(long nVec, Window
 // :537-550.  beta = rz_new / rz_old (guarded), p = z + beta p
 template <class T, bool LM>
 __global__ void __launch_bounds__(kBlock) k_pcgStep3(long nVec, WindowRanges win, ReduceWorkspace ws, int rzNew, int rzOld, const T* __restrict__ z, T* __restrict__ p,
-                                                     OwnedRanges own, HaloWait hw) {
+                                                     OwnedRanges own, HaloWait hw, int lIter) {
     using V = typename VecOf<T>::type; constexpr int N = VecOf<T>::N;
     pdlTrigger(); pdlWait();
-    if (LM && ws.scalars[kFlags] != 0.0) return;
+    if (LM) { const double f = ws.scalars[kFlags]; if (f != 0.0 && f != 1.0 + lIter) return; }   // a flag raised by THIS iteration's zeta test still lets its Step3 run
     double drn, dro; loadScalars2(ws, rzNew, rzOld, drn, dro);
     const T rn = (T)drn, ro = (T)dro;
     T beta = T(0);
@@ -625,23 +637,24 @@ struct Plan : PlanBase {
     }
 
     // ---- one PCG iteration, launched on `stream` (captured into the loop graph or issued directly)
-    void launchStep2(int rzOld, int rzNew, T* p, bool pushZ = false) {
+    void launchStep2(int rzOld, int rzNew, T* p, bool pushZ = false, int zetaIter = -1) {
         const ZPush<T> zp = pushZ ? zPush : ZPush<T>{};
+        const T zetaTol = (T)sp.q_tolerance;
         long nVec = n / VecOf<T>::N;
         if (lm) {
-            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStep2, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp);
-            else k_pcgStep2<T, true, false><<<gridStep2, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp);
+            if (E->usePreconditioner) k_pcgStep2<T, true, true><<<gridStep2, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp, zetaIter, zetaTol);
+            else k_pcgStep2<T, true, false><<<gridStep2, kBlock, 0, stream>>>(nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp, zetaIter, zetaTol);
         } else {
-            if (E->usePreconditioner) launchPdl(k_pcgStep2<T, false, true>, gridStep2, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp);
-            else launchPdl(k_pcgStep2<T, false, false>, gridStep2, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp);
+            if (E->usePreconditioner) launchPdl(k_pcgStep2<T, false, true>, gridStep2, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp, zetaIter, zetaTol);
+            else launchPdl(k_pcgStep2<T, false, false>, gridStep2, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, ownVec, rzOld, rzNew, delta, p, r, Ap, pre, b, z, zp, zetaIter, zetaTol);
         }
         ++launches;
     }
-    void launchStep3(int rzNew, int rzOld, T* p, bool waitZ = false) {
+    void launchStep3(int rzNew, int rzOld, T* p, bool waitZ = false, int lIter = 0) {
         const HaloWait hw = waitZ ? zWait : HaloWait{};
         long nVec = n / VecOf<T>::N;
-        if (lm) k_pcgStep3<T, true><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, rzNew, rzOld, z, p, ownVec, hw);
-        else launchPdl(k_pcgStep3<T, false>, gridStream, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, rzNew, rzOld, (const T*)z, p, ownVec, hw);
+        if (lm) k_pcgStep3<T, true><<<gridStream, kBlock, 0, stream>>>(nVecWin(), winVec, ws, rzNew, rzOld, z, p, ownVec, hw, lIter);
+        else launchPdl(k_pcgStep3<T, false>, gridStream, kBlock, 0, stream, usePdl, nVecWin(), winVec, ws, rzNew, rzOld, (const T*)z, p, ownVec, hw, lIter);
         ++launches;
     }
     // Emits iterations [0, L).  rz slot convention: iteration l reads rz[l&1] as "old", writes rz[(l+1)&1].
@@ -675,15 +688,16 @@ struct Plan : PlanBase {
             }
             const bool step3Fused = fuse && !lm && l + 1 < L;   // Step3 of this iteration runs inside the next Step1
             const bool zInStep2 = world > 1 && zPush.n > 0 && !reset && !step3Fused;   // Step2 pushes z's boundary entries, the standalone Step3 waits for them
+            const bool zetaInStep2 = lm && world == 1 && !reset;   // single GPU: PCGStep2's finishing CTA takes the zeta decision
             if (!reset) {
                 tBeginFine("PCGStep2");
-                launchStep2(rzOld, rzNew, cur, zInStep2);
+                launchStep2(rzOld, rzNew, cur, zInStep2, zetaInStep2 ? l : -1);
                 tEndFine();
             }
             if (!zInStep2 && !(kernelHalo && step3Fused)) exchangeHalo(haloZ, z);   // neighbours need z on my boundary rows for their p = z + beta p
             if (step3Fused) pending = true;   // defer Step3 into the next Step1
-            else { tBeginFine("PCGStep3"); launchStep3(rzNew, rzOld, cur, zInStep2); tEndFine(); }
-            if (lm) { k_lmZeta<T><<<1, 1, 0, stream>>>(ws, l, (T)sp.q_tolerance); ++launches; }
+            else { tBeginFine("PCGStep3"); launchStep3(rzNew, rzOld, cur, zInStep2, l); tEndFine(); }
+            if (lm && !zetaInStep2) { k_lmZeta<T><<<1, 1, 0, stream>>>(ws, l, (T)sp.q_tolerance); ++launches; }
         }
         pFinal = cur;
     }

@@ -31,7 +31,7 @@
 
 namespace optb {
 
-template <class T> struct RnaPack { T sa, ca, sb, cb, sg, cg, ux, uy, uz, g, nx, ny, nz, s, tgt, pad; };   // s = n.(O - C); tgt = m_v
+template <class T> struct alignas(16) RnaPack { T sa, ca, sb, cb, sg, cg, ux, uy, uz, g, nx, ny, nz, s, tgt, pad; };   // 16-byte aligned: the gathers load it with 128-bit loads (they are bound by L1 requests, not bytes)   // s = n.(O - C); tgt = m_v
 template <class T> struct RnaV3 { T x, y, z; };
 
 template <class T>

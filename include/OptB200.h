@@ -48,7 +48,7 @@ float OptB200_PcgLoopMsLastStep(Opt_Plan* plan);
 int OptB200_ProfileKernels(Opt_Plan* plan, void** problemparams, int reps, int maxOut, const char** names, float* avgMs);
 /* ---- multi-GPU slab decomposition (one process per GPU) --------------------------
  * Each rank plans its LOCAL domain = owned slab + 1 halo row towards every neighbour and binds local
- * buffers.  OptB200_PlanCommHandles writes 3 CUDA IPC handles (192 bytes: scalar mailbox, z, p); the host
+ * buffers.  OptB200_PlanCommHandles writes 4 CUDA IPC handles (256 bytes: scalar mailbox block, z, p, delta) and returns the byte count; the host
  * all-gathers them (any transport, e.g. torch.distributed) and passes the rank-ordered concatenation to
  * OptB200_PlanConnect together with this rank's owned local rows [ownedBegin, ownedEnd) and the LOCAL row
  * counts of the upper / lower neighbour (0 = none).  Afterwards Opt_ProblemInit/Step must be called

@@ -514,6 +514,83 @@ __device__ __forceinline__ double gridAllReduceLLMulti(double v, unsigned long l
     return out;
 }
 
+// Two values in ONE round, no data release: the all-reduce of the single-reduction PCG loop kernel (gamma = r.z and delta = w.z travel
+// together; tile edges move as LL data words, so the reduction carries no ordering duty and contains no fence at all).
+// `words` = [2 parities][kMaxLLCtas + 1][4]: per CTA slot the lo/hi words of both values, slot kMaxLLCtas = the result (single GPU);
+// MULTI: the rank partials go to mailbox slots `slot` and `slot + 1` of every rank (4 * world words = one warp at world = 8).
+template <int NT, bool MULTI>
+__device__ __forceinline__ void gridAllReduce2LL(double v0, double v1, unsigned long long* words, unsigned long long* arrivals, unsigned long long k,
+                                                 const CommView& comm, int slot, double& o0, double& o1) {
+    static_assert(NT >= kMaxLLCtas && NT % 32 == 0 && NT / 32 <= 32, "one polling thread per CTA slot");
+    static_assert(kMaxRanks == 8, "lane mapping below assumes at most 32 mailbox words for the two values");
+    __shared__ double s_w[2][NT / 32];
+    __shared__ double s_p[2][kMaxLLCtas];
+    __shared__ double s_v[2];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned long long seq = k & 0xffffffffull;
+    unsigned long long* row = words + (size_t)(k & 1ull) * (4 * (kMaxLLCtas + 1));
+    auto word = [&](double a, double b, int l) -> unsigned long long {   // word l of the pair: 0,1 = lo/hi of a; 2,3 = lo/hi of b
+        const unsigned long long bits = (unsigned long long)__double_as_longlong((l & 2) ? b : a);
+        return (((l & 1) ? (bits >> 32) : (bits & 0xffffffffull)) << 32) | seq;
+    };
+    auto unword = [](unsigned long long lo, unsigned long long hi) -> double { return __longlong_as_double((long long)((lo >> 32) | ((hi >> 32) << 32))); };
+    v0 = warpSum(v0); v1 = warpSum(v1);
+    if (lane == 0) { s_w[0][wid] = v0; s_w[1][wid] = v1; }
+    __syncthreads();
+    if (wid == 0) {
+        double t0 = lane < NT / 32 ? s_w[0][lane] : 0.0, t1 = lane < NT / 32 ? s_w[1][lane] : 0.0;
+        t0 = warpSum(t0); t1 = warpSum(t1);
+        if (lane < 4) stVolatileU64(row + 4 * blockIdx.x + lane, word(t0, t1, lane));
+        if (lane == 0) { const unsigned long long prev = atomicAdd(arrivals, 1ull); s_last = (prev + 1ull == (unsigned long long)gridDim.x * k); }
+    }
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < gridDim.x) {
+            const unsigned long long* src = row + 4 * threadIdx.x;
+            unsigned long long w[4], spins = 0; bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { w[i] = ldVolatileU64(src + i); ok = ok && ((w[i] & 0xffffffffull) == seq); }
+                if (++spins > (1ull << 24)) __trap();
+            } while (!ok);
+            s_p[0][threadIdx.x] = unword(w[0], w[1]); s_p[1][threadIdx.x] = unword(w[2], w[3]);
+        }
+        __syncthreads();
+        if (wid == 0) {
+            double u0 = 0.0, u1 = 0.0;
+            for (unsigned i = lane; i < gridDim.x; i += 32) { u0 += s_p[0][i]; u1 += s_p[1][i]; }   // fixed order
+            u0 = warpSum(u0); u1 = warpSum(u1);
+            if (MULTI) { if (lane < 4 * comm.world) stVolatileU64(comm.peerWords[lane >> 2] + mailboxWord(slot + ((lane >> 1) & 1), k, comm.rank) + (lane & 1), word(u0, u1, lane & 3)); }
+            else if (lane < 4) stVolatileU64(row + 4 * kMaxLLCtas + lane, word(u0, u1, lane));
+        }
+    }
+    if (wid == 0) {
+        unsigned long long w = 0ull;
+        const int nWords = MULTI ? 4 * comm.world : 4;
+        if (lane < nWords) {
+            const unsigned long long* src = MULTI ? comm.peerWords[comm.rank] + mailboxWord(slot + ((lane >> 1) & 1), k, lane >> 2) + (lane & 1) : row + 4 * kMaxLLCtas + lane;
+            unsigned long long spins = 0;
+            do { w = ldVolatileU64(src); if (++spins > (1ull << 26)) __trap(); } while ((w & 0xffffffffull) != seq);   // a lost CTA / rank is a bug: fail, do not hang
+        }
+        __syncwarp();
+        const unsigned payload = (unsigned)(w >> 32);
+        double sum0 = 0.0, sum1 = 0.0;
+        const int senders = MULTI ? comm.world : 1;
+        for (int r = 0; r < senders; ++r) {   // fixed rank order => bitwise identical on every rank
+            const unsigned a = __shfl_sync(0xffffffffu, payload, 4 * r), b = __shfl_sync(0xffffffffu, payload, 4 * r + 1);
+            const unsigned c = __shfl_sync(0xffffffffu, payload, 4 * r + 2), d = __shfl_sync(0xffffffffu, payload, 4 * r + 3);
+            sum0 += __longlong_as_double((long long)((unsigned long long)a | ((unsigned long long)b << 32)));
+            sum1 += __longlong_as_double((long long)((unsigned long long)c | ((unsigned long long)d << 32)));
+        }
+        if (lane == 0) { s_v[0] = sum0; s_v[1] = sum1; }
+    }
+    __syncthreads();
+    o0 = s_v[0]; o1 = s_v[1];
+    __syncthreads();
+}
+
 // Self-validating data words for peer memory (NCCL-LL style): an opt_float travels as one (float) or two (double) 8-byte words, each
 // payload32 | sequence32, written with a single 8-byte store.  The reader polls the word itself until it carries the expected
 // sequence -- no flag, no fence on either side; the sequence only grows, so a stale word is never mistaken for a new one.

@@ -896,6 +896,196 @@ __global__ void __launch_bounds__(1024, 1) k_iwPcgLoopTile(IWData<T> D, ReduceWo
     if (!MULTI && L > 0 && blockIdx.x == 0 && tid == 0) { ws.scalars[kPAp] = dPAp; ws.scalars[L & 1] = dRz; ws.scalars[(L + 1) & 1] = dRzPrev; }
 }
 
+// ------------------------------------------------------------------------------------ whole PCG loop, state on chip, ONE reduction per step
+// The two dependent all-reduces of a PCG step (p.Ap before alpha, r.z before beta) are what the collective loop kernel above spends its
+// time in: 19.6 us per step on 8 GPUs, ~4 us of it arithmetic.  This kernel runs the SAME Jacobi-PCG in the Chronopoulos-Gear
+// arrangement (the "single allreduce of the two PCG scalars" of BASELINE.json's north star): the matvec is applied to z instead of p,
+//     w = A z,  gamma = r.z,  delta = w.z            <- ONE all-reduce of two scalars per step
+//     beta = gamma / gamma_old,   alpha = gamma / (delta - beta gamma / alpha_old)      (= r.z / p.Ap, since p.Ap = delta - beta gamma / alpha_old)
+//     p = z + beta p,  s = w + beta s (= A p),  delta_x += alpha p,  r -= alpha s,  z = pre r
+// In exact arithmetic these are the reference's iterates (solverGPUGaussNewton.t:421-550, same guards: a non-positive denominator gives
+// alpha = 0, a non-positive gamma_old gives beta = 0); in floating point A p is carried by a recurrence instead of being applied, so the
+// iterates differ in the last bits (tests: state after k steps vs the oracle to the usual 3e-4; a 400-step fp32 prototype against fp64
+// loses nothing over the two-reduction form).  Tile state: z (with ring), geometry (with ring), r, pre, flags in shared memory;
+// p, s, delta_x, w of a thread's pixels in registers (512 threads x up to 8 pixels).  Tile edges of z go to the neighbouring tiles as LL
+// data words (edgeLL: one row of words per tile side; llStore / llLoad), and to a neighbouring RANK through the peer scratch rows as in
+// k_iwPcgLoopTile -- pure dataflow: the kernel contains no fence and no barrier besides the all-reduce itself.
+template <class T, int KMAX, bool MULTI>
+__global__ void __launch_bounds__(512, 1) k_iwCgLoopTile(IWData<T> D, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long* arrivals, unsigned long long* edgeLL,
+                                                         unsigned long long k0, int L, int tw, int th, int tilesAcross, int tilesDown, IWTileMulti<T> M,
+                                                         T* delta, T* r, T* z, T* p, T* Ap, const T* __restrict__ pre) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    constexpr int NT = 512, WN = LLWords<T>::N;
+    const int W = D.W, H = D.H, tid = threadIdx.x;
+    const int tcol = blockIdx.x % tilesAcross, trow = blockIdx.x / tilesAcross;
+    const int tx0 = tcol * tw, ty0 = D.y0 + trow * th;
+    const int twE = min(tw, W - tx0), thE = min(th, D.y1 - ty0);
+    const int pw = tw + 2;
+    const int nRing = (th + 2) * pw, nCap = tw * th;
+    T* sZx = reinterpret_cast<T*>(smemRaw); T* sZy = sZx + nRing; T* sZa = sZy + nRing;
+    T* sGc = sZa + nRing; T* sGs = sGc + nRing; T* sGx = sGs + nRing; T* sGy = sGx + nRing;
+    T* sRx = sGy + nRing; T* sRy = sRx + nCap; T* sRa = sRy + nCap; T* sQo = sRa + nCap; T* sQa = sQo + nCap;
+    unsigned char* sF = reinterpret_cast<unsigned char*>(sQa + nCap);
+    // LL edge rows of a tile: [top tw][bottom tw][left th][right th], 3 scalars per cell
+    const size_t edgeStride = (size_t)2 * (tw + th) * 3 * WN;
+    auto edgeOf = [&](int tile, int side) -> unsigned long long* {
+        return edgeLL + (size_t)tile * edgeStride + (size_t)(side == 0 ? 0 : (side == 1 ? tw : (side == 2 ? 2 * tw : 2 * tw + th))) * 3 * WN;
+    };
+    // prologue: z0 = the initial direction p = pre r (PCGInit1), ring cells from the p vector (its halo rows were exchanged by the caller)
+    const Vec2<T>* pO = reinterpret_cast<const Vec2<T>*>(p);
+    for (int c = tid; c < (th + 2) * pw; c += NT) {
+        const int lr = c / pw, lc = c - lr * pw, gx = tx0 - 1 + lc, gy = ty0 - 1 + lr;
+        T zx = T(0), zy = T(0), za = T(0); Vec4<T> g{ T(0), T(0), T(0), T(0) };
+        if (lr <= thE + 1 && lc <= twE + 1 && gx >= 0 && gx < W && gy >= 0 && gy < H) { const long j = (long)gy * W + gx; const Vec2<T> po = pO[j]; zx = po.x; zy = po.y; za = p[D.offA + j]; g = D.geom[j]; }
+        sZx[c] = zx; sZy[c] = zy; sZa[c] = za; sGc[c] = g.x; sGs[c] = g.y; sGx[c] = g.z; sGy[c] = g.w;
+    }
+    T px[KMAX], py[KMAX], pa[KMAX], sx[KMAX], sy[KMAX], sa[KMAX], dx[KMAX], dy[KMAX], da[KMAX], wx[KMAX], wy[KMAX], wa[KMAX];
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) {
+        px[q] = py[q] = pa[q] = sx[q] = sy[q] = sa[q] = dx[q] = dy[q] = da[q] = wx[q] = wy[q] = wa[q] = T(0);
+        const int c = tid + q * NT;
+        if (c < nCap) {
+            const int ly = c / tw, lx = c - ly * tw;
+            sF[c] = 0; sRx[c] = sRy[c] = sRa[c] = sQo[c] = sQa[c] = T(0);
+            if (lx < twE && ly < thE) {
+                const long i = (long)(ty0 + ly) * W + tx0 + lx;
+                const Vec2<T> ro = reinterpret_cast<const Vec2<T>*>(r)[i]; sRx[c] = ro.x; sRy[c] = ro.y; sRa[c] = r[D.offA + i];
+                sQo[c] = reinterpret_cast<const Vec2<T>*>(pre)[i].x; sQa[c] = pre[D.offA + i];
+                sF[c] = D.flags[i];
+                const Vec2<T> dO = reinterpret_cast<const Vec2<T>*>(delta)[i]; dx[q] = dO.x; dy[q] = dO.y; da[q] = delta[D.offA + i];
+            }
+        }
+    }
+    __syncthreads();
+    const T w2 = D.w * D.w, wf2 = D.wf * D.wf;
+    // w = A z for the thread's pixels, and the two partial dot products
+    auto matvec = [&](T& accG, T& accD) {
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q) {
+            const int c = tid + q * NT;
+            T ox = T(0), oy = T(0), oa = T(0);
+            if (c < nCap) {
+                const int ly = c / tw, lx = c - ly * tw, cc = (ly + 1) * pw + lx + 1;
+                const unsigned fl = sF[c];
+                if (fl & 32u) {
+                    const T zix = sZx[cc], ziy = sZy[cc], zai = sZa[cc];
+                    const T gc = sGc[cc], gs = sGs[cc], gux = sGx[cc], guy = sGy[cc];
+                    T ax = T(0), ay = T(0), aa = T(0);
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) {
+                        if (fl & (1u << nb)) {
+                            const int jj = cc + (nb == 0 ? 1 : (nb == 1 ? -1 : (nb == 2 ? pw : -pw)));
+                            const T jc = sGc[jj], js = sGs[jj];
+                            const T ddx = gux - sGx[jj], ddy = guy - sGy[jj];
+                            const T eix = -gs * ddx - gc * ddy, eiy = gc * ddx - gs * ddy;
+                            const T ejx = -js * ddx - jc * ddy, ejy = jc * ddx - js * ddy;
+                            const T zaj = sZa[jj];
+                            const T qx = zix - sZx[jj], qy = ziy - sZy[jj];
+                            ax += T(2) * qx - eix * zai - ejx * zaj;
+                            ay += T(2) * qy - eiy * zai - ejy * zaj;
+                            aa += (eix * eix + eiy * eiy) * zai - (eix * qx + eiy * qy);
+                        }
+                    }
+                    ox = w2 * ax; oy = w2 * ay; oa = w2 * aa;
+                    if (fl & 16u) { ox += wf2 * zix; oy += wf2 * ziy; }
+                    accD += zix * ox + ziy * oy + zai * oa;
+                    accG += sRx[c] * zix; accG += sRy[c] * ziy; accG += sRa[c] * zai;
+                }
+            }
+            wx[q] = ox; wy[q] = oy; wa[q] = oa;
+        }
+    };
+    unsigned long long k = k0;
+    T accG = T(0), accD = T(0);
+    matvec(accG, accD);
+    double dG, dD;
+    gridAllReduce2LL<NT, MULTI>((double)accG, (double)accD, llWords, arrivals, ++k, ws.comm, kLoopMailboxSlot, dG, dD);
+    T gam = (T)dG, alpha = T(0), beta = T(0);
+    { const T den = (T)dD; if (den > T(0)) alpha = gam / den; }
+    for (int it = 0; it < L; ++it) {
+        const bool more = it + 1 < L;
+        const unsigned seq = (unsigned)(k + 1ull);     // = the k of the all-reduce that follows: tags z of iteration it + 1
+        // ---------------- updates (PCGStep3 of the previous step, PCGStep2 of this one), then z of the next step goes to shared memory and to the neighbours
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q) {
+            const int c = tid + q * NT;
+            if (c < nCap) {
+                const int ly = c / tw, lx = c - ly * tw;
+                if (lx < twE && ly < thE) {
+                    const int cc = (ly + 1) * pw + lx + 1;
+                    px[q] = sZx[cc] + beta * px[q]; py[q] = sZy[cc] + beta * py[q]; pa[q] = sZa[cc] + beta * pa[q];
+                    sx[q] = wx[q] + beta * sx[q]; sy[q] = wy[q] + beta * sy[q]; sa[q] = wa[q] + beta * sa[q];
+                    dx[q] = dx[q] + alpha * px[q]; dy[q] = dy[q] + alpha * py[q]; da[q] = da[q] + alpha * pa[q];
+                    const T rx = sRx[c] - alpha * sx[q], ry = sRy[c] - alpha * sy[q], ra = sRa[c] - alpha * sa[q];
+                    sRx[c] = rx; sRy[c] = ry; sRa[c] = ra;
+                    const T qo = sQo[c];
+                    const T zx = qo * rx, zy = qo * ry, za = sQa[c] * ra;
+                    sZx[cc] = zx; sZy[cc] = zy; sZa[cc] = za;
+                    if (more) {
+                        if (ly == 0) {
+                            if (trow > 0) { unsigned long long* e = edgeOf(blockIdx.x, 0) + (size_t)lx * 3 * WN; llStore(e, zx, seq); llStore(e + WN, zy, seq); llStore(e + 2 * WN, za, seq); }
+                            else if (MULTI && M.toUp) { unsigned long long* e = M.toUp + (size_t)(tx0 + lx) * 3 * WN; llStore(e, zx, seq); llStore(e + WN, zy, seq); llStore(e + 2 * WN, za, seq); }
+                        }
+                        if (ly == thE - 1) {
+                            if (trow + 1 < tilesDown) { unsigned long long* e = edgeOf(blockIdx.x, 1) + (size_t)lx * 3 * WN; llStore(e, zx, seq); llStore(e + WN, zy, seq); llStore(e + 2 * WN, za, seq); }
+                            else if (MULTI && M.toDn) { unsigned long long* e = M.toDn + (size_t)(tx0 + lx) * 3 * WN; llStore(e, zx, seq); llStore(e + WN, zy, seq); llStore(e + 2 * WN, za, seq); }
+                        }
+                        if (lx == 0 && tcol > 0) { unsigned long long* e = edgeOf(blockIdx.x, 2) + (size_t)ly * 3 * WN; llStore(e, zx, seq); llStore(e + WN, zy, seq); llStore(e + 2 * WN, za, seq); }
+                        if (lx == twE - 1 && tcol + 1 < tilesAcross) { unsigned long long* e = edgeOf(blockIdx.x, 3) + (size_t)ly * 3 * WN; llStore(e, zx, seq); llStore(e + WN, zy, seq); llStore(e + 2 * WN, za, seq); }
+                    }
+                }
+            }
+        }
+        if (!more) break;
+        // ---------------- ring cells: the neighbours' z of the same step (LL words: the poll IS the synchronisation)
+        for (int c = tid; c < 2 * (twE + thE); c += NT) {
+            int lr, lc; const unsigned long long* e = nullptr;
+            if (c < twE) {                     // row above
+                lr = 0; lc = c + 1;
+                if (trow > 0) e = edgeOf(blockIdx.x - tilesAcross, 1) + (size_t)c * 3 * WN;
+                else if (MULTI && M.fromUp) e = M.fromUp + (size_t)(tx0 + c) * 3 * WN;
+            } else if (c < 2 * twE) {          // row below
+                const int i = c - twE; lr = thE + 1; lc = i + 1;
+                if (trow + 1 < tilesDown) e = edgeOf(blockIdx.x + tilesAcross, 0) + (size_t)i * 3 * WN;
+                else if (MULTI && M.fromDn) e = M.fromDn + (size_t)(tx0 + i) * 3 * WN;
+            } else if (c < 2 * twE + thE) {    // column to the left
+                const int i = c - 2 * twE; lr = i + 1; lc = 0;
+                if (tcol > 0) e = edgeOf(blockIdx.x - 1, 3) + (size_t)i * 3 * WN;
+            } else {                           // column to the right
+                const int i = c - 2 * twE - thE; lr = i + 1; lc = twE + 1;
+                if (tcol + 1 < tilesAcross) e = edgeOf(blockIdx.x + 1, 2) + (size_t)i * 3 * WN;
+            }
+            if (e) { const int cc = lr * pw + lc; T a, b, cval; llLoad(e, seq, a); llLoad(e + WN, seq, b); llLoad(e + 2 * WN, seq, cval); sZx[cc] = a; sZy[cc] = b; sZa[cc] = cval; }
+        }
+        __syncthreads();
+        // ---------------- w = A z, gamma, delta: the step's only all-reduce
+        accG = T(0); accD = T(0);
+        matvec(accG, accD);
+        gridAllReduce2LL<NT, MULTI>((double)accG, (double)accD, llWords, arrivals, ++k, ws.comm, kLoopMailboxSlot, dG, dD);
+        const T gNew = (T)dG, dNew = (T)dD;
+        beta = T(0); if (gam > T(0)) beta = gNew / gam;                                  // :541-546
+        T den = dNew; if (alpha != T(0)) den = dNew - beta * gNew / alpha;               // = p.Ap of the coming step
+        alpha = T(0); if (den > T(0)) alpha = gNew / den;                                // :456-461
+        gam = gNew;
+    }
+    // the state goes back to the plan's vectors: delta, r, z; p and Ap (= s) as they were used by the last update
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q) {
+        const int c = tid + q * NT;
+        if (c < nCap) {
+            const int ly = c / tw, lx = c - ly * tw;
+            if (lx < twE && ly < thE) {
+                const int cc = (ly + 1) * pw + lx + 1; const long i = (long)(ty0 + ly) * W + tx0 + lx;
+                reinterpret_cast<Vec2<T>*>(p)[i] = Vec2<T>{ px[q], py[q] }; p[D.offA + i] = pa[q];
+                reinterpret_cast<Vec2<T>*>(delta)[i] = Vec2<T>{ dx[q], dy[q] }; delta[D.offA + i] = da[q];
+                reinterpret_cast<Vec2<T>*>(r)[i] = Vec2<T>{ sRx[c], sRy[c] }; r[D.offA + i] = sRa[c];
+                reinterpret_cast<Vec2<T>*>(z)[i] = Vec2<T>{ sZx[cc], sZy[cc] }; z[D.offA + i] = sZa[cc];
+                reinterpret_cast<Vec2<T>*>(Ap)[i] = Vec2<T>{ sx[q], sy[q] }; Ap[D.offA + i] = sa[q];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ computeCost
 // solverGPUGaussNewton.t:580-592 + o.t:2375-2385: 1/2 sum r^2 over residuals centred at active pixels.
 // MODEL: computeModelCost (:666-678, o.t:2174-2199): 1/2 sum (r + J delta)^2.
@@ -1060,7 +1250,7 @@ struct ImageWarpingOps : EnergyOps<T> {
         gridCost = gridOf((const void*)k_iwCost<T, false>);
         setupTma(sms);
     }
-    ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); if (loopSync) cudaFree(loopSync); if (llWords) cudaFree(llWords); if (tileWords) cudaFree(tileWords); }
+    ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); if (loopSync) cudaFree(loopSync); if (llWords) cudaFree(llWords); if (tileWords) cudaFree(tileWords); if (cgWords) cudaFree(cgWords); if (edgeLL) cudaFree(edgeLL); }
     const char* name() const override { return "image_warping"; }
     unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(D); }
     int upperRows = 0, lowerRows = 0;
@@ -1153,6 +1343,50 @@ struct ImageWarpingOps : EnergyOps<T> {
         }
         return true;
     }
+    // single-reduction (Chronopoulos-Gear) form of the tile loop: default for the multi-rank collective kernel (OPTB_CG_LOOP=0: the
+    // two-reduction kernel), opt-in on a single GPU (OPTB_CG_LOOP=1) where the reference's exact recurrences stay the default
+    unsigned long long* cgWords = nullptr; unsigned long long* edgeLL = nullptr; unsigned long long cgSeq = 0; size_t edgeWords = 0; const void* cgChecked = nullptr;
+    bool useCg(bool multi) const { const char* e = getenv("OPTB_CG_LOOP"); return e ? atoi(e) != 0 : multi; }
+    int cgKmax() const { const long need = ((long)tileW * tileH + 511) / 512; return need <= 4 ? 4 : (need <= 7 ? 7 : 8); }
+    template <int KMAX, bool MULTI> const void* cgFn() const { return (const void*)k_iwCgLoopTile<T, KMAX, MULTI>; }
+    const void* cgFnFor(bool multi) const {
+        const int km = cgKmax();
+        if (multi) return km == 4 ? cgFn<4, true>() : (km == 7 ? cgFn<7, true>() : cgFn<8, true>());
+        return km == 4 ? cgFn<4, false>() : (km == 7 ? cgFn<7, false>() : cgFn<8, false>());
+    }
+    bool cgPrepare(const void* fn) {   // attributes + co-residency, once per kernel variant
+        if (cgChecked == fn) return true;
+        const size_t smem = tileSmemFor(tileW, tileH, false);
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return false; }
+        int occ = 0, dev = 0, sms = 148; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 512, smem);
+        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if ((long)occ * sms < tileGrid) return false;
+        cgChecked = fn;
+        return true;
+    }
+    bool launchCg(const LaunchCtx& c, int L, bool multi, const IWTileMulti<T>& M, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {
+        const void* fn = cgFnFor(multi);
+        if (!cgPrepare(fn)) return false;
+        constexpr size_t llCount = 8 * (kMaxLLCtas + 1) + 1;   // two parities of (slots + result) x 4 words, then the arrival counter
+        const size_t needEdge = (size_t)tileGrid * 2 * (tileW + tileH) * 3 * LLWords<T>::N;
+        if (!cgWords || needEdge != edgeWords) {   // (re)allocated zeroed: sequence numbers restart with the buffers
+            if (cgWords) cudaFree(cgWords); if (edgeLL) cudaFree(edgeLL);
+            OPT_CUDA_CHECK(cudaMalloc((void**)&cgWords, sizeof(unsigned long long) * llCount)); OPT_CUDA_CHECK(cudaMemset(cgWords, 0, sizeof(unsigned long long) * llCount));
+            OPT_CUDA_CHECK(cudaMalloc((void**)&edgeLL, sizeof(unsigned long long) * std::max<size_t>(needEdge, 1))); OPT_CUDA_CHECK(cudaMemset(edgeLL, 0, sizeof(unsigned long long) * std::max<size_t>(needEdge, 1)));
+            edgeWords = needEdge; cgSeq = 0;
+        }
+        unsigned long long* arrivals = cgWords + 8 * (kMaxLLCtas + 1);
+        unsigned long long k0 = cgSeq; cgSeq += (unsigned long long)L;   // exactly L all-reduces per launch (the arrival counter counts gridDim per reduction)
+        ReduceWorkspace ws = c.ws;
+        IWTileMulti<T> Mv = M;
+        const int tilesDown = tileGrid / tileAcross;
+        const size_t smem = tileSmemFor(tileW, tileH, false);
+        void* args[] = { (void*)&D, (void*)&ws, (void*)&cgWords, (void*)&arrivals, (void*)&edgeLL, (void*)&k0, (void*)&L, (void*)&tileW, (void*)&tileH, (void*)&tileAcross, (void*)&tilesDown,
+                         (void*)&Mv, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre };
+        const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3((unsigned)tileGrid), dim3(512), args, smem, c.stream);
+        if (le != cudaSuccess) { if (multi) OPT_CUDA_CHECK(le); cudaGetLastError(); cgSeq = k0; return false; }
+        return true;
+    }
     size_t tileSmemFor(int a, int b, bool multi) const {
         const size_t nRing = (size_t)(b + 2) * (a + 2), nCap = (size_t)a * b;
         size_t bytes = ((nRing * 7 + nCap * 5) * sizeof(T) + nCap + 15) / 16 * 16;
@@ -1170,7 +1404,7 @@ struct ImageWarpingOps : EnergyOps<T> {
         int a = 0, b = 0;
         if (const char* spec = getenv("OPTB_RESIDENT_TILE")) { if (sscanf(spec, "%dx%d", &a, &b) != 2 || a < 1 || b < 1 || !fits(a, b)) return false; }
         else {
-            if (!multi) return false;                       // single GPU: the row-slab kernel is the default, tiles only on request
+            if (!multi && !useCg(false)) return false;      // single GPU: the row-slab kernel is the default, tiles only on request
             bool found = false;
             const int widths[6] = { D.W, 1024, 512, 256, 128, 64 };
             for (int aw : widths) {   // widest tiles first: fewest ring cells per pixel for a given area
@@ -1191,6 +1425,7 @@ struct ImageWarpingOps : EnergyOps<T> {
         int dev = 0, coop = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (!coop || !chooseTile(true)) { tileW = -1; tileMulti = true; return false; }
+        if (useCg(true)) { if (!cgPrepare(cgFnFor(true))) { tileW = -1; return false; } return true; }
         const void* fn = tileK <= 2 ? (const void*)k_iwPcgLoopTile<T, 2, true> : (const void*)k_iwPcgLoopTile<T, 4, true>;
         int occ = 0;
         if (tileK > 4 || cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tileSmem) != cudaSuccess) { cudaGetLastError(); tileW = -1; return false; }
@@ -1211,8 +1446,10 @@ struct ImageWarpingOps : EnergyOps<T> {
             M.toUp = haloZ->peerVec[0] ? (unsigned long long*)scratchUp + rowWords : nullptr;    // I am my upper neighbour's lower neighbour
             M.toDn = haloZ->peerVec[1] ? (unsigned long long*)scratchDn : nullptr;
             if ((haloZ->peerVec[0] && !scratchUp) || (haloZ->peerVec[1] && !scratchDn) || !mine) return false;
+            if (useCg(true)) return launchCg(c, L, true, M, delta, r, z, p, Ap, pre);
             return tileK <= 2 ? launchTileK<2, true>(c, L, M, delta, r, z, p, Ap, pre) : launchTileK<4, true>(c, L, M, delta, r, z, p, Ap, pre);
         }
+        if (useCg(false)) return launchCg(c, L, false, M, delta, r, z, p, Ap, pre);
         return tileK <= 2 ? launchTileK<2, false>(c, L, M, delta, r, z, p, Ap, pre) : launchTileK<4, false>(c, L, M, delta, r, z, p, Ap, pre);
     }
     bool launchResident(const LaunchCtx& c, int L, T* delta, T* r, T* z, T* p, T* Ap, const T* pre) {

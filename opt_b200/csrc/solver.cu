@@ -322,9 +322,11 @@ __global__ void __launch_bounds__(1024) k_haloExchange(const HaloPlan* __restric
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned long long e = haloEpochNow(ws);
-        for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) stReleaseSys(hp.peerFlag[d], e);
-        for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) { while (ldAcquireSys(hp.myFlag[d]) < e) {} }
+        // own sequence number and own flag words: several exchanges may happen between two r.z productions (p before the loop kernel,
+        // delta after it), and the in-kernel halo paths number THEIR flags by the r.z epochs
+        const unsigned long long e = *hp.epoch + 1ull; *hp.epoch = e;
+        for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) stReleaseSys(hp.peerXFlag[d], e);
+        for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) { while (ldAcquireSys(hp.myXFlag[d]) < e) {} }
     }
 }
 
@@ -345,12 +347,12 @@ struct Plan : PlanBase {
     long nVecWin() const { return winVec.n ? winVec.total : n / VecOf<T>::N; }
     // multi-GPU mailbox block (cudaMalloc'ed so it can be exported through CUDA IPC), see common.cuh CommView
     struct CommBlock { unsigned long long words[kNumScalars][2][kMaxRanks][2]; unsigned long long haloFlags[2]; unsigned long long epoch[kNumScalars]; unsigned long long haloEpoch;
-                       unsigned long long fitFlags[kMaxRanks]; };   // fitFlags[r]: (connect generation << 2) | 1 (rank r cannot run the collective loop kernel) or 2 (it can)
+                       unsigned long long fitFlags[kMaxRanks]; unsigned long long xFlags[2]; };   // fitFlags[r]: (connect generation << 2) | 1 (rank r cannot run the collective loop kernel) or 2 (it can)
     CommBlock* commBlock = nullptr;
     int world = 1, rank = 0;
-    HaloPlan haloP{}, haloZ{};
+    HaloPlan haloP{}, haloZ{}, haloD{};   // halo descriptions of p, z and delta (same segments, different peer vectors)
     ZPush<T> zPush{}; HaloWait zWait{};   // in-kernel halo of z (Step2 pushes, Step3 waits); n == 0: not available, use k_haloExchange
-    HaloPlan* dHaloP = nullptr; HaloPlan* dHaloZ = nullptr;       // device copies (kernels take them by pointer)
+    HaloPlan* dHaloP = nullptr; HaloPlan* dHaloZ = nullptr; HaloPlan* dHaloD = nullptr;   // device copies (kernels take them by pointer)
     unsigned long long** dPeerTable = nullptr;
     std::vector<void*> ipcOpened;
     double* hScalars = nullptr;  // pinned mirror
@@ -422,7 +424,7 @@ struct Plan : PlanBase {
         if (loopExec) cudaGraphExecDestroy(loopExec);
         for (T* v : { delta, r, z, p, p2, Ap, pre, b, Adelta, CtC, SSq, prevX }) if (v) cudaFree(v);
         for (void* q : ipcOpened) cudaIpcCloseMemHandle(q);
-        cudaFree(commBlock); cudaFree(dHaloP); cudaFree(dHaloZ); cudaFree(dPeerTable);
+        cudaFree(commBlock); cudaFree(dHaloP); cudaFree(dHaloZ); cudaFree(dHaloD); cudaFree(dPeerTable);
         cudaFree(ws.partials); cudaFree(ws.counters); cudaFree(ws.scalars); cudaFreeHost(hScalars);
         cudaEventDestroy(evEntry); cudaEventDestroy(evLoop0); cudaEventDestroy(evLoop1); cudaEventDestroy(evCost); cudaEventDestroy(evExit);
         if (ownStream) cudaStreamDestroy(stream);
@@ -481,13 +483,15 @@ struct Plan : PlanBase {
         OPT_CUDA_CHECK(cudaStreamWaitEvent(stream, evEntry, 0));
     }
     // ---- multi-GPU wiring (include/OptB200.h: OptB200_PlanCommHandles / OptB200_PlanConnect)
+    static constexpr int kHandlesPerRank = 4;   // mailbox block (+ peer scratch), z, p, delta
     int commHandles(void* out, int outBytes) override {
-        if (outBytes < 3 * (int)sizeof(cudaIpcMemHandle_t)) return -1;
+        if (outBytes < kHandlesPerRank * (int)sizeof(cudaIpcMemHandle_t)) return -1;
         cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)out;
         OPT_CUDA_CHECK(cudaIpcGetMemHandle(&h[0], commBlock));
         OPT_CUDA_CHECK(cudaIpcGetMemHandle(&h[1], z));
         OPT_CUDA_CHECK(cudaIpcGetMemHandle(&h[2], p));
-        return 3 * (int)sizeof(cudaIpcMemHandle_t);
+        OPT_CUDA_CHECK(cudaIpcGetMemHandle(&h[3], delta));
+        return kHandlesPerRank * (int)sizeof(cudaIpcMemHandle_t);
     }
     int connect(int rank_, int world_, const void* allHandles, int ownedBegin, int ownedEnd, int upperRows, int lowerRows) override {
         if (world_ < 1 || world_ > kMaxRanks || rank_ < 0 || rank_ >= world_) return -1;
@@ -498,16 +502,16 @@ struct Plan : PlanBase {
         auto open = [&](const cudaIpcMemHandle_t& hh) { void* q = nullptr; OPT_CUDA_CHECK(cudaIpcOpenMemHandle(&q, hh, cudaIpcMemLazyEnablePeerAccess)); ipcOpened.push_back(q); return q; };
         ws.comm.world = world; ws.comm.rank = rank; ws.comm.epoch = commBlock->epoch;
         for (int r = 0; r < world; ++r) {
-            CommBlock* cb = (r == rank) ? commBlock : (CommBlock*)open(h[3 * r + 0]);
+            CommBlock* cb = (r == rank) ? commBlock : (CommBlock*)open(h[kHandlesPerRank * r + 0]);
             hostPeerTable[r] = &cb->words[0][0][0][0];
             peerBlocks[r] = cb;
         }
         if (!dPeerTable) OPT_CUDA_CHECK(cudaMalloc((void**)&dPeerTable, sizeof(void*) * kMaxRanks));
         OPT_CUDA_CHECK(cudaMemcpy(dPeerTable, hostPeerTable, sizeof(void*) * kMaxRanks, cudaMemcpyHostToDevice));
         ws.comm.peerWords = dPeerTable;
-        void* upZ = nullptr; void* upP = nullptr; void* dnZ = nullptr; void* dnP = nullptr;
-        if (rank > 0 && upperRows > 0) { upZ = open(h[3 * (rank - 1) + 1]); upP = open(h[3 * (rank - 1) + 2]); }
-        if (rank + 1 < world && lowerRows > 0) { dnZ = open(h[3 * (rank + 1) + 1]); dnP = open(h[3 * (rank + 1) + 2]); }
+        void* upZ = nullptr; void* upP = nullptr; void* dnZ = nullptr; void* dnP = nullptr; void* upD = nullptr; void* dnD = nullptr;
+        if (rank > 0 && upperRows > 0) { upZ = open(h[kHandlesPerRank * (rank - 1) + 1]); upP = open(h[kHandlesPerRank * (rank - 1) + 2]); upD = open(h[kHandlesPerRank * (rank - 1) + 3]); }
+        if (rank + 1 < world && lowerRows > 0) { dnZ = open(h[kHandlesPerRank * (rank + 1) + 1]); dnP = open(h[kHandlesPerRank * (rank + 1) + 2]); dnD = open(h[kHandlesPerRank * (rank + 1) + 3]); }
         auto segs = E->haloSegments();
         auto fill = [&](HaloPlan& hp, void* up, void* dn) {
             hp = HaloPlan{};
@@ -518,12 +522,16 @@ struct Plan : PlanBase {
             hp.peerFlag[0] = up ? &peerBlocks[rank - 1]->haloFlags[1] : nullptr;
             hp.peerFlag[1] = dn ? &peerBlocks[rank + 1]->haloFlags[0] : nullptr;
             hp.myFlag[0] = &commBlock->haloFlags[0]; hp.myFlag[1] = &commBlock->haloFlags[1];
+            hp.peerXFlag[0] = up ? &peerBlocks[rank - 1]->xFlags[1] : nullptr;
+            hp.peerXFlag[1] = dn ? &peerBlocks[rank + 1]->xFlags[0] : nullptr;
+            hp.myXFlag[0] = &commBlock->xFlags[0]; hp.myXFlag[1] = &commBlock->xFlags[1];
             hp.epoch = &commBlock->haloEpoch;
         };
-        fill(haloP, upP, dnP); fill(haloZ, upZ, dnZ);
-        if (!dHaloP) { OPT_CUDA_CHECK(cudaMalloc((void**)&dHaloP, sizeof(HaloPlan))); OPT_CUDA_CHECK(cudaMalloc((void**)&dHaloZ, sizeof(HaloPlan))); }
+        fill(haloP, upP, dnP); fill(haloZ, upZ, dnZ); fill(haloD, upD, dnD);
+        if (!dHaloP) { OPT_CUDA_CHECK(cudaMalloc((void**)&dHaloP, sizeof(HaloPlan))); OPT_CUDA_CHECK(cudaMalloc((void**)&dHaloZ, sizeof(HaloPlan))); OPT_CUDA_CHECK(cudaMalloc((void**)&dHaloD, sizeof(HaloPlan))); }
         OPT_CUDA_CHECK(cudaMemcpy(dHaloP, &haloP, sizeof(HaloPlan), cudaMemcpyHostToDevice));
         OPT_CUDA_CHECK(cudaMemcpy(dHaloZ, &haloZ, sizeof(HaloPlan), cudaMemcpyHostToDevice));
+        OPT_CUDA_CHECK(cudaMemcpy(dHaloD, &haloD, sizeof(HaloPlan), cudaMemcpyHostToDevice));
         auto ranges = E->ownedScalarRanges();
         ownVec = OwnedRanges{}; ownScalar = OwnedRanges{};
         for (size_t i = 0; i < ranges.size() && i < 4; ++i) {
@@ -608,7 +616,7 @@ struct Plan : PlanBase {
     void exchangeHalo(const HaloPlan& hp, const T* vec) {
         if (world <= 1 || hp.nSeg == 0 || (!hp.peerVec[0] && !hp.peerVec[1])) return;
         if (getenv("OPTB_SKIP_HALO")) return;   // timing experiment only (results are wrong)
-        k_haloExchange<T><<<1, 1024, 0, stream>>>(&hp == &haloP ? dHaloP : dHaloZ, ws, vec); ++launches;
+        k_haloExchange<T><<<1, 1024, 0, stream>>>(&hp == &haloP ? dHaloP : (&hp == &haloZ ? dHaloZ : dHaloD), ws, vec); ++launches;
     }
     void readScalars() {
         resolveCost();
@@ -714,6 +722,9 @@ struct Plan : PlanBase {
             if (world > 1 && !pHaloFresh) { exchangeHalo(haloP, p); pHaloFresh = true; }   // the multi-rank form stages p's halo rows from memory
             if (E->pcgLoop(ctx(), L, persistentMode > 0, delta, r, z, p, p2, Ap, pre, &pf, world > 1 ? &haloZ : nullptr)) {
                 pFinal = pf; ++launches;
+                // the update of X on my halo rows must equal the owner's (no X exchange): the collective kernel writes delta
+                // on owned rows only (the single-reduction form keeps no shadow copy of the neighbour's boundary row), so fetch the halo rows of delta
+                if (world > 1) exchangeHalo(haloD, delta);
                 OPT_CUDA_CHECK(cudaEventRecord(evLoop1, stream));
                 return;
             }

@@ -48,9 +48,11 @@ struct HaloPlan {
     long srcOff[kMaxHaloSegs], dstOff[kMaxHaloSegs], len[kMaxHaloSegs];   // in scalars
     int dir[kMaxHaloSegs];               // 0 = to the upper neighbour, 1 = to the lower neighbour
     void* peerVec[2];                    // neighbour's copy of the vector being exchanged (nullptr: no neighbour)
-    unsigned long long* peerFlag[2];     // neighbour's "halo arrived from me" flag
+    unsigned long long* peerFlag[2];     // neighbour's "halo arrived from me" flag (in-kernel halo paths: numbered by the r.z epochs)
     unsigned long long* myFlag[2];       // my flags, written by the upper / lower neighbour
-    unsigned long long* epoch;           // local counter (stand-alone exchange kernel only)
+    unsigned long long* peerXFlag[2];    // the same pair for the stand-alone exchange kernel, numbered by its own device-side counter ...
+    unsigned long long* myXFlag[2];
+    unsigned long long* epoch;           // ... this one (local; every rank runs the same sequence of exchange kernels)
 };
 
 struct LaunchCtx {

@@ -152,12 +152,12 @@ class OptSolver:
         return self.L.OptB200_PcgLoopMsLastStep(self.plan)
 
     def comm_handles(self):
-        """192 bytes: CUDA IPC handles of this plan's scalar mailbox, z and p (OptB200_PlanCommHandles)"""
-        buf = ctypes.create_string_buffer(192)
-        n = self.L.OptB200_PlanCommHandles(self.plan, buf, 192)
-        if n != 192:
+        """CUDA IPC handles of this plan's scalar mailbox block, z, p and delta (OptB200_PlanCommHandles: 4 x 64 bytes)"""
+        buf = ctypes.create_string_buffer(1024)
+        n = self.L.OptB200_PlanCommHandles(self.plan, buf, 1024)
+        if n <= 0:
             raise capi.OptError("OptB200_PlanCommHandles failed")
-        return buf.raw
+        return buf.raw[:n]
 
     def connect(self, rank, world, all_handles, owned_begin, owned_end, upper_rows, lower_rows):
         rc = self.L.OptB200_PlanConnect(self.plan, int(rank), int(world), all_handles, int(owned_begin), int(owned_end), int(upper_rows), int(lower_rows))

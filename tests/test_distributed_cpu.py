@@ -42,14 +42,14 @@ def _worker(rank, world, port, q):
 
     class FakeSolver:   # records what the C ABI would receive
         def comm_handles(self):
-            return bytes([rank + 1]) * 192
+            return bytes([rank + 1]) * 256
         def connect(self, *a):
             self.args = a
     fs = FakeSolver()
     connect_plan(fs, slab)
     r_, w_, blob, ob, oe, up, dn = fs.args
     assert (r_, w_, ob, oe, up, dn) == (rank, world, slab.owned_begin, slab.owned_end, slab.upper_rows, slab.lower_rows)
-    assert len(blob) == 192 * world and all(blob[192 * r] == r + 1 for r in range(world))
+    assert len(blob) == 256 * world and all(blob[256 * r] == r + 1 for r in range(world))
     loc[1][:] = -1.0
     slab.owned(loc[1], W)[:] = rank                     # only owned rows count
     g = gather_owned_rows(loc[1], W, slab)

@@ -109,6 +109,49 @@ def test_pcg_iterations_parity(built, dp, k, loop):
         assert abs(a - b) <= (1e-9 if dp else 2e-3) * max(abs(b), 1e-30), name
 
 
+@pytest.mark.parametrize("dp", [False, True])
+@pytest.mark.parametrize("k", [1, 2, 7, 25])
+@pytest.mark.parametrize("W,H,tile", [(48, 40, None), (200, 150, "64x16")])
+def test_single_reduction_loop_parity(built, dp, k, W, H, tile):
+    """the Chronopoulos-Gear form of the on-chip loop (k_iwCgLoopTile: one all-reduce per PCG step, A p carried by a recurrence; the
+    default of the multi-rank collective kernel, OPTB_CG_LOOP=1 on one GPU): state after k iterations vs the oracle's standard PCG.
+    p is not compared: the kernel stops before the update that needs the next r.z, so its p is one update behind."""
+    env = {"OPTB_CG_LOOP": "1"}
+    if tile:
+        env["OPTB_RESIDENT_TILE"] = tile
+    with _env(**env):
+        s, o, host = _mk(W, H, dp, mask="random", seed=2, perturb=0.3)
+    N = W * H
+    dev = workloads.to_device(host)
+    for q in (s, o):
+        q.set_solver_parameter("nIterations", 1); q.set_solver_parameter("lIterations", 50)
+        q.set_max_linear_iterations(k)
+    s.init(dev); o.init(host)
+    s.step(dev); o.step(host)
+    assert s.launches_last_step() <= 3, s.launches_last_step()      # PCGInit1 + ONE loop kernel: the single-reduction path was really taken
+    tol = 1e-9 if dp else (3e-4 if k <= 7 else 2e-3)
+    for name in ("delta", "r", "z", "Ap_X"):
+        a = s.read_vector(name); b = _oracle_flat(s, o.get_vector(name), N)
+        scale = max(1e-30, np.abs(b).max())
+        assert np.abs(a - b).max() <= tol * scale, (name, k, float(np.abs(a - b).max()), float(scale))
+
+
+def test_single_reduction_loop_solve(built):
+    """full GN solves: cost and unknowns of the single-reduction loop vs the oracle"""
+    W, H = 96, 80
+    sp = {"nIterations": 4, "lIterations": 60}
+    with _env(OPTB_CG_LOOP="1"):
+        s, o, host = _mk(W, H, False, mask="blob", seed=4, perturb=0.2)
+    ref = workloads.clone_params(host)
+    for k, v in sp.items():
+        o.set_solver_parameter(k, v)
+    ocost = o.solve(ref)
+    dev = workloads.to_device(host)
+    cost = s.solve(sp, dev)
+    assert abs(cost - ocost) <= 2e-4 * abs(ocost), (cost, ocost)
+    assert np.linalg.norm(dev[0].cpu().numpy() - ref[0]) <= 1e-4 * np.linalg.norm(ref[0])
+
+
 @pytest.mark.parametrize("loop", ["per_step", "resident", "persistent_l2"])
 def test_persistent_loop_multirow_slabs(built, loop):
     """taller than the SM count: the on-chip loop gets slabs of several rows, the last one partial; the L2 loop gets

@@ -12,11 +12,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("cg", ["1", "0"])          # single-reduction kernel (the default) and the two-reduction kernel
 @pytest.mark.parametrize("world,args,tile", [(2, ["128", "96"], None), (2, ["256", "130"], "64x8"), (4, ["192", "64"], None)])
-def test_persistent_slab_solve_matches_single_gpu(built, world, args, tile):
+def test_persistent_slab_solve_matches_single_gpu(built, world, args, tile, cg):
     import torch
     port = 29500 + (os.getpid() % 400)
     env = dict(os.environ); env["OPTB_TEST_MAX_LAUNCHES"] = "12"       # the collective loop kernel is the default when every rank's slab fits
+    env["OPTB_CG_LOOP"] = cg
     if torch.cuda.device_count() < world:
         env["OPTB_SHARE_GPU"] = "1"                                   # ranks time-slice one GPU (see tests/test_gpu_multi.py)
     if tile:

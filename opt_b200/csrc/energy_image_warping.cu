@@ -1343,10 +1343,13 @@ struct ImageWarpingOps : EnergyOps<T> {
         }
         return true;
     }
-    // single-reduction (Chronopoulos-Gear) form of the tile loop: default for the multi-rank collective kernel (OPTB_CG_LOOP=0: the
-    // two-reduction kernel), opt-in on a single GPU (OPTB_CG_LOOP=1) where the reference's exact recurrences stay the default
+    // single-reduction (Chronopoulos-Gear) form of the tile loop: OPT-IN (OPTB_CG_LOOP=1), single GPU and multi-rank.  The default loops
+    // keep the reference's recurrences exactly (the collective two-reduction kernel is bitwise equal to the single-GPU on-chip loop); this
+    // one is faster where the all-reduces dominate but carries A p by a recurrence: in fp32 its iterates drift from the reference's by
+    // more than a summation-order change does (measured: cost after 40 un-converged PCG steps off by 1.3e-3 on a 128x96 case where the
+    // two-reduction kernel is exact; 1e-6 on others) -- parity first, so it is not a default.
     unsigned long long* cgWords = nullptr; unsigned long long* edgeLL = nullptr; unsigned long long cgSeq = 0; size_t edgeWords = 0; const void* cgChecked = nullptr;
-    bool useCg(bool multi) const { const char* e = getenv("OPTB_CG_LOOP"); return e ? atoi(e) != 0 : multi; }
+    bool useCg(bool) const { const char* e = getenv("OPTB_CG_LOOP"); return e && atoi(e) != 0; }
     int cgKmax() const { const long need = ((long)tileW * tileH + 511) / 512; return need <= 4 ? 4 : (need <= 7 ? 7 : 8); }
     template <int KMAX, bool MULTI> const void* cgFn() const { return (const void*)k_iwCgLoopTile<T, KMAX, MULTI>; }
     const void* cgFnFor(bool multi) const {

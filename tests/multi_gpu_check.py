@@ -153,7 +153,8 @@ def main():
         e_off = np.linalg.norm(off - o1) / np.linalg.norm(o1); e_ang = np.linalg.norm(ang - a1) / max(np.linalg.norm(a1), 1e-12)
         print(f"multi_gpu_check world={world} {W}x{H} {kind}: costs {costs[0]:.6f} -> {costs[-1]:.6f}; vs 1 GPU: cost rel {rel_c:.2e}, Offset {e_off:.2e}, Angle {e_ang:.2e}")
         print("  multi :", [f"{c:.6g}" for c in costs]); print("  single:", [f"{c:.6g}" for c in c1])
-        ok = rel_c < 1e-4 and e_off < 1e-5 and e_ang < 2e-3 and len(costs) == len(c1)
+        tol = float(os.environ.get("OPTB_TEST_TOL_SCALE", "1"))       # > 1: paths whose iterates are not the reference's bit for bit (single-reduction loop)
+        ok = rel_c < 1e-4 * tol and e_off < 1e-5 * tol and e_ang < 2e-3 * tol and len(costs) == len(c1)
         print(f"  launches in the last step: {launches}")
         if max_launches > 0 and launches > max_launches:
             print(f"  expected at most {max_launches} launches: the persistent multi-GPU loop was not taken"); ok = False

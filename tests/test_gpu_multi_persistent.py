@@ -12,13 +12,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("cg", ["1", "0"])          # single-reduction kernel (the default) and the two-reduction kernel
+@pytest.mark.parametrize("cg", ["0", "1"])          # the two-reduction kernel (default: the reference's recurrences) and the opt-in single-reduction kernel
 @pytest.mark.parametrize("world,args,tile", [(2, ["128", "96"], None), (2, ["256", "130"], "64x8"), (4, ["192", "64"], None)])
 def test_persistent_slab_solve_matches_single_gpu(built, world, args, tile, cg):
     import torch
     port = 29500 + (os.getpid() % 400)
     env = dict(os.environ); env["OPTB_TEST_MAX_LAUNCHES"] = "12"       # the collective loop kernel is the default when every rank's slab fits
     env["OPTB_CG_LOOP"] = cg
+    if cg == "1":
+        env["OPTB_TEST_TOL_SCALE"] = "30"     # A p carried by a recurrence: equal to the reference's iterates in exact arithmetic, ~1e-3 apart in fp32 after 40 un-converged steps
     if torch.cuda.device_count() < world:
         env["OPTB_SHARE_GPU"] = "1"                                   # ranks time-slice one GPU (see tests/test_gpu_multi.py)
     if tile:

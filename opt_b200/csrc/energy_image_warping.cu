@@ -204,9 +204,12 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJ(IWData<T> D, ReduceWorksp
 // Each thread marches down a 4-pixel column strip: the vertical pair term is evaluated once and
 // credited to both of its pixels (the J^T J pair block is antisymmetric in the offset rows), the
 // horizontal pairs are evaluated one-sided from both ends so no cross-lane exchange is needed.
+// Shape: 64 x IW_TH pixel tiles, IW_STAGES tiles in flight per CTA, IW_STRIP rows per thread (256 threads = 64 columns x IW_TH / IW_STRIP
+// strips).  Measured in the bench loop at 2048^2 (fused kernel, tools/build_variants.sh): 16/2/4 (2 CTAs per SM) 59.9 us, 8/2/2 61.1,
+// 8/3/2 59.3, 8/4/2 59.5, 8/6/2 69.8, 32/2/8 58.6, 16/4/4 59.6, 16/3/4 (one CTA per SM, two tiles ahead) 55.4-56.1 -- the default.
 #ifndef IW_TH
 #define IW_TH 16
-#define IW_STAGES 2
+#define IW_STAGES 3
 #define IW_STRIP 4
 #endif
 constexpr int kTW = 64, kTH = IW_TH, kStages = IW_STAGES, kStrip = IW_STRIP;

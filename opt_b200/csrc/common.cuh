@@ -42,6 +42,22 @@ enum Scalar : int {
 
 constexpr int kMaxRanks = 8;
 
+// Wait-loop watchdog.  A waiter that never sees its word is a bug (a lost CTA / rank), and a hang would cost the whole job, so the
+// loops give up with __trap() -- but by WALL CLOCK, not by poll count: on a time-sliced GPU (MPS off, two processes sharing a device --
+// the multi-rank tests do exactly that) or under a debugger a peer can be descheduled for many milliseconds, which a poll-count limit
+// (2^24 polls ~ 1 s) turned into a spurious abort.  %globaltimer is read once per 4096 polls; the limit is 30 s.
+__device__ __forceinline__ unsigned long long globalTimerNs() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+struct SpinGuard {
+    unsigned long long spins = 0, t0 = 0;
+    __device__ __forceinline__ void tick() {
+        if ((++spins & 4095ull) == 0ull) {
+            const unsigned long long now = globalTimerNs();
+            if (t0 == 0ull) t0 = now; else if (now - t0 > 30000000000ull) __trap();
+        }
+    }
+};
+
+
 // Cross-GPU view of the scalar mailboxes ("a single allreduce of the PCG scalars").
 // Every rank owns one mailbox block (cudaMalloc + CUDA IPC); peerWords[r] is rank r's block mapped into
 // this process.  A reduction's last CTA stores its local sum into slot [scalar][epoch&1][myRank] of EVERY
@@ -120,9 +136,9 @@ __device__ __forceinline__ double loadScalarGlobal(const ReduceWorkspace& ws, in
     const unsigned long long* row = ws.comm.peerWords[ws.comm.rank] + mailboxWord(slot, e, 0);
     const int nWords = 2 * ws.comm.world;
     unsigned long long w[2 * kMaxRanks];
-    bool ok;
+    bool ok; SpinGuard guard;
     do {
-        ok = true;
+        ok = true; guard.tick();
 #pragma unroll
         for (int i = 0; i < 2 * kMaxRanks; ++i) { w[i] = want; if (i < nWords) w[i] = ldVolatileU64(row + i); }
 #pragma unroll
@@ -153,7 +169,8 @@ __device__ __forceinline__ void loadScalars2(const ReduceWorkspace& ws, int slot
         if (e != 0ull && sender < ws.comm.world) {
             const unsigned long long want = e & 0xffffffffull;
             const unsigned long long* src = ws.comm.peerWords[ws.comm.rank] + mailboxWord(slot, e, sender) + word;
-            do { w = ldVolatileU64(src); } while ((w & 0xffffffffull) != want);
+            SpinGuard guard;
+            do { w = ldVolatileU64(src); guard.tick(); } while ((w & 0xffffffffull) != want);
         }
         __syncwarp();
         const unsigned payload = (unsigned)(w >> 32);   // 0 for idle lanes and for a slot that was never produced
@@ -351,8 +368,8 @@ __device__ __forceinline__ double gridAllReduce(double v, double* partials, Loop
         }
     }
     if (threadIdx.x == 0) {
-        unsigned long long spins = 0;
-        while (ldVolatileU64(&S->flag[k & 1ull]) != k) { if (++spins > (1ull << 24)) __trap(); }   // a lost CTA is a bug: fail, do not hang
+        SpinGuard guard;
+        while (ldVolatileU64(&S->flag[k & 1ull]) != k) guard.tick();   // a lost CTA is a bug: fail, do not hang
         __threadfence();
         s_val = *reinterpret_cast<volatile double*>(&S->value[k & 1ull]);
     }
@@ -403,10 +420,10 @@ __device__ __forceinline__ double gridAllReduceLL(double v, unsigned long long* 
     if (s_last) {
         if (threadIdx.x < gridDim.x) {
             const unsigned long long* src = row + 2 * threadIdx.x;
-            unsigned long long w0, w1, spins = 0;
+            unsigned long long w0, w1; SpinGuard guard;
             do {
                 w0 = ldVolatileU64(src); w1 = ldVolatileU64(src + 1);
-                if (++spins > (1ull << 24)) __trap();
+                guard.tick();
             } while ((w0 & 0xffffffffull) != seq || (w1 & 0xffffffffull) != seq);
             s_part[threadIdx.x] = __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
         }
@@ -422,10 +439,10 @@ __device__ __forceinline__ double gridAllReduceLL(double v, unsigned long long* 
     }
     if (threadIdx.x == 0) {
         const unsigned long long* src = row + 2 * kMaxLLCtas;
-        unsigned long long w0, w1, spins = 0;
+        unsigned long long w0, w1; SpinGuard guard;
         do {
             w0 = ldVolatileU64(src); w1 = ldVolatileU64(src + 1);
-            if (++spins > (1ull << 24)) __trap();   // a lost CTA is a bug: fail, do not hang
+            guard.tick();   // a lost CTA is a bug: fail, do not hang
         } while ((w0 & 0xffffffffull) != seq || (w1 & 0xffffffffull) != seq);
         if (releaseData) __threadfence();   // acquire side: loads issued after the barrier see the other CTAs' stores
         s_val = __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
@@ -474,10 +491,10 @@ __device__ __forceinline__ double gridAllReduceLLMulti(double v, unsigned long l
     if (s_last) {
         if (threadIdx.x < gridDim.x) {
             const unsigned long long* src = row + 2 * threadIdx.x;
-            unsigned long long w0, w1, spins = 0;
+            unsigned long long w0, w1; SpinGuard guard;
             do {
                 w0 = ldVolatileU64(src); w1 = ldVolatileU64(src + 1);
-                if (++spins > (1ull << 24)) __trap();
+                guard.tick();
             } while ((w0 & 0xffffffffull) != seq || (w1 & 0xffffffffull) != seq);
             s_part[threadIdx.x] = __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
         }
@@ -496,8 +513,8 @@ __device__ __forceinline__ double gridAllReduceLLMulti(double v, unsigned long l
         unsigned long long w = 0ull;
         if (lane < 2 * comm.world) {     // lane = 2 * sender + word
             const unsigned long long* src = comm.peerWords[comm.rank] + mailboxWord(slot, k, lane >> 1) + (lane & 1);
-            unsigned long long spins = 0;
-            do { w = ldVolatileU64(src); if (++spins > (1ull << 26)) __trap(); } while ((w & 0xffffffffull) != seq);   // a lost rank is a bug: fail, do not hang
+            SpinGuard guard;
+            do { w = ldVolatileU64(src); guard.tick(); } while ((w & 0xffffffffull) != seq);   // a lost rank is a bug: fail, do not hang
         }
         __syncwarp();
         const unsigned payload = (unsigned)(w >> 32);
@@ -548,12 +565,12 @@ __device__ __forceinline__ void gridAllReduce2LL(double v0, double v1, unsigned 
     if (s_last) {
         if (threadIdx.x < gridDim.x) {
             const unsigned long long* src = row + 4 * threadIdx.x;
-            unsigned long long w[4], spins = 0; bool ok;
+            unsigned long long w[4]; SpinGuard guard; bool ok;
             do {
                 ok = true;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { w[i] = ldVolatileU64(src + i); ok = ok && ((w[i] & 0xffffffffull) == seq); }
-                if (++spins > (1ull << 24)) __trap();
+                guard.tick();
             } while (!ok);
             s_p[0][threadIdx.x] = unword(w[0], w[1]); s_p[1][threadIdx.x] = unword(w[2], w[3]);
         }
@@ -571,8 +588,8 @@ __device__ __forceinline__ void gridAllReduce2LL(double v0, double v1, unsigned 
         const int nWords = MULTI ? 4 * comm.world : 4;
         if (lane < nWords) {
             const unsigned long long* src = MULTI ? comm.peerWords[comm.rank] + mailboxWord(slot + ((lane >> 1) & 1), k, lane >> 2) + (lane & 1) : row + 4 * kMaxLLCtas + lane;
-            unsigned long long spins = 0;
-            do { w = ldVolatileU64(src); if (++spins > (1ull << 26)) __trap(); } while ((w & 0xffffffffull) != seq);   // a lost CTA / rank is a bug: fail, do not hang
+            SpinGuard guard;
+            do { w = ldVolatileU64(src); guard.tick(); } while ((w & 0xffffffffull) != seq);   // a lost CTA / rank is a bug: fail, do not hang
         }
         __syncwarp();
         const unsigned payload = (unsigned)(w >> 32);
@@ -603,13 +620,13 @@ __device__ __forceinline__ void llStore(unsigned long long* slot, double v, unsi
     stVolatileU64(slot + 1, ((bits >> 32) << 32) | (unsigned long long)seq);
 }
 __device__ __forceinline__ void llLoad(const unsigned long long* slot, unsigned seq, float& out) {
-    unsigned long long w, spins = 0;
-    do { w = ldVolatileU64(slot); if (++spins > (1ull << 26)) __trap(); } while ((unsigned)(w & 0xffffffffull) != seq);   // a lost rank is a bug: fail, do not hang
+    unsigned long long w; SpinGuard guard;
+    do { w = ldVolatileU64(slot); guard.tick(); } while ((unsigned)(w & 0xffffffffull) != seq);   // a lost rank is a bug: fail, do not hang
     out = __uint_as_float((unsigned)(w >> 32));
 }
 __device__ __forceinline__ void llLoad(const unsigned long long* slot, unsigned seq, double& out) {
-    unsigned long long w0, w1, spins = 0;
-    do { w0 = ldVolatileU64(slot); w1 = ldVolatileU64(slot + 1); if (++spins > (1ull << 26)) __trap(); } while ((unsigned)(w0 & 0xffffffffull) != seq || (unsigned)(w1 & 0xffffffffull) != seq);
+    unsigned long long w0, w1; SpinGuard guard;
+    do { w0 = ldVolatileU64(slot); w1 = ldVolatileU64(slot + 1); guard.tick(); } while ((unsigned)(w0 & 0xffffffffull) != seq || (unsigned)(w1 & 0xffffffffull) != seq);
     out = __longlong_as_double((long long)((w0 >> 32) | ((w1 >> 32) << 32)));
 }
 template <class T> struct LLWords;

@@ -306,8 +306,8 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const
         const int x0 = (tile % tilesX) * kTW, y0 = (tile / tilesX) * kTH;
         if (halo) {
             bool waited = false;
-            if (myFlagUp && y0 - 1 <= D.y0 - 1) { while (ldAcquireSys(myFlagUp) < haloE) {} waited = true; }
-            if (myFlagDn && y0 + kTH >= D.y1) { while (ldAcquireSys(myFlagDn) < haloE) {} waited = true; }
+            if (myFlagUp && y0 - 1 <= D.y0 - 1) { SpinGuard g; while (ldAcquireSys(myFlagUp) < haloE) g.tick(); waited = true; }
+            if (myFlagDn && y0 + kTH >= D.y1) { SpinGuard g; while (ldAcquireSys(myFlagDn) < haloE) g.tick(); waited = true; }
             if (waited) asm volatile("fence.proxy.async.global;" ::: "memory");
         }
         mbarExpectTx(&bars[stage], (unsigned)(kBytesO + kBytesA + kBytesG + kBytesF + (FUSE3 ? kBytesO + kBytesA : 0)));

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kBlock) k_pcgStep3(long nVec, WindowRanges win
     if (hw.n) {
         if (threadIdx.x == 0) {
             const unsigned long long e = haloEpochNow(ws);
-            for (int d = 0; d < 2; ++d) if (hw.flag[d]) { while (ldAcquireSys(hw.flag[d]) < e) {} }
+            for (int d = 0; d < 2; ++d) if (hw.flag[d]) { SpinGuard g; while (ldAcquireSys(hw.flag[d]) < e) g.tick(); }
         }
         __syncthreads();
         for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < hw.total; j += (long)gridDim.x * kBlock) {
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(1024) k_haloExchange(const HaloPlan* __restric
         // delta after it), and the in-kernel halo paths number THEIR flags by the r.z epochs
         const unsigned long long e = *hp.epoch + 1ull; *hp.epoch = e;
         for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) stReleaseSys(hp.peerXFlag[d], e);
-        for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) { while (ldAcquireSys(hp.myXFlag[d]) < e) {} }
+        for (int d = 0; d < 2; ++d) if (hp.peerVec[d]) { SpinGuard g; while (ldAcquireSys(hp.myXFlag[d]) < e) g.tick(); }
     }
 }
 

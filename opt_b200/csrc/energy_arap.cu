@@ -209,84 +209,6 @@ __global__ void __launch_bounds__(kBlock) k_arapApplyJTJ(ArapData<T> D, ReduceWo
     if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
 }
 
-// ------------------------------------------------------------------------------------ PCGStep1 on symmetric graphs, factored form
-// The gather above rebuilds, for every neighbour visit, the three derivative columns dR_k d of BOTH end points (~150 instructions per edge,
-// 918 per vertex at valence 6; ncu: issue-bound at 31.9 us for 501 k vertices).  With M_v(d) = [dR_0 d, dR_1 d, dR_2 d] (dR_k = dR/dA_k at
-// vertex v) the operator factors per VERTEX:
-//     M_v(d) pA_v   = (sum_k pA_v[k] dR_k(v)) d =: Q_v d             -- Q_v: one 3x3 matrix per vertex per PCG step
-//     M_v(d)^T y    = [ <dR_k(v), y d^T>_F ]_k                        -- accumulate S_v = sum_edges y d^T, contract with dR_k once at the end
-// so that a neighbour visit is:  d = U_v - U_b,  e = pO_v - pO_b,  y = e - Q_v d,  aO += y + (e - Q_b d),  S += y d^T   (~45 instructions),
-// using the reverse edge b -> v exactly like the merged loop above (symmetric graphs only).  k_arapDirQ forms Q for every vertex of the
-// window first (a streaming pass: 12 + 24 B read, 48 B written per vertex).  Same operator, different association of the sums.
-template <class T> struct alignas(16) ArapQ { T q[12]; };   // row-major 3x3 in q[0..8], 16-byte aligned for 128-bit gathers
-template <class T> struct ArapDR { T a[9], b[9], g[9]; };   // dR/dalpha, dR/dbeta, dR/dgamma (row-major), from the packed sin/cos
-template <class T> __device__ __forceinline__ ArapDR<T> arapDR(const ArapPack<T>& s) {
-    const ArapRot<T> R(s);
-    ArapDR<T> D;
-    D.a[0] = T(0); D.a[1] = R.m2; D.a[2] = -R.m1; D.a[3] = T(0); D.a[4] = R.m5; D.a[5] = -R.m4; D.a[6] = T(0); D.a[7] = R.m8; D.a[8] = -R.m7;
-    const T r0 = -s.sb, r1 = s.cb * s.sa, r2 = s.cb * s.ca;
-    D.b[0] = s.cg * r0; D.b[1] = s.cg * r1; D.b[2] = s.cg * r2; D.b[3] = s.sg * r0; D.b[4] = s.sg * r1; D.b[5] = s.sg * r2;
-    D.b[6] = -s.cb; D.b[7] = -s.sb * s.sa; D.b[8] = -s.sb * s.ca;
-    D.g[0] = -R.m3; D.g[1] = -R.m4; D.g[2] = -R.m5; D.g[3] = R.m0; D.g[4] = R.m1; D.g[5] = R.m2; D.g[6] = T(0); D.g[7] = T(0); D.g[8] = T(0);
-    return D;
-}
-template <class T>
-__global__ void __launch_bounds__(kBlock) k_arapDirQ(ArapData<T> D, const T* __restrict__ x, ArapQ<T>* __restrict__ Q) {
-    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
-        const ArapDR<T> R = arapDR(D.pack[v]);
-        const V3<T> a = ld3(x + D.offA, v);
-        ArapQ<T> q;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) q.q[i] = a.x * R.a[i] + a.y * R.b[i] + a.z * R.g[i];
-        q.q[9] = q.q[10] = q.q[11] = T(0);
-        Q[v] = q;
-    }
-}
-template <class T, bool LM>
-__global__ void __launch_bounds__(kBlock) k_arapApplyJTJSym(ArapData<T> D, ReduceWorkspace ws, int dotSlot, const T* __restrict__ x, const ArapQ<T>* __restrict__ Q,
-                                                            T* __restrict__ out, const T* __restrict__ CtC) {
-    const T w2 = D.w * D.w, wf2 = D.wf * D.wf;
-    T acc = T(0);
-    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
-        const long o = 3L * v, a = D.offA + 3L * v;
-        if (v < D.lo || v >= D.hi) { out[o] = out[o + 1] = out[o + 2] = T(0); out[a] = out[a + 1] = out[a + 2] = T(0); continue; }   // halo vertex
-        const ArapPack<T> sv = D.pack[v];
-        const V3<T> pOv = ld3(x, v), pAv = ld3(x + D.offA, v);
-        const ArapQ<T> Qv = Q[v];
-        V3<T> aO{ T(0), T(0), T(0) };
-        T S[9] = { T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0) };
-        for (int k = D.outStart[v]; k < D.outStart[v + 1]; ++k) {
-            const int b = D.outNbr[k];
-            const ArapPack<T>& sb_ = D.pack[b];
-            const V3<T> d = { sv.ux - sb_.ux, sv.uy - sb_.uy, sv.uz - sb_.uz };
-            const V3<T> pOb = ld3(x, b);
-            const ArapQ<T> Qb = Q[b];
-            const V3<T> e = { pOv.x - pOb.x, pOv.y - pOb.y, pOv.z - pOb.z };
-            const V3<T> qv = { Qv.q[0] * d.x + Qv.q[1] * d.y + Qv.q[2] * d.z, Qv.q[3] * d.x + Qv.q[4] * d.y + Qv.q[5] * d.z, Qv.q[6] * d.x + Qv.q[7] * d.y + Qv.q[8] * d.z };
-            const V3<T> qb = { Qb.q[0] * d.x + Qb.q[1] * d.y + Qb.q[2] * d.z, Qb.q[3] * d.x + Qb.q[4] * d.y + Qb.q[5] * d.z, Qb.q[6] * d.x + Qb.q[7] * d.y + Qb.q[8] * d.z };
-            const V3<T> y = { e.x - qv.x, e.y - qv.y, e.z - qv.z };                 // (J p) of the edge v -> b, over w
-            aO.x += y.x + (e.x - qb.x); aO.y += y.y + (e.y - qb.y); aO.z += y.z + (e.z - qb.z);   // ... and minus (J p) of the reverse edge b -> v (its rest edge is -d)
-            S[0] += y.x * d.x; S[1] += y.x * d.y; S[2] += y.x * d.z;
-            S[3] += y.y * d.x; S[4] += y.y * d.y; S[5] += y.y * d.z;
-            S[6] += y.z * d.x; S[7] += y.z * d.y; S[8] += y.z * d.z;
-        }
-        const ArapDR<T> R = arapDR(sv);
-        T ca = T(0), cb = T(0), cg = T(0);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { ca += R.a[i] * S[i]; cb += R.b[i] * S[i]; cg += R.g[i] * S[i]; }
-        const T f = sv.fit != T(0) ? wf2 : T(0);
-        V3<T> oO = { w2 * aO.x + f * pOv.x, w2 * aO.y + f * pOv.y, w2 * aO.z + f * pOv.z };
-        V3<T> oA = { -(w2 * ca), -(w2 * cb), -(w2 * cg) };
-        if (LM) {
-            oO.x += CtC[o] * pOv.x; oO.y += CtC[o + 1] * pOv.y; oO.z += CtC[o + 2] * pOv.z;
-            oA.x += CtC[a] * pAv.x; oA.y += CtC[a + 1] * pAv.y; oA.z += CtC[a + 2] * pAv.z;
-        }
-        acc += dot3(pOv, oO) + dot3(pAv, oA);
-        out[o] = oO.x; out[o + 1] = oO.y; out[o + 2] = oO.z; out[a] = oA.x; out[a + 1] = oA.y; out[a + 2] = oA.z;
-    }
-    if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
-}
-
 // ------------------------------------------------------------------------------------ computeCost (+_Graph) / computeModelCost (+_Graph)
 template <class T, bool MODEL>
 __global__ void __launch_bounds__(kBlock) k_arapCost(ArapData<T> D, ReduceWorkspace ws, int slot, const T* __restrict__ delta) {
@@ -375,7 +297,6 @@ struct ArapOps : EnergyOps<T> {
     void* cubTemp = nullptr; size_t cubBytes = 0; int capE = 0;
     bool csrValid = false;
     int sms = 148;
-    ArapQ<T>* dirQ = nullptr; bool factored = !getenv("OPTB_ARAP_NO_FACTORED");   // factored J^T J on symmetric graphs (A/B: the direct merged gather)
     ArapOps(const unsigned* dims) {
         D.N = (int)dims[0]; D.lo = D.wlo = 0; D.hi = D.whi = D.N;
         this->unknowns.resize(2);
@@ -387,11 +308,10 @@ struct ArapOps : EnergyOps<T> {
         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         OPT_CUDA_CHECK(cudaMalloc((void**)&D.pack, sizeof(ArapPack<T>) * (size_t)D.N));
         OPT_CUDA_CHECK(cudaMalloc((void**)&outStart, sizeof(int) * (D.N + 2))); OPT_CUDA_CHECK(cudaMalloc((void**)&inStart, sizeof(int) * (D.N + 2)));
-        if (factored) OPT_CUDA_CHECK(cudaMalloc((void**)&dirQ, sizeof(ArapQ<T>) * (size_t)D.N));   // up front: no allocation inside a stream capture
     }
-    ~ArapOps() override { for (void* q : { (void*)D.pack, (void*)outStart, (void*)outNbr, (void*)inStart, (void*)inNbr, (void*)keysTmp, cubTemp, (void*)dirQ }) if (q) cudaFree(q); }
+    ~ArapOps() override { for (void* q : { (void*)D.pack, (void*)outStart, (void*)outNbr, (void*)inStart, (void*)inNbr, (void*)keysTmp, cubTemp }) if (q) cudaFree(q); }
     const char* name() const override { return "arap_mesh_deformation"; }
-    unsigned long long captureKey() const override { const void* q = dirQ; return EnergyOps<T>::hashValue(q, EnergyOps<T>::hashValue(D)); }
+    unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(D); }
     int grid() const { long g = ((long)(D.whi - D.wlo) + kBlock - 1) / kBlock; long cap = (long)sms * 8; if (g > cap) g = cap; if (g > kMaxPartials) g = kMaxPartials; return g < 1 ? 1 : (int)g; }
     void bind(void** q) override {   // positions: arap_mesh_deformation.t:2-8
         D.wf = (T) * (const float*)q[0]; D.w = (T) * (const float*)q[1];
@@ -452,12 +372,6 @@ struct ArapOps : EnergyOps<T> {
         k_arapInit<T><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, rzSlot, this->usePreconditioner ? 1 : 0, delta, r, pre, p);
     }
     void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot, const HaloPlan*) override {
-        if (D.symmetric && factored) {   // symmetric graphs: per-vertex Q pass, then the factored gather (see k_arapApplyJTJSym)
-            k_arapDirQ<T><<<grid(), kBlock, 0, c.stream>>>(D, x, dirQ);
-            if (CtC) k_arapApplyJTJSym<T, true><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, x, dirQ, out, CtC);
-            else k_arapApplyJTJSym<T, false><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, x, dirQ, out, nullptr);
-            return;
-        }
         if (CtC) k_arapApplyJTJ<T, false, true><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, 0, 0, x, nullptr, nullptr, out, CtC);
         else k_arapApplyJTJ<T, false, false><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, 0, 0, x, nullptr, nullptr, out, nullptr);
     }

@@ -66,88 +66,6 @@ __global__ void __launch_bounds__(kBlock) k_rnaApplyJTJ(RnaData<T> D, ReduceWork
     }
     if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
 }
-// PCGStep1 on symmetric graphs, factored form (the derivation is in energy_arap.cu, k_arapApplyJTJSym): the edge rows of this energy are
-// ARAP's, so M_v(d) pA_v = Q_v d with one 3x3 matrix Q_v = sum_k pA_v[k] dR_k(v) per vertex per PCG step, and M_v(d)^T y is the contraction
-// of S_v = sum_edges y d^T with dR_k(v).  A neighbour visit needs U_b, pO_b and Q_b (15 scalars) instead of the 16-scalar pack + pO_b + pA_b
-// and ~45 instead of ~150 floating-point instructions -- in fp64, where both the L1 request rate and the arithmetic bound the direct gather.
-template <class T> struct alignas(16) RnaQ { T q[12]; };
-template <class T> struct RnaDR { T a[9], b[9], g[9]; };
-template <class T> __device__ __forceinline__ RnaDR<T> rnaDR(const RnaPack<T>& s) {
-    const RnaRot<T> R(s);
-    RnaDR<T> D;
-    D.a[0] = T(0); D.a[1] = R.m2; D.a[2] = -R.m1; D.a[3] = T(0); D.a[4] = R.m5; D.a[5] = -R.m4; D.a[6] = T(0); D.a[7] = R.m8; D.a[8] = -R.m7;
-    const T r0 = -s.sb, r1 = s.cb * s.sa, r2 = s.cb * s.ca;
-    D.b[0] = s.cg * r0; D.b[1] = s.cg * r1; D.b[2] = s.cg * r2; D.b[3] = s.sg * r0; D.b[4] = s.sg * r1; D.b[5] = s.sg * r2;
-    D.b[6] = -s.cb; D.b[7] = -s.sb * s.sa; D.b[8] = -s.sb * s.ca;
-    D.g[0] = -R.m3; D.g[1] = -R.m4; D.g[2] = -R.m5; D.g[3] = R.m0; D.g[4] = R.m1; D.g[5] = R.m2; D.g[6] = T(0); D.g[7] = T(0); D.g[8] = T(0);
-    return D;
-}
-template <class T>
-__global__ void __launch_bounds__(kBlock) k_rnaDirQ(RnaData<T> D, const T* __restrict__ x, RnaQ<T>* __restrict__ Q) {
-    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
-        const RnaDR<T> R = rnaDR(D.pack[v]);
-        const RnaV3<T> a = rnaLd3(x + D.offA, v);
-        RnaQ<T> q;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) q.q[i] = a.x * R.a[i] + a.y * R.b[i] + a.z * R.g[i];
-        q.q[9] = q.q[10] = q.q[11] = T(0);
-        Q[v] = q;
-    }
-}
-template <class T, bool LM>
-__global__ void __launch_bounds__(kBlock) k_rnaApplyJTJSym(RnaData<T> D, ReduceWorkspace ws, int dotSlot, const T* __restrict__ x, const RnaQ<T>* __restrict__ Q,
-                                                           T* __restrict__ out, const T* __restrict__ CtC) {
-    T acc = T(0);
-    const T w2 = D.w * D.w;
-    for (int v = D.wlo + blockIdx.x * kBlock + threadIdx.x; v < D.whi; v += gridDim.x * kBlock) {
-        RnaOut<T> o;
-        if (v < D.lo || v >= D.hi) { o.O = RnaV3<T>{ T(0), T(0), T(0) }; o.A = o.O; o.g = T(0); rnaStore(out, D, v, o); continue; }
-        const RnaPack<T> sv = D.pack[v];
-        const long a0 = 3L * v, a1 = D.offA + 3L * v, a2 = D.offG + v;
-        const RnaV3<T> pOv{ x[a0], x[a0 + 1], x[a0 + 2] }, pAv{ x[a1], x[a1 + 1], x[a1 + 2] }; const T pgv = x[a2];
-        const RnaQ<T> Qv = Q[v];
-        RnaV3<T> aO{ T(0), T(0), T(0) };
-        T S[9] = { T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0) };
-        for (int k = D.outStart[v]; k < D.outStart[v + 1]; ++k) {
-            const int b = D.outNbr[k];
-            const RnaPack<T>& sb_ = D.pack[b];
-            const RnaV3<T> d{ sv.ux - sb_.ux, sv.uy - sb_.uy, sv.uz - sb_.uz };
-            const RnaV3<T> pOb = rnaLd3(x, b);
-            const RnaQ<T> Qb = Q[b];
-            const RnaV3<T> e{ pOv.x - pOb.x, pOv.y - pOb.y, pOv.z - pOb.z };
-            const RnaV3<T> qv{ Qv.q[0] * d.x + Qv.q[1] * d.y + Qv.q[2] * d.z, Qv.q[3] * d.x + Qv.q[4] * d.y + Qv.q[5] * d.z, Qv.q[6] * d.x + Qv.q[7] * d.y + Qv.q[8] * d.z };
-            const RnaV3<T> qb{ Qb.q[0] * d.x + Qb.q[1] * d.y + Qb.q[2] * d.z, Qb.q[3] * d.x + Qb.q[4] * d.y + Qb.q[5] * d.z, Qb.q[6] * d.x + Qb.q[7] * d.y + Qb.q[8] * d.z };
-            const RnaV3<T> y{ e.x - qv.x, e.y - qv.y, e.z - qv.z };
-            aO.x += y.x + (e.x - qb.x); aO.y += y.y + (e.y - qb.y); aO.z += y.z + (e.z - qb.z);
-            S[0] += y.x * d.x; S[1] += y.x * d.y; S[2] += y.x * d.z;
-            S[3] += y.y * d.x; S[4] += y.y * d.y; S[5] += y.y * d.z;
-            S[6] += y.z * d.x; S[7] += y.z * d.y; S[8] += y.z * d.z;
-        }
-        const RnaDR<T> R = rnaDR(sv);
-        T ca = T(0), cb = T(0), cg = T(0);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { ca += R.a[i] * S[i]; cb += R.b[i] * S[i]; cg += R.g[i] * S[i]; }
-        o.O = RnaV3<T>{ w2 * aO.x, w2 * aO.y, w2 * aO.z };
-        o.A = RnaV3<T>{ -(w2 * ca), -(w2 * cb), -(w2 * cg) };
-        o.g = T(0);
-        if (sv.tgt != T(0)) {   // r_plane and r_conf (as rnaGather<T, 0>)
-            const RnaV3<T> a1O{ D.wf * sv.g * sv.nx, D.wf * sv.g * sv.ny, D.wf * sv.g * sv.nz };
-            const T a1g = D.wf * sv.s, a2g = T(-2) * D.wc * sv.g;
-            const T m = sv.tgt;
-            const T y1 = a1O.x * pOv.x + a1O.y * pOv.y + a1O.z * pOv.z + a1g * pgv, y2 = a2g * pgv;
-            o.O.x += m * (a1O.x * y1); o.O.y += m * (a1O.y * y1); o.O.z += m * (a1O.z * y1);
-            o.g += m * (a1g * y1 + a2g * y2);
-        }
-        if (LM) {
-            o.O.x += CtC[a0] * pOv.x; o.O.y += CtC[a0 + 1] * pOv.y; o.O.z += CtC[a0 + 2] * pOv.z;
-            o.A.x += CtC[a1] * pAv.x; o.A.y += CtC[a1 + 1] * pAv.y; o.A.z += CtC[a1 + 2] * pAv.z;
-            o.g += CtC[a2] * pgv;
-        }
-        acc += rnaDot(pOv, o.O) + rnaDot(pAv, o.A) + pgv * o.g;
-        rnaStore(out, D, v, o);
-    }
-    if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
-}
 template <class T, bool MODEL>
 __global__ void __launch_bounds__(kBlock) k_rnaCost(RnaData<T> D, ReduceWorkspace ws, int slot, const T* __restrict__ delta) {
     T acc = T(0);
@@ -192,7 +110,6 @@ struct RnaOps : EnergyOps<T> {
     void* cubTemp = nullptr; size_t cubBytes = 0; int capE = 0;
     bool csrValid = false, packValid = false;
     int sms = 148;
-    RnaQ<T>* dirQ = nullptr; bool factored = !getenv("OPTB_RNA_NO_FACTORED");   // factored J^T J on symmetric graphs (A/B: the direct merged gather)
     RnaOps(const unsigned* dims) {
         D.N = (int)dims[0]; D.lo = D.wlo = 0; D.hi = D.whi = D.N;
         this->unknowns.resize(3);
@@ -206,11 +123,10 @@ struct RnaOps : EnergyOps<T> {
         int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         OPT_CUDA_CHECK(cudaMalloc((void**)&D.pack, sizeof(RnaPack<T>) * (size_t)D.N));
         OPT_CUDA_CHECK(cudaMalloc((void**)&outStart, sizeof(int) * (D.N + 2))); OPT_CUDA_CHECK(cudaMalloc((void**)&inStart, sizeof(int) * (D.N + 2)));
-        if (factored) OPT_CUDA_CHECK(cudaMalloc((void**)&dirQ, sizeof(RnaQ<T>) * (size_t)D.N));   // up front: no allocation inside a stream capture
     }
-    ~RnaOps() override { for (void* q : { (void*)D.pack, (void*)outStart, (void*)outNbr, (void*)inStart, (void*)inNbr, (void*)keysTmp, cubTemp, (void*)dirQ }) if (q) cudaFree(q); }
+    ~RnaOps() override { for (void* q : { (void*)D.pack, (void*)outStart, (void*)outNbr, (void*)inStart, (void*)inNbr, (void*)keysTmp, cubTemp }) if (q) cudaFree(q); }
     const char* name() const override { return "robust_nonrigid_alignment"; }
-    unsigned long long captureKey() const override { const void* q = dirQ; return EnergyOps<T>::hashValue(q, EnergyOps<T>::hashValue(D)); }
+    unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(D); }
     int grid() const { long g = ((long)(D.whi - D.wlo) + kBlock - 1) / kBlock; long cap = (long)sms * 8; if (g > cap) g = cap; if (g > kMaxPartials) g = kMaxPartials; return g < 1 ? 1 : (int)g; }
     void bind(void** q) override {   // positions: robust_nonrigid_alignment.t:5-13
         D.wf = (T) * (const float*)q[0]; D.w = (T) * (const float*)q[1];
@@ -278,12 +194,6 @@ struct RnaOps : EnergyOps<T> {
         k_rnaInit<T><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, rzSlot, this->usePreconditioner ? 1 : 0, delta, r, pre, p);
     }
     void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot, const HaloPlan*) override {
-        if (D.symmetric && factored) {   // per-vertex Q pass, then the factored gather
-            k_rnaDirQ<T><<<grid(), kBlock, 0, c.stream>>>(D, x, dirQ);
-            if (CtC) k_rnaApplyJTJSym<T, true><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, x, dirQ, out, CtC);
-            else k_rnaApplyJTJSym<T, false><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, x, dirQ, out, nullptr);
-            return;
-        }
         if (CtC) k_rnaApplyJTJ<T, true><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, x, out, CtC);
         else k_rnaApplyJTJ<T, false><<<grid(), kBlock, 0, c.stream>>>(D, c.ws, dotSlot, x, out, nullptr);
     }

@@ -40,19 +40,6 @@ def test_rna_unmerged_gather_matches_oracle(built):
         lines.append(f"g.test_kernel_parity(None, 'robust_nonrigid_alignment', {dp})")
         lines.append(f"g.test_solve_parity(None, 'robust_nonrigid_alignment', 'LMGPU', {dp})")
     _child("\n".join(lines), "UNMERGED_OK", switch="OPTB_RNA_NO_SYMMETRIC")
-    _child("\n".join(lines), "DIRECT_OK", switch="OPTB_RNA_NO_FACTORED")      # the direct merged gather instead of the factored form (the default)
-
-
-def test_arap_direct_gather_matches_oracle(built):
-    """arap_mesh_deformation's J^T J on symmetric graphs runs in a factored form (per-vertex Q = sum_k pA_k dR_k, then ~45 instructions per
-    neighbour visit); OPTB_ARAP_NO_FACTORED=1 keeps the direct merged gather and OPTB_ARAP_NO_SYMMETRIC=1 the two-loop form that arbitrary
-    graphs take -- the default is checked by tests/test_gpu_generic_energies.py, these two here"""
-    lines = []
-    for dp in (False, True):
-        lines.append(f"g.test_kernel_parity(None, 'arap_mesh_deformation', {dp})")
-        lines.append(f"g.test_solve_parity(None, 'arap_mesh_deformation', 'gaussNewtonGPU', {dp})")
-    _child("\n".join(lines), "DIRECT_OK", switch="OPTB_ARAP_NO_FACTORED")
-    _child("\n".join(lines), "TWO_LOOP_OK", switch="OPTB_ARAP_NO_SYMMETRIC")
 
 
 def test_hand_written_and_generic_agree(built):

@@ -130,10 +130,13 @@ def test_single_reduction_loop_parity(built, dp, k, W, H, tile):
     s.step(dev); o.step(host)
     assert s.launches_last_step() <= 3, s.launches_last_step()      # PCGInit1 + ONE loop kernel: the single-reduction path was really taken
     tol = 1e-9 if dp else (3e-4 if k <= 7 else 2e-3)
+    r0max = float(np.abs(o.eval_jtf(workloads.clone_params(host))[1]).max())
     for name in ("delta", "r", "z", "Ap_X"):
         a = s.read_vector(name); b = _oracle_flat(s, o.get_vector(name), N)
         scale = max(1e-30, np.abs(b).max())
-        assert np.abs(a - b).max() <= tol * scale, (name, k, float(np.abs(a - b).max()), float(scale))
+        # r, z = pre r and Ap are differences of terms of size |J^T F|: once PCG has shrunk them the fp32 floor is a few ulp of THAT scale
+        floor = 0.0 if (dp or name == "delta") else 2e-5 * r0max
+        assert np.abs(a - b).max() <= max(tol * scale, floor), (name, k, float(np.abs(a - b).max()), float(scale), r0max)
 
 
 def test_single_reduction_loop_solve(built):

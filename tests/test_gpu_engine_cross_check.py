@@ -42,6 +42,16 @@ def test_rna_unmerged_gather_matches_oracle(built):
     _child("\n".join(lines), "UNMERGED_OK", switch="OPTB_RNA_NO_SYMMETRIC")
 
 
+def test_arap_two_loop_gather_matches_oracle(built):
+    """arap_mesh_deformation's gather merges an edge with its reverse on symmetric graphs; OPTB_ARAP_NO_SYMMETRIC=1 keeps the two-loop form
+    that arbitrary graphs take (the default is checked by tests/test_gpu_generic_energies.py)"""
+    lines = []
+    for dp in (False, True):
+        lines.append(f"g.test_kernel_parity(None, 'arap_mesh_deformation', {dp})")
+        lines.append(f"g.test_solve_parity(None, 'arap_mesh_deformation', 'gaussNewtonGPU', {dp})")
+    _child("\n".join(lines), "TWO_LOOP_OK", switch="OPTB_ARAP_NO_SYMMETRIC")
+
+
 def test_hand_written_and_generic_agree(built):
     _child("""
 import numpy as np

@@ -37,6 +37,7 @@ enum Scalar : int {
     kQ = 5,         // q (LM)
     kQPrev = 6,     // previous q (LM zeta test on device)
     kFlags = 7,     // device-side control word (LM early-out), stored as a double 0/1
+    kRadius = 10,   // LM trust-region radius of the current nonlinear iteration (host decides, kernels read it here: the iteration graph stays the same)
     kNumScalars = 16
 };
 

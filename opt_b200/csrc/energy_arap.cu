@@ -311,6 +311,7 @@ struct ArapOps : EnergyOps<T> {
     }
     ~ArapOps() override { for (void* q : { (void*)D.pack, (void*)outStart, (void*)outNbr, (void*)inStart, (void*)inNbr, (void*)keysTmp, cubTemp }) if (q) cudaFree(q); }
     const char* name() const override { return "arap_mesh_deformation"; }
+    bool capturable() const override { return csrValid; }   // the neighbour lists are built (with a read-back) at the first use after Opt_ProblemInit
     unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(D); }
     int grid() const { long g = ((long)(D.whi - D.wlo) + kBlock - 1) / kBlock; long cap = (long)sms * 8; if (g > cap) g = cap; if (g > kMaxPartials) g = kMaxPartials; return g < 1 ? 1 : (int)g; }
     void bind(void** q) override {   // positions: arap_mesh_deformation.t:2-8

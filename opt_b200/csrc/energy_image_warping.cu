@@ -1255,6 +1255,7 @@ struct ImageWarpingOps : EnergyOps<T> {
     }
     ~ImageWarpingOps() override { cudaFree(D.geom); cudaFree(D.flags); if (loopSync) cudaFree(loopSync); if (llWords) cudaFree(llWords); if (tileWords) cudaFree(tileWords); if (cgWords) cudaFree(cgWords); if (edgeLL) cudaFree(edgeLL); }
     const char* name() const override { return "image_warping"; }
+    bool capturable() const override { return true; }
     unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(D); }
     int upperRows = 0, lowerRows = 0;
     bool setSlab(int ownedBegin, int ownedEnd, int up, int dn) override {

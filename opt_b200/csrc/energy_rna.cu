@@ -126,6 +126,7 @@ struct RnaOps : EnergyOps<T> {
     }
     ~RnaOps() override { for (void* q : { (void*)D.pack, (void*)outStart, (void*)outNbr, (void*)inStart, (void*)inNbr, (void*)keysTmp, cubTemp }) if (q) cudaFree(q); }
     const char* name() const override { return "robust_nonrigid_alignment"; }
+    bool capturable() const override { return csrValid; }
     unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(D); }
     int grid() const { long g = ((long)(D.whi - D.wlo) + kBlock - 1) / kBlock; long cap = (long)sms * 8; if (g > cap) g = cap; if (g > kMaxPartials) g = kMaxPartials; return g < 1 ? 1 : (int)g; }
     void bind(void** q) override {   // positions: robust_nonrigid_alignment.t:5-13

@@ -202,6 +202,7 @@ struct SfsOps : EnergyOps<T> {
     int tilesX = 0, numTiles = 0, gridTiled = 1; bool tiled = true;
     ~SfsOps() override { cudaFree(P.B); cudaFree(P.dB); cudaFree(P.cR); cudaFree(P.cC); cudaFree(P.fl); }
     const char* name() const override { return "shape_from_shading"; }
+    bool capturable() const override { return true; }
     unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(P); }
     void bind(void** q) override {   // positions: shape_from_shading.t:5-28 (all scalar Params are float, cast to opt_float on use, o.t:1699)
         auto f = [&](int k) { return (T) * (const float*)q[k]; };

@@ -268,7 +268,10 @@ template <class T> __global__ void __launch_bounds__(kBlock) k_copy(long n, T* _
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, WindowRanges win, ReduceWorkspace ws, OwnedRanges own, int rzSlot, T* __restrict__ CtC, T* __restrict__ SSq,
                                                                T* __restrict__ pre, const T* __restrict__ r, T* __restrict__ b, T* __restrict__ p,
-                                                               const T* __restrict__ delta, T radius, T minDiag, T maxDiag) {
+                                                               const T* __restrict__ delta, T minDiag, T maxDiag) {
+    // the trust-region radius of this nonlinear iteration lives in the plan's scalar block (written by the host before the iteration): the
+    // captured iteration graph is the same for every radius.  CtC arrives unscaled (diag J^T J) and gets its 1/radius here (:616-622).
+    const T radius = (T)ws.scalars[kRadius], invRadius = T(1) / radius;
     T accD = T(0), accQ = T(0);
     for (long j = (long)blockIdx.x * kBlock + threadIdx.x; j < n; j += (long)gridDim.x * kBlock) {
         const long i = win.map(j);
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(kBlock) k_lmFinalizeDiagonal(long n, WindowRan
         T ssq = SSq[i];
         if (preIn > T(0) && !(ssq > T(0))) { ssq = preIn; SSq[i] = ssq; }
         if (preIn > T(0) && ssq > T(0)) {
-            T unclamped = CtC[i];
+            T unclamped = CtC[i] * invRadius;
             T invS = T(1) / ssq;
             T clampMul = invS / radius;
             T mn = minDiag * clampMul, mx = maxDiag * clampMul;
@@ -412,6 +415,7 @@ struct Plan : PlanBase {
         if (const char* s = getenv("OPTB_PDL")) usePdl = atoi(s) != 0;
         persistentMode = -1; if (const char* s = getenv("OPTB_PERSISTENT")) persistentMode = atoi(s) != 0 ? 1 : 0;
         if (const char* s = getenv("OPTB_SYNC_STEPS")) asyncSteps = atoi(s) == 0;
+        if (getenv("OPTB_NO_ITER_GRAPH")) useIterGraph = false;
         // The reference's harness always asks for the timing table (examples/shared/OptSolver.h:47-48), so the flag alone must
         // not cost the fast path: by default the table has one row per REGION (PCGInit1, the whole PCG loop, update, cost);
         // OPTB_TIMING_TABLE=1 switches to one row per kernel by issuing the per-step kernels individually.
@@ -422,6 +426,8 @@ struct Plan : PlanBase {
         cudaStreamSynchronize(stream);
         dropTimedLaunches();
         if (loopExec) cudaGraphExecDestroy(loopExec);
+        if (iterExec) cudaGraphExecDestroy(iterExec);
+        if (hRadius) cudaFreeHost(hRadius);
         for (T* v : { delta, r, z, p, p2, Ap, pre, b, Adelta, CtC, SSq, prevX }) if (v) cudaFree(v);
         for (void* q : ipcOpened) cudaIpcCloseMemHandle(q);
         cudaFree(commBlock); cudaFree(dHaloP); cudaFree(dHaloZ); cudaFree(dHaloD); cudaFree(dPeerTable);
@@ -721,7 +727,7 @@ struct Plan : PlanBase {
             T* pf = nullptr;
             if (world > 1 && !pHaloFresh) { exchangeHalo(haloP, p); pHaloFresh = true; }   // the multi-rank form stages p's halo rows from memory
             if (E->pcgLoop(ctx(), L, persistentMode > 0, delta, r, z, p, p2, Ap, pre, &pf, world > 1 ? &haloZ : nullptr)) {
-                pFinal = pf; ++launches;
+                pFinal = pf; ++launches; lastLoopPersistent = true;
                 // the update of X on my halo rows must equal the owner's (no X exchange): the collective kernel writes delta
                 // on owned rows only (the single-reduction form keeps no shadow copy of the neighbour's boundary row), so fetch the halo rows of delta
                 if (world > 1) exchangeHalo(haloD, delta);
@@ -729,6 +735,7 @@ struct Plan : PlanBase {
                 return;
             }
         }
+        lastLoopPersistent = false;
         if (useGraph && L > 0) {
             // The captured kernel nodes hold their arguments BY VALUE (weights, caller pointers, plan-owned buffers the energy may have
             // reallocated in bind()/pcgInit(), q_tolerance, the reset period): re-capture whenever any of that differs from what the
@@ -809,6 +816,80 @@ struct Plan : PlanBase {
     // OPTB_PERSISTENT=0: always the CUDA graph of per-step kernels.
     int persistentMode = 0;
 
+    // ---- one nonlinear iteration as ONE graph launch (from the second iteration of a solve on, for energies whose entry points are pure
+    // launches): PCGInit1, the LM diagonal kernels, the whole PCG loop, model cost, update, precompute, cost and the read-back of the scalars.
+    // What changes from iteration to iteration (the trust-region radius) is read from device memory, so the graph is re-captured only when
+    // the fingerprint of its by-value arguments changes (as for the loop graph).  The reference issues ~15 + 3 L launches and one blocking
+    // copy per PCG step here; for shape_from_shading (L = 10) the launches outside the loop were 45 % of an iteration.
+    cudaGraphExec_t iterExec = nullptr; unsigned long long iterKey = 0; int iterLaunchCount = 0; T* iterPFinal = nullptr;
+    bool useIterGraph = true, lastLoopPersistent = false;
+    double* hRadius = nullptr;
+    void uploadRadius() {
+        if (!hRadius) OPT_CUDA_CHECK(cudaMallocHost((void**)&hRadius, sizeof(double)));
+        *hRadius = (double)trust_region_radius;
+        OPT_CUDA_CHECK(cudaMemcpyAsync(ws.scalars + kRadius, hRadius, sizeof(double), cudaMemcpyHostToDevice, stream));
+    }
+    void enqueueIterationForCapture(int L) {   // the launch sequence of step() without its timing hooks; nIter >= 1 (no PCGSaveSSq)
+        LaunchCtx c = ctx();
+        if (lm) OPT_CUDA_CHECK(cudaMemcpyAsync(ws.scalars + kRadius, hRadius, sizeof(double), cudaMemcpyHostToDevice, stream));
+        E->pcgInit(c, delta, r, pre, p, kRz0); ++launches;
+        if (lm) {
+            E->computeCtC(c, CtC, T(1)); ++launches;
+            k_lmFinalizeDiagonal<T><<<gridStream, kBlock, 0, stream>>>(winScalar.n ? winScalar.total : n, winScalar, ws, ownScalar, kRz0, CtC, SSq, pre, r, b, p, delta, min_lm_diagonal, max_lm_diagonal); ++launches;
+            k_copyScalar<<<1, 1, 0, stream>>>(ws, kQPrev, kQ);
+            k_setScalar<<<1, 1, 0, stream>>>(ws, kFlags, 0.0); launches += 2;
+        }
+        pHaloFresh = false;
+        if (!(world > 1 && loopFuses() && E->inKernelHalo() && L > 0)) { exchangeHalo(haloP, p); pHaloFresh = true; }
+        const bool fuse = loopFuses();
+        OPT_CUDA_CHECK(cudaEventRecordWithFlags(evLoop0, stream, cudaEventRecordExternal));
+        emitLoop(L, fuse);   // (the one-kernel loops are not captured: their reduction sequence numbers are launch arguments -- see launchIterationGraph)
+        OPT_CUDA_CHECK(cudaEventRecordWithFlags(evLoop1, stream, cudaEventRecordExternal));
+        if (lm) {
+            E->modelCost(c, delta); ++launches;
+            for (auto& u : E->unknowns) { long cnt = u.elements * u.channels; k_copy<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, prevX + u.offset, (const T*)u.user); ++launches; }
+        }
+        for (auto& u : E->unknowns) { long cnt = u.elements * u.channels; k_axpyInto<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, (T*)u.user, delta + u.offset); ++launches; }
+        E->precompute(c);
+        E->cost(c); ++launches;
+        if (world > 1) { k_finalizeScalars<<<1, 32, 0, stream>>>(ws, (1u << kRz0) | (1u << kRz1) | (1u << kPAp) | (1u << kCost) | (1u << kModelCost) | (1u << kQ)); ++launches; }
+        OPT_CUDA_CHECK(cudaMemcpyAsync(hScalars, ws.scalars, sizeof(double) * kNumScalars, cudaMemcpyDeviceToHost, stream));
+    }
+    // returns false when this iteration has to take the launch-by-launch path
+    bool launchIterationGraph(int L) {
+        if (!useIterGraph || !useGraph || nIter == 0 || timingOn || maxLinIters >= 0 || L <= 0 || !E->capturable()) return false;
+        if (lastLoopPersistent) return false;   // the whole-loop cooperative kernels take their reduction sequence base as a launch argument (a replayed
+                                                // graph would repeat it); they already are one launch per iteration
+        if (world > 1 && multiLoopState < 0) return false;          // the collective decision is taken (with host polling) in the first iteration
+        if (!hRadius) OPT_CUDA_CHECK(cudaMallocHost((void**)&hRadius, sizeof(double)));
+        const bool fuse = loopFuses();
+        unsigned long long key = E->captureKey();
+        { const long v[] = { (long)L, (long)fuse, (long)lm, (long)sp.residual_reset_period, (long)world, (long)rank, (long)persistentMode, (long)multiLoopState, (long)n }; key = EnergyOps<T>::hashBytes(v, sizeof(v), key); }
+        key = EnergyOps<T>::hashValue(sp.q_tolerance, key); key = EnergyOps<T>::hashValue(min_lm_diagonal, key); key = EnergyOps<T>::hashValue(max_lm_diagonal, key);
+        key = EnergyOps<T>::hashValue(winVec, key); key = EnergyOps<T>::hashValue(ownVec, key);
+        if (!iterExec || iterKey != key) {
+            cudaGraph_t g;
+            const int saved = launches;
+            OPT_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            enqueueIterationForCapture(L);
+            OPT_CUDA_CHECK(cudaStreamEndCapture(stream, &g));
+            bool updated = false;
+            if (iterExec) {
+                cudaGraphExecUpdateResultInfo info{};
+                if (cudaGraphExecUpdate(iterExec, g, &info) == cudaSuccess) updated = true;
+                else { cudaGetLastError(); cudaGraphExecDestroy(iterExec); iterExec = nullptr; }
+            }
+            if (!updated) OPT_CUDA_CHECK(cudaGraphInstantiate(&iterExec, g, 0));
+            OPT_CUDA_CHECK(cudaGraphDestroy(g));
+            iterKey = key; iterLaunchCount = launches - saved; launches = saved; iterPFinal = pFinal; ++graphBuilds;
+        }
+        if (lm) *hRadius = (double)trust_region_radius;
+        pFinal = iterPFinal;
+        OPT_CUDA_CHECK(cudaGraphLaunch(iterExec, stream));
+        launches += iterLaunchCount;
+        return true;
+    }
+
     int step(void** params) override {   // :1016-1177
         E->bind(params);
         if (finished || !(nIter < sp.nIterations)) {
@@ -819,13 +900,29 @@ struct Plan : PlanBase {
         enter();
         launches = 0;
         LaunchCtx c = ctx();
+        {
+            int Lg = sp.lIterations;
+            if (!lm && verbosity == 0 && asyncSteps) resolveCost();     // the previous step's value, before its pinned slot is reused
+            if (launchIterationGraph(Lg)) {
+                if (!lm && verbosity == 0 && asyncSteps) {              // GN: the cost stays behind an event (see computeCostAsync)
+                    OPT_CUDA_CHECK(cudaEventRecord(evCost, stream)); costPending = true;
+                    OPT_CUDA_CHECK(cudaEventRecord(evExit, stream)); OPT_CUDA_CHECK(cudaStreamWaitEvent(userStream, evExit, 0));
+                    loopMsPending = true; ++nIter;
+                    return 1;
+                }
+                OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
+                OPT_CUDA_CHECK(cudaEventElapsedTime(&loopMs, evLoop0, evLoop1)); loopMsPending = false;
+                return decide((T)hScalars[kCost], c);
+            }
+        }
         tBegin("PCGInit1");
         E->pcgInit(c, delta, r, pre, p, kRz0); ++launches;          // PCGInit1 (+_Graph,+_Finish)
         tEnd();
         if (lm) {   // :1038-1053
             if (nIter == 0) { k_copy<T><<<gridStream, kBlock, 0, stream>>>(n, SSq, pre); ++launches; }   // PCGSaveSSq
-            E->computeCtC(c, CtC, T(1) / trust_region_radius); ++launches;
-            k_lmFinalizeDiagonal<T><<<gridStream, kBlock, 0, stream>>>(winScalar.n ? winScalar.total : n, winScalar, ws, ownScalar, kRz0, CtC, SSq, pre, r, b, p, delta, trust_region_radius, min_lm_diagonal, max_lm_diagonal); ++launches;
+            uploadRadius();
+            E->computeCtC(c, CtC, T(1)); ++launches;
+            k_lmFinalizeDiagonal<T><<<gridStream, kBlock, 0, stream>>>(winScalar.n ? winScalar.total : n, winScalar, ws, ownScalar, kRz0, CtC, SSq, pre, r, b, p, delta, min_lm_diagonal, max_lm_diagonal); ++launches;
             k_copyScalar<<<1, 1, 0, stream>>>(ws, kQPrev, kQ);          // Q0 = fetchQ
             k_setScalar<<<1, 1, 0, stream>>>(ws, kFlags, 0.0); launches += 2;
         }
@@ -836,7 +933,6 @@ struct Plan : PlanBase {
         runLoop(L);
         if (!timingFine) tEnd();
         if (maxLinIters >= 0) { OPT_CUDA_CHECK(cudaStreamSynchronize(stream)); return 1; }   // debug hook: PCG state left for inspection
-        T model_cost_change = 0;
         if (lm) {   // :1108-1113
             E->modelCost(c, delta); ++launches;
             for (auto& u : E->unknowns) { long cnt = u.elements * u.channels; k_copy<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, prevX + u.offset, (const T*)u.user); ++launches; }   // savePreviousUnknowns
@@ -859,6 +955,11 @@ struct Plan : PlanBase {
         T newCost = computeCost();
         tEnd();    // syncs; hScalars also carries the model cost and the loop timing is complete
         OPT_CUDA_CHECK(cudaEventElapsedTime(&loopMs, evLoop0, evLoop1)); loopMsPending = false;
+        return decide(newCost, c);
+    }
+    // the host side of the nonlinear iteration: accept / reject / trust-region update (:1119-1157), with the cost and model cost already read back
+    int decide(T newCost, const LaunchCtx& c) {
+        T model_cost_change = 0;
         int ret = 1;
         if (lm) {   // :1119-1157
             T model_cost = (T)hScalars[kModelCost];

@@ -119,6 +119,9 @@ struct EnergyOps {
     virtual std::vector<std::pair<long, long>> processScalarRanges() const { return {}; }
     // called at every Opt_ProblemInit: graph indices / masks may have changed since the last solve
     virtual void newSolve() {}
+    // true when, in the current state, none of the per-iteration entry points (pcgInit, precompute, cost, modelCost, computeCtC, applyJTJ,
+    // step3ApplyJTJ, pcgLoop) allocates, synchronises or reads anything back: a whole nonlinear iteration can then be stream-captured
+    virtual bool capturable() const { return false; }
     // Fingerprint of everything the inner-loop kernels (applyJTJ / step3ApplyJTJ) receive BY VALUE or as launch geometry:
     // weights, caller pointers, plan-owned buffers that bind()/pcgInit() may reallocate, residual counts.  The plan compares it
     // (after pcgInit, when all of that is final for the step) with the fingerprint its captured PCG-loop graph was built from and

@@ -105,7 +105,7 @@ def effective_cpus():
     return max(1, n)
 
 
-CPU_ROWS, CPU_STEPS, CPU_REPEATS = 1024, 100, 3      # fixed sample: W_FULL x 1024 slab, 100 PCG steps, best of 3
+CPU_ROWS, CPU_STEPS, CPU_REPEATS = 1024, 100, 5      # fixed sample: W_FULL x 1024 slab, 100 PCG steps, best of 5
 
 
 def _cpu_child(rows, steps, threads, repeats):

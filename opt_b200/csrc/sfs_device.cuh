@@ -152,8 +152,11 @@ template <class T> SFS_HD T sfsCoefS(const SfsData<T>& P, int x, int y, int comp
 template <class T> SFS_HD T sfsFS(const SfsData<T>& P, int x, int y, int comp) {   // value of r_s,comp centred at (x, y)
     const long c = (long)y * P.W + x;
     if (!(P.fl[c] & kSfsFlat)) return T(0);
+    // the five coefficients need the factor of three columns (comp 0) or three rows (comp 1): 3 divisions instead of one per coefficient
+    const T a3[3] = { comp == 0 ? sfsAx(P, x - 1) : (comp == 1 ? sfsAy(P, y - 1) : T(1)), comp == 0 ? sfsAx(P, x) : (comp == 1 ? sfsAy(P, y) : T(1)),
+                      comp == 0 ? sfsAx(P, x + 1) : (comp == 1 ? sfsAy(P, y + 1) : T(1)) };
     T s = T(0);
-    SFS_UNROLL for (int k = 0; k < 5; ++k) s += sfsCoefS(P, x, y, comp, k) * P.X[c + (long)sfsDy(2, k) * P.W + sfsDx(2, k)];
+    SFS_UNROLL for (int k = 0; k < 5; ++k) s += sfsCoefFromA(P, a3[1 + (comp == 1 ? sfsDy(2, k) : sfsDx(2, k))], k) * P.X[c + (long)sfsDy(2, k) * P.W + sfsDx(2, k)];
     return s;
 }
 
@@ -193,15 +196,17 @@ template <class T, int MODE> SFS_HD T sfsGather(const SfsData<T>& P, int x, int 
             acc += a * yv;
         }
     }
-    // r_s (three components): u is dependency k of the row centred at c = u - offset_k, if that centre is flat
+    // r_s (three components): u is dependency k of the row centred at c = u - offset_k, if that centre is flat.  Dependency k of that row
+    // IS u, so its coefficient is built from u's own back-projection factors: two divisions per unknown, not one per (row, component)
     {
+        const T aU[3] = { sfsAx(P, x), sfsAy(P, y), T(1) };
         SFS_UNROLL for (int k = 0; k < 5; ++k) {
             const int cx = x - sfsDx(2, k), cy = y - sfsDy(2, k);
             if (!sfsInImage(P, cx, cy)) continue;
             const long c = (long)cy * P.W + cx;
             if (!(P.fl[c] & kSfsFlat)) continue;
             SFS_UNROLL for (int comp = 0; comp < 3; ++comp) {
-                const T a = sfsCoefS(P, cx, cy, comp, k);
+                const T a = sfsCoefFromA(P, aU[comp], k);
                 if (MODE == 2) { acc += a * a; continue; }
                 T yv;
                 if (MODE == 1) yv = sfsFS(P, cx, cy, comp);

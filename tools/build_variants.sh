@@ -17,6 +17,7 @@ for v in "$@"; do
     th8s3) build th8s3 "-DIW_TH=8 -DIW_STAGES=3 -DIW_STRIP=2";;
     th8s4) build th8s4 "-DIW_TH=8 -DIW_STAGES=4 -DIW_STRIP=2";;
     th16s3) build th16s3 "-DIW_TH=16 -DIW_STAGES=3 -DIW_STRIP=4";;
+    th16s2) build th16s2 "-DIW_TH=16 -DIW_STAGES=2 -DIW_STRIP=4";;
     th16s4) build th16s4 "-DIW_TH=16 -DIW_STAGES=4 -DIW_STRIP=4";;
     th32s2) build th32s2 "-DIW_TH=32 -DIW_STAGES=2 -DIW_STRIP=8";;
     th8s6) build th8s6 "-DIW_TH=8 -DIW_STAGES=6 -DIW_STRIP=2";;

@@ -212,7 +212,10 @@ __global__ void __launch_bounds__(kBlock) k_iwApplyJTJ(IWData<T> D, ReduceWorksp
 #define IW_STAGES 3
 #define IW_STRIP 4
 #endif
-constexpr int kTW = 64, kTH = IW_TH, kStages = IW_STAGES, kStrip = IW_STRIP;
+constexpr int kTW = 64, kTH = IW_TH, kStagesSingle = IW_STAGES, kStagesMulti = 2, kStrip = IW_STRIP;
+// Pipeline depth per use: one GPU = IW_STAGES (3: one CTA per SM, two tiles ahead).  Multi-rank slabs = 2 stages, two CTAs per SM: there the
+// last CTA first pushes the halo rows to the neighbours (NVLink stores + a system-scope release, several microseconds); with one CTA per
+// SM that SM idles meanwhile and its CTA becomes the kernel's straggler (measured at 4 ranks: 50.3 instead of 45.2 us per PCG step).
 // TMA rule (measured, tools/tma_probe.cu): the innermost box coordinate must start on a 16-byte
 // boundary, so 2-channel rows are staged from pixel x0-2 and 1-channel rows from pixel x0-4.
 constexpr int kRowO = 2 * (kTW + 4);      // floats per staged row of a 2-channel image (pixels x0-2 .. x0+TW+1)
@@ -276,7 +279,7 @@ __device__ __forceinline__ void iwPairOne(const IWPoint& i, const IWPoint& j, fl
     Ai = (eix * eix + eiy * eiy) * i.pa - (eix * px + eiy * py);
 }
 
-template <bool FUSE3, bool LM>
+template <bool FUSE3, bool LM, int kStages>
 __global__ void __launch_bounds__(kBlock) k_iwApplyJTJTma(IWData<float> D, const __grid_constant__ IWMaps M, ReduceWorkspace ws, int dotSlot, int rzNew,
                                                           int rzOld, float* __restrict__ pOut, float* __restrict__ out, const float* __restrict__ CtC,
                                                           int tilesX, int numTiles, const float* __restrict__ haloSrc, const HaloPlan* __restrict__ hpp) {
@@ -1167,7 +1170,7 @@ struct ImageWarpingOps : EnergyOps<T> {
     float wFit = 0, wReg = 0;
     int gridInit = 0, gridJTJ = 0, gridJTJF = 0, gridCost = 0;
     // TMA path (fp32, W % 4 == 0): tensor maps are cached per (p vector, z vector) pair
-    bool tmaOk = false; int tmaTilesX = 0, tmaTiles = 0, gridTma = 0, gridTmaF = 0;
+    bool tmaOk = false; int tmaTilesX = 0, tmaTiles = 0, gridTma[2] = { 0, 0 }, gridTmaF[2] = { 0, 0 };   // [0]: multi-rank shape (2 stages), [1]: single GPU (IW_STAGES)
     std::map<std::pair<const void*, const void*>, IWMaps> mapCache;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1221,10 +1224,14 @@ struct ImageWarpingOps : EnergyOps<T> {
             int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, f, kBlock, bytes); if (occ < 1) occ = 1;
             long g = (long)sms * occ; if (g > tmaTiles) g = tmaTiles; if (g > kMaxPartials) g = kMaxPartials; return (int)(g < 1 ? 1 : g);
         };
-        gridTma = prep((const void*)k_iwApplyJTJTma<false, false>, kStages * kStageBytesPlain);
-        prep((const void*)k_iwApplyJTJTma<false, true>, kStages * kStageBytesPlain);
-        gridTmaF = prep((const void*)k_iwApplyJTJTma<true, false>, kStages * kStageBytesFused);
-        prep((const void*)k_iwApplyJTJTma<true, true>, kStages * kStageBytesFused);
+        gridTma[0] = prep((const void*)k_iwApplyJTJTma<false, false, kStagesMulti>, kStagesMulti * kStageBytesPlain);
+        prep((const void*)k_iwApplyJTJTma<false, true, kStagesMulti>, kStagesMulti * kStageBytesPlain);
+        gridTmaF[0] = prep((const void*)k_iwApplyJTJTma<true, false, kStagesMulti>, kStagesMulti * kStageBytesFused);
+        prep((const void*)k_iwApplyJTJTma<true, true, kStagesMulti>, kStagesMulti * kStageBytesFused);
+        gridTma[1] = prep((const void*)k_iwApplyJTJTma<false, false, kStagesSingle>, kStagesSingle * kStageBytesPlain);
+        prep((const void*)k_iwApplyJTJTma<false, true, kStagesSingle>, kStagesSingle * kStageBytesPlain);
+        gridTmaF[1] = prep((const void*)k_iwApplyJTJTma<true, false, kStagesSingle>, kStagesSingle * kStageBytesFused);
+        prep((const void*)k_iwApplyJTJTma<true, true, kStagesSingle>, kStagesSingle * kStageBytesFused);
         tmaOk = true;
     }
     ImageWarpingOps(const unsigned* dims) {
@@ -1508,8 +1515,13 @@ struct ImageWarpingOps : EnergyOps<T> {
             if (tmaOk) {
                 const IWMaps& m = mapsFor(x, nullptr);
                 const HaloPlan* hp = halo;
-                if (CtC) k_iwApplyJTJTma<false, true><<<gridTma, kBlock, kStages * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, CtC, tmaTilesX, tmaTiles, x, hp);
-                else launchPdl(k_iwApplyJTJTma<false, false>, gridTma, kBlock, (size_t)(kStages * kStageBytesPlain), c.stream, c.pdl, D, m, c.ws, dotSlot, 0, 0, (float*)nullptr, out, (const float*)nullptr, tmaTilesX, tmaTiles, (const float*)x, hp);
+                if (upperRows > 0 || lowerRows > 0) {
+                    if (CtC) k_iwApplyJTJTma<false, true, kStagesMulti><<<gridTma[0], kBlock, kStagesMulti * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, CtC, tmaTilesX, tmaTiles, x, hp);
+                    else launchPdl(k_iwApplyJTJTma<false, false, kStagesMulti>, gridTma[0], kBlock, (size_t)(kStagesMulti * kStageBytesPlain), c.stream, c.pdl, D, m, c.ws, dotSlot, 0, 0, (float*)nullptr, out, (const float*)nullptr, tmaTilesX, tmaTiles, (const float*)x, hp);
+                } else {
+                    if (CtC) k_iwApplyJTJTma<false, true, kStagesSingle><<<gridTma[1], kBlock, kStagesSingle * kStageBytesPlain, c.stream>>>(D, m, c.ws, dotSlot, 0, 0, nullptr, out, CtC, tmaTilesX, tmaTiles, x, hp);
+                    else launchPdl(k_iwApplyJTJTma<false, false, kStagesSingle>, gridTma[1], kBlock, (size_t)(kStagesSingle * kStageBytesPlain), c.stream, c.pdl, D, m, c.ws, dotSlot, 0, 0, (float*)nullptr, out, (const float*)nullptr, tmaTilesX, tmaTiles, (const float*)x, hp);
+                }
                 return;
             }
         }
@@ -1522,8 +1534,13 @@ struct ImageWarpingOps : EnergyOps<T> {
             if (tmaOk) {
                 const IWMaps& m = mapsFor(pOld, z);
                 const HaloPlan* hp = halo;
-                if (CtC) k_iwApplyJTJTma<true, true><<<gridTmaF, kBlock, kStages * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, CtC, tmaTilesX, tmaTiles, z, hp);
-                else launchPdl(k_iwApplyJTJTma<true, false>, gridTmaF, kBlock, (size_t)(kStages * kStageBytesFused), c.stream, c.pdl, D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, (const float*)nullptr, tmaTilesX, tmaTiles, (const float*)z, hp);
+                if (upperRows > 0 || lowerRows > 0) {
+                    if (CtC) k_iwApplyJTJTma<true, true, kStagesMulti><<<gridTmaF[0], kBlock, kStagesMulti * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, CtC, tmaTilesX, tmaTiles, z, hp);
+                    else launchPdl(k_iwApplyJTJTma<true, false, kStagesMulti>, gridTmaF[0], kBlock, (size_t)(kStagesMulti * kStageBytesFused), c.stream, c.pdl, D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, (const float*)nullptr, tmaTilesX, tmaTiles, (const float*)z, hp);
+                } else {
+                    if (CtC) k_iwApplyJTJTma<true, true, kStagesSingle><<<gridTmaF[1], kBlock, kStagesSingle * kStageBytesFused, c.stream>>>(D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, CtC, tmaTilesX, tmaTiles, z, hp);
+                    else launchPdl(k_iwApplyJTJTma<true, false, kStagesSingle>, gridTmaF[1], kBlock, (size_t)(kStagesSingle * kStageBytesFused), c.stream, c.pdl, D, m, c.ws, dotSlot, rzNew, rzOld, pNew, out, (const float*)nullptr, tmaTilesX, tmaTiles, (const float*)z, hp);
+                }
                 return true;
             }
         }

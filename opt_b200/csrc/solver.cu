@@ -944,9 +944,11 @@ struct Plan : PlanBase {
         }
         tEnd();
         E->precompute(c);
-        if (!lm && verbosity == 0 && !timingOn && asyncSteps) {   // GN: nothing below needs the cost on the host
-            resolveCost();          // the previous step's value, before its pinned slot is reused
+        if (!lm && verbosity == 0 && asyncSteps) {   // GN: nothing below needs the cost on the host (the timing table, when asked for, is
+            resolveCost();                           // assembled from event pairs when the solve ends)
+            tBegin("computeCost");
             computeCostAsync();
+            tEnd();
             loopMsPending = true;
             ++nIter;
             return 1;

@@ -200,3 +200,40 @@ def test_tile_scheme_equals_global_pcg(W, H, world, tw, th):
         got = R.delta
         want = ref[R.lo:R.hi]
         assert np.abs(got - want).max() <= 1e-11 * scale, (R.lo, R.hi, np.abs(got - want).max(), scale)
+
+
+def test_single_reduction_recurrences_equal_standard_pcg():
+    """the arrangement of k_iwCgLoopTile (matvec on z, gamma = r.z and delta = w.z in one reduction, alpha = gamma / (delta - beta gamma /
+    alpha_old), A p carried as s = w + beta s, the loop ending after the L-th update) reproduces the reference's PCG iterates
+    (solverGPUGaussNewton.t:421-550, same guards) in exact arithmetic -- checked in fp64 on a random SPD system with a Jacobi preconditioner"""
+    rng = np.random.default_rng(11)
+    n, L = 120, 25
+    B = rng.normal(size=(n, n)); A = B @ B.T + n * np.eye(n)
+    b = rng.normal(size=n); M = 1.0 / (1.0 + np.sqrt(np.diag(A))) ** 2        # the CERES-style guarded inverse the solver uses
+    # reference arrangement
+    x = np.zeros(n); r = b.copy(); z = M * r; p = z.copy(); rz = r @ z
+    for _ in range(L):
+        Ap = A @ p; den = p @ Ap
+        alpha = rz / den if den > 0 else 0.0
+        x = x + alpha * p; r = r - alpha * Ap; z = M * r; rz_new = r @ z
+        beta = rz_new / rz if rz > 0 else 0.0
+        p = z + beta * p; rz = rz_new
+    # single-reduction arrangement
+    xc = np.zeros(n); rc = b.copy(); u = M * rc; w = A @ u
+    gam, dlt = rc @ u, w @ u
+    alpha = gam / dlt if dlt > 0 else 0.0; beta = 0.0
+    pc = np.zeros(n); s = np.zeros(n)
+    for it in range(L):
+        pc = u + beta * pc; s = w + beta * s
+        xc = xc + alpha * pc; rc = rc - alpha * s
+        u = M * rc
+        if it + 1 == L:
+            break
+        w = A @ u
+        g_new, d_new = rc @ u, w @ u
+        beta = g_new / gam if gam > 0 else 0.0
+        den = d_new - beta * g_new / alpha if alpha != 0 else d_new
+        alpha = g_new / den if den > 0 else 0.0
+        gam = g_new
+    assert np.linalg.norm(xc - x) <= 1e-9 * np.linalg.norm(x)
+    assert np.linalg.norm(rc - r) <= 1e-9 * np.linalg.norm(b)

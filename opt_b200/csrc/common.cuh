@@ -536,7 +536,9 @@ __device__ __forceinline__ double gridAllReduceLLMulti(double v, unsigned long l
 // together; tile edges move as LL data words, so the reduction carries no ordering duty and contains no fence at all).
 // `words` = [2 parities][kMaxLLCtas + 1][4]: per CTA slot the lo/hi words of both values, slot kMaxLLCtas = the result (single GPU);
 // MULTI: the rank partials go to mailbox slots `slot` and `slot + 1` of every rank (4 * world words = one warp at world = 8).
-template <int NT, bool MULTI>
+// RELEASE: the CTA's earlier global stores are visible to the other CTAs of THIS GPU after the call (the three device-scope fences of
+// gridAllReduceLL's releaseData; single GPU use -- k_sfsLoopResident publishes its tile-edge z that way).
+template <int NT, bool MULTI, bool RELEASE = false>
 __device__ __forceinline__ void gridAllReduce2LL(double v0, double v1, unsigned long long* words, unsigned long long* arrivals, unsigned long long k,
                                                  const CommView& comm, int slot, double& o0, double& o1) {
     static_assert(NT >= kMaxLLCtas && NT % 32 == 0 && NT / 32 <= 32, "one polling thread per CTA slot");
@@ -560,7 +562,7 @@ __device__ __forceinline__ void gridAllReduce2LL(double v0, double v1, unsigned 
         double t0 = lane < NT / 32 ? s_w[0][lane] : 0.0, t1 = lane < NT / 32 ? s_w[1][lane] : 0.0;
         t0 = warpSum(t0); t1 = warpSum(t1);
         if (lane < 4) stVolatileU64(row + 4 * blockIdx.x + lane, word(t0, t1, lane));
-        if (lane == 0) { const unsigned long long prev = atomicAdd(arrivals, 1ull); s_last = (prev + 1ull == (unsigned long long)gridDim.x * k); }
+        if (lane == 0) { if (RELEASE) __threadfence(); const unsigned long long prev = atomicAdd(arrivals, 1ull); s_last = (prev + 1ull == (unsigned long long)gridDim.x * k); }
     }
     __syncthreads();
     if (s_last) {
@@ -580,6 +582,7 @@ __device__ __forceinline__ void gridAllReduce2LL(double v0, double v1, unsigned 
             double u0 = 0.0, u1 = 0.0;
             for (unsigned i = lane; i < gridDim.x; i += 32) { u0 += s_p[0][i]; u1 += s_p[1][i]; }   // fixed order
             u0 = warpSum(u0); u1 = warpSum(u1);
+            if (RELEASE) __threadfence();   // cumulativity: the arrivals observed above (and the stores they release) precede the result
             if (MULTI) { if (lane < 4 * comm.world) stVolatileU64(comm.peerWords[lane >> 2] + mailboxWord(slot + ((lane >> 1) & 1), k, comm.rank) + (lane & 1), word(u0, u1, lane & 3)); }
             else if (lane < 4) stVolatileU64(row + 4 * kMaxLLCtas + lane, word(u0, u1, lane));
         }
@@ -602,7 +605,7 @@ __device__ __forceinline__ void gridAllReduce2LL(double v0, double v1, unsigned 
             sum0 += __longlong_as_double((long long)((unsigned long long)a | ((unsigned long long)b << 32)));
             sum1 += __longlong_as_double((long long)((unsigned long long)c | ((unsigned long long)d << 32)));
         }
-        if (lane == 0) { s_v[0] = sum0; s_v[1] = sum1; }
+        if (lane == 0) { if (RELEASE) __threadfence(); s_v[0] = sum0; s_v[1] = sum1; }   // acquire side: loads issued after the call see the other CTAs' stores
     }
     __syncthreads();
     o0 = s_v[0]; o1 = s_v[1];

@@ -11,10 +11,16 @@
 // Per PCG step the gather reads p, the 10 row coefficients and the flag byte of a pixel's neighbourhood (L1/L2 hits after
 // the first touch): ~53 B/pixel from HBM against the 208+ B/pixel of the cached-Jacobian engine this energy used before.
 // Default for this energy (OPTB_GENERIC=1 selects the cached-Jacobian engine instead); parity: tests/test_gpu_generic_energies.py.
+// Two further kernels work on tiles through the host/device functions of sfs_tile.cuh (run on the CPU by tests/test_sfs_host_parity.py):
+//   k_sfsInitTiled      PCGInit1 + PCGComputeCtC + PCGFinalizeDiagonal (+ the Q0 / flag scalars) in ONE pass: the LM iteration's head
+//                       was five launches (38 + 17 + 17 us + two one-thread kernels at 640x480)
+//   k_sfsLoopResident   the PCG loop up to the first residual reset as ONE cooperative kernel, the tile's direction, coefficients and
+//                       flags in shared memory, delta / r / b / CtC / z / Ap in registers (640x480: 140 tiles of 64x35 on 148 SMs)
 #include <algorithm>
 #include <type_traits>
 #include "solver.h"
 #include "sfs_device.cuh"
+#include "sfs_tile.cuh"
 
 namespace optb {
 
@@ -30,6 +36,19 @@ template <class T>
 __global__ void __launch_bounds__(kBlock) k_sfsBuildRows(SfsData<T> P) {
     const long N = (long)P.W * P.H;
     for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < N; i += (long)gridDim.x * kBlock) sfsBuildRows(P, (int)(i % P.W), (int)(i / P.W));
+}
+// precompute pass 2 + computeCost in one launch: the cost of the rows centred at a pixel needs exactly what pass 2 has at hand (pass 1 of
+// the pixel and of its right / lower neighbours)
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_sfsBuildRowsCost(SfsData<T> P, ReduceWorkspace ws, int slot) {
+    const long N = (long)P.W * P.H;
+    T acc = T(0);
+    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < N; i += (long)gridDim.x * kBlock) {
+        const int x = (int)(i % P.W), y = (int)(i / P.W);
+        sfsBuildRows(P, x, y);
+        acc += sfsCostAt<T, false>(P, x, y, nullptr);
+    }
+    gridReduceTo<kBlock>((double)acc, ws, slot);
 }
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_sfsInit(SfsData<T> P, int usePre, ReduceWorkspace ws, int rzSlot, T* __restrict__ delta, T* __restrict__ r,
@@ -162,6 +181,121 @@ __global__ void __launch_bounds__(kBlock) k_sfsApplyJTJTiled(SfsData<T> P, Reduc
     }
     if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
 }
+// ------------------------------------------------------------------------------------ PCGInit1 (+ LM head), tiled
+// One pass over 32x8 tiles: the residual of every row centred in tile + 1-pixel ring is formed ONCE (the per-pixel k_sfsInit forms each
+// 5 / 15 times), then every pixel gathers -J^T F and diag J^T J from shared memory and finishes PCGInit1; LM: PCGSaveSSq (first
+// iteration), PCGComputeCtC and PCGFinalizeDiagonal are applied to the pixel right away and Q0 = q = 0 and the early-out flag are reset,
+// i.e. k_sfsInit + k_sfsCtC + k_lmFinalizeDiagonal + k_copyScalar + k_setScalar of the launch-by-launch path (solver.cu).
+template <class T, bool LM>
+__global__ void __launch_bounds__(kBlock) k_sfsInitTiled(SfsData<T> P, ReduceWorkspace ws, int rzSlot, SfsInitOut<T> O, int usePre, int saveSSq, T minDiag, T maxDiag,
+                                                         int tilesX, int numTiles) {
+    __shared__ __align__(16) unsigned char planes[sfsTilePlaneBytes<T>(kSfsTW, kSfsTH)];
+    const int tid = threadIdx.x, tx = tid % kSfsTW, ty = tid / kSfsTW;
+    const T radius = LM ? (T)ws.scalars[kRadius] : T(1);
+    if (LM && blockIdx.x == 0 && tid == 0) { ws.scalars[kQ] = 0.0; ws.scalars[kQPrev] = 0.0; ws.scalars[kFlags] = 0.0; }   // delta = 0 => q = 0 (:631-664), Q0 = q, no early-out yet
+    T acc = T(0);
+    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        const SfsTileView<T> V = sfsCarveTile<T>(planes, (tile % tilesX) * kSfsTW, (tile / tilesX) * kSfsTH, kSfsTW, kSfsTH);
+        __syncthreads();   // the previous tile's gathers are done with the planes
+        for (int i = tid; i < V.PW() + V.PH(); i += kBlock) sfsTileFactors(P, V, i);
+        for (int c = tid; c < V.cells(); c += kBlock) sfsTileStageCell(P, V, c);
+        __syncthreads();
+        for (int c = tid; c < V.cells(); c += kBlock) sfsTileRowResiduals(P, V, c);
+        __syncthreads();
+        const int px = V.x0 + tx, py = V.y0 + ty;
+        if (px < P.W && py < P.H) {
+            const long u = (long)py * P.W + px;
+            const bool inc = (V.sfl[(ty + 1) * V.RW() + tx + 1] & kSfsIncluded) != 0;
+            T jtf = T(0), dg = T(0);
+            if (inc) { jtf = sfsTileGather(P, V, ty, tx, P.wp * sfsFP(P, u)); if (LM || usePre) dg = sfsTileGatherDiag(P, V, ty, tx); }
+            acc += sfsInitPixel<T, LM>(inc, jtf, dg, u, O, usePre, saveSSq, radius, minDiag, maxDiag);
+        }
+    }
+    gridReduceTo<kBlock>((double)acc, ws, rzSlot);
+}
+
+// ------------------------------------------------------------------------------------ whole PCG loop, state on chip
+// L iterations of PCGStep1/2/3 (:1056-1102) from the state PCGInit1 (+ FinalizeDiagonal) left, as one cooperative kernel: one CTA per
+// tw x th tile (sfs_tile.cuh).  Per iteration only the z of pixels within two of a tile border crosses CTAs (published to the plan's z
+// vector before the r.z all-reduce, which releases it; read back into the neighbours' rings at the top of the next iteration) plus the
+// two all-reduces (p.Ap; then r.z and q in one round).  LM: zeta = (l+1)(Q1-Q0)/Q1 < q_tolerance ends the loop in every CTA at once
+// (they all hold the same reduced q); the flag word tells the per-step kernels of a following residual-reset iteration to do nothing.
+// The reduction sequence number lives in device memory (seqWord) so that the launch is replayable from a captured graph.
+template <class T, int KMAX>
+__global__ void __launch_bounds__(1024, 1) k_sfsLoopResident(SfsData<T> P, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long* arrivals, unsigned long long* seqWord,
+                                                             int L, int tw, int th, int tilesX, int usePre, int lm, int resetPeriod, int withModelCost, T qTol,
+                                                             T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    constexpr int NT = 1024;
+    const int tid = threadIdx.x;
+    const SfsTileView<T> V = sfsCarveTile<T>(smemRaw, ((int)blockIdx.x % tilesX) * tw, ((int)blockIdx.x / tilesX) * th, tw, th, true);
+    SfsLoopRegs<T, KMAX> R;
+    for (int i = tid; i < V.PW() + V.PH(); i += NT) sfsTileFactors(P, V, i);
+    for (int c = tid; c < V.cells(); c += NT) sfsTileStageCell(P, V, c);
+    sfsLoopLoad<T, KMAX>(P, V, R, tid, NT, delta, r, b, CtC, pre, p, usePre, lm);
+    unsigned long long k = ldVolatileU64(seqWord);   // written by the previous launch on this stream; every CTA reads it before the first all-reduce can complete
+    double dRz = ws.scalars[kRz0], dRzPrev = 0.0, dPAp = 0.0, dQ = 0.0, unused = 0.0;
+    T Q0 = lm ? (T)ws.scalars[kQPrev] : T(0);
+    int done = 0, broke = -1;
+    __syncthreads();
+    for (int l = 0; l < L; ++l) {
+        if (l > 0) {   // PCGStep3 of iteration l - 1
+            T beta = T(0);
+            { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
+            sfsLoopUpdateDirection<T, KMAX>(P, V, R, tid, NT, beta, z);
+            __syncthreads();
+        }
+        for (int c = tid; c < V.cells(); c += NT) sfsTileRowsTimesVec(P, V, c, V.sp);
+        __syncthreads();
+        const T acc = sfsLoopApply<T, KMAX>(P, V, R, tid, NT);
+        gridAllReduce2LL<NT, false, false>((double)acc, 0.0, llWords, arrivals, ++k, ws.comm, 0, dPAp, unused);
+        T alpha = T(0);
+        { const T num = (T)dRz, den = (T)dPAp; if (den > T(0)) alpha = num / den; }
+        T accRz = T(0), accQ = T(0);
+        if (lm && resetPeriod > 0 && ((l + 1) % resetPeriod) == 0) {   // residual reset (:1077-1083): r = b - A delta instead of r -= alpha A p
+            double u0, u1;
+            sfsLoopResetFirstHalf<T, KMAX>(P, V, R, tid, NT, alpha, delta);
+            gridAllReduce2LL<NT, false, true>(0.0, 0.0, llWords, arrivals, ++k, ws.comm, 0, u0, u1);   // grid barrier that releases the tile-edge delta
+            sfsLoopFetchRing<T>(P, V, tid, NT, V.sd, delta);
+            __syncthreads();
+            for (int c = tid; c < V.cells(); c += NT) sfsTileRowsTimesVec(P, V, c, V.sd);
+            __syncthreads();
+            sfsLoopResetSecondHalf<T, KMAX>(P, V, R, tid, NT, usePre, z, accRz, accQ);
+        } else {
+            sfsLoopStep2<T, KMAX>(P, V, R, tid, NT, alpha, usePre, z, accRz, accQ);
+        }
+        dRzPrev = dRz;
+        gridAllReduce2LL<NT, false, true>((double)accRz, (double)accQ, llWords, arrivals, ++k, ws.comm, 0, dRz, dQ);   // releases the tile-edge z
+        done = l + 1;
+        if (lm) {
+            const T Q1 = (T)dQ;
+            const T zeta = T(l + 1) * (Q1 - Q0) / Q1;
+            Q0 = Q1;
+            if (zeta < qTol) { broke = l; break; }   // the reference updates p once more before it leaves (the epilogue does)
+        }
+    }
+    if (withModelCost) {   // computeModelCost (:666-678) for the delta just found: its rows need delta on a 1-pixel ring
+        double u0, u1, dModel;
+        sfsLoopPublishDelta<T, KMAX>(P, V, R, tid, NT, delta);
+        gridAllReduce2LL<NT, false, true>(0.0, 0.0, llWords, arrivals, ++k, ws.comm, 0, u0, u1);   // grid barrier that releases the tile-edge delta
+        sfsLoopFetchRing<T>(P, V, tid, NT, V.sd, delta);
+        __syncthreads();
+        for (int c = tid; c < V.cells(); c += NT) sfsTileRowsTimesVec(P, V, c, V.sd);
+        __syncthreads();
+        const T e = sfsLoopModelCost<T, KMAX>(P, V, R, tid, NT);
+        gridAllReduce2LL<NT, false, false>((double)e, 0.0, llWords, arrivals, ++k, ws.comm, 0, dModel, u1);
+        if (blockIdx.x == 0 && tid == 0) ws.scalars[kModelCost] = dModel;
+    }
+    T beta = T(0);
+    { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
+    sfsLoopStore<T, KMAX>(P, V, R, tid, NT, done > 0, beta, delta, r, z, p, Ap);
+    if (blockIdx.x == 0 && tid == 0 && done > 0) {   // leave the scalars as the kernel-per-step loop does (iteration l reads rz[l&1], writes rz[(l+1)&1])
+        ws.scalars[kPAp] = dPAp; ws.scalars[done & 1] = dRz; ws.scalars[(done + 1) & 1] = dRzPrev;
+        if (lm) { ws.scalars[kQ] = dQ; ws.scalars[kQPrev] = (double)Q0; if (broke >= 0) ws.scalars[kFlags] = 1.0 + broke; }
+        *seqWord = k;
+    }
+}
+__global__ void k_sfsCoopProbe(int* out) { if (out) *out = 1; }
 template <class T, bool MODEL>
 __global__ void __launch_bounds__(kBlock) k_sfsCost(SfsData<T> P, ReduceWorkspace ws, int slot, const T* __restrict__ delta) {
     const long N = (long)P.W * P.H;
@@ -198,14 +332,75 @@ struct SfsOps : EnergyOps<T> {
         if (occ < 1) occ = 1;
         gridTiled = (int)std::min<long>(std::min<long>(numTiles, (long)sms * occ), kMaxPartials);
         tiled = !getenv("OPTB_SFS_NO_TILED");   // the one-pass gather (A/B measurements)
+        { int o2 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, (const void*)k_sfsInitTiled<T, true>, kBlock, 0); if (o2 < 1) o2 = 1;
+          gridInit = (int)std::min<long>(std::min<long>(numTiles, (long)sms * o2), kMaxPartials); }
+        fusedHead = tiled && !getenv("OPTB_SFS_NO_FUSED_INIT");
+        fuseCost = !getenv("OPTB_SFS_NO_FUSED_COST");
+        fuseModel = !getenv("OPTB_SFS_NO_FUSED_MODEL");
+        if (tiled && !getenv("OPTB_SFS_NO_RESIDENT")) setUpResidentLoop(dev, sms);
     }
-    int tilesX = 0, numTiles = 0, gridTiled = 1; bool tiled = true;
-    ~SfsOps() override { cudaFree(P.B); cudaFree(P.dB); cudaFree(P.cR); cudaFree(P.cC); cudaFree(P.fl); }
+    int tilesX = 0, numTiles = 0, gridTiled = 1, gridInit = 1; bool tiled = true, fusedHead = true;
+    // ---- whole-loop kernel: tile shape, shared memory, reduction words (all fixed for the life of the plan)
+    static constexpr int kLoopK = 3;              // pixels per thread
+    int loopTW = 0, loopTH = 0, loopTilesX = 0, loopGrid = 0; size_t loopSmem = 0;
+    unsigned long long* loopWords = nullptr;      // [2 parities][kMaxLLCtas + 1][4] reduction words, arrival counter, sequence word
+    void setUpResidentLoop(int dev, int sms) {
+        int coop = 0, maxSmem = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (!coop) return;
+        const void* fn = (const void*)k_sfsLoopResident<T, kLoopK>;
+        cudaFuncAttributes fa{};
+        if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) { cudaGetLastError(); return; }
+        // one tile per SM at most; tile widths in multiples of 32 (warp = one tile row segment), the squarest shape that fits wins:
+        // its ring (what crosses CTAs every step) and its (tile + ring) planes are the smallest
+        long best = -1;
+        for (int tw = 32; tw <= (P.W + 31) / 32 * 32 && tw <= 1024; tw += 32) {
+            const int tx = (P.W + tw - 1) / tw;
+            if (tx > sms || tx > kMaxLLCtas) continue;
+            int th = (P.H + sms / tx - 1) / (sms / tx);
+            if (th < 4) th = 4;
+            if ((long)tw * th > (long)kLoopK * 1024) continue;
+            const size_t bytes = sfsTilePlaneBytes<T>(tw, th, true);
+            if (bytes + fa.sharedSizeBytes > (size_t)maxSmem) continue;
+            const long cost = (long)(tw + 2) * (th + 2) + (long)(tw + 4) * (th + 4);
+            if (best < 0 || cost < best) { best = cost; loopTW = tw; loopTH = th; loopTilesX = tx; loopGrid = tx * ((P.H + th - 1) / th); loopSmem = bytes; }
+        }
+        if (best < 0) { loopTW = 0; return; }
+        int occ = 0;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)loopSmem) != cudaSuccess
+            || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 1024, loopSmem) != cudaSuccess || occ < 1 || loopGrid > sms * occ || loopGrid > kMaxLLCtas) {
+            cudaGetLastError(); loopTW = 0; return;
+        }
+        // a cooperative launch inside a stream capture must work: the loop kernel is a node of the plan's PCG-loop / iteration graphs
+        {
+            cudaStream_t s = nullptr; cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr; bool ok = false;
+            int* none = nullptr; void* args[] = { (void*)&none };
+            if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) {
+                if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_sfsCoopProbe, dim3(1), dim3(32), args, 0, s);
+                    const cudaError_t ee = cudaStreamEndCapture(s, &g);
+                    if (le == cudaSuccess && ee == cudaSuccess && g && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess)
+                        ok = cudaGraphLaunch(ge, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess;
+                }
+                if (ge) cudaGraphExecDestroy(ge);
+                if (g) cudaGraphDestroy(g);
+                cudaStreamDestroy(s);
+            }
+            cudaGetLastError();
+            if (!ok) { loopTW = 0; return; }
+        }
+        constexpr size_t words = 2 * 4 * (kMaxLLCtas + 1) + 2;
+        OPT_CUDA_CHECK(cudaMalloc((void**)&loopWords, sizeof(unsigned long long) * words));
+        OPT_CUDA_CHECK(cudaMemset(loopWords, 0, sizeof(unsigned long long) * words));
+    }
+    ~SfsOps() override { cudaFree(P.B); cudaFree(P.dB); cudaFree(P.cR); cudaFree(P.cC); cudaFree(P.fl); cudaFree(loopWords); }
     const char* name() const override { return "shape_from_shading"; }
     bool capturable() const override { return true; }
-    unsigned long long captureKey() const override { return EnergyOps<T>::hashValue(P); }
+    unsigned long long captureKey() const override { const int shape[] = { loopTW, loopTH, (int)fusedHead, (int)tiled, (int)fuseCost, (int)fuseModel }; return EnergyOps<T>::hashBytes(shape, sizeof(shape), EnergyOps<T>::hashValue(P)); }
     void bind(void** q) override {   // positions: shape_from_shading.t:5-28 (all scalar Params are float, cast to opt_float on use, o.t:1699)
         auto f = [&](int k) { return (T) * (const float*)q[k]; };
+        costFresh = false;
         P.wp = (T)sqrt((double)f(0)); P.ws = (T)sqrt((double)f(1)); P.wg = (T)sqrt((double)f(2));
         if (std::is_same<T, float>::value) { P.wp = (T)sqrtf(*(const float*)q[0]); P.ws = (T)sqrtf(*(const float*)q[1]); P.wg = (T)sqrtf(*(const float*)q[2]); }
         P.fx = f(3); P.fy = f(4); P.ux = f(5); P.uy = f(6);
@@ -213,12 +408,41 @@ struct SfsOps : EnergyOps<T> {
         this->unknowns[0].user = q[16];
         P.X = (const T*)q[16]; P.D = (const T*)q[17]; P.Im = (const T*)q[18]; P.eR = (const unsigned char*)q[19]; P.eC = (const unsigned char*)q[20];
     }
+    // precompute also leaves the cost of the X it linearised at in scalars[kCost]; the cost() that follows it (every call site in
+    // solver.cu pairs them) is then free
+    bool fuseCost = true, costFresh = false;
     void precompute(const LaunchCtx& c) override {
         k_sfsPrecomputeB<T><<<grid, kBlock, 0, c.stream>>>(P);
-        k_sfsBuildRows<T><<<grid, kBlock, 0, c.stream>>>(P);
+        if (fuseCost) { k_sfsBuildRowsCost<T><<<grid, kBlock, 0, c.stream>>>(P, c.ws, kCost); costFresh = true; }
+        else k_sfsBuildRows<T><<<grid, kBlock, 0, c.stream>>>(P);
     }
     void pcgInit(const LaunchCtx& c, T* delta, T* r, T* pre, T* p, int rzSlot) override {
+        if (fusedHead) {
+            const SfsInitOut<T> O{ delta, r, pre, p, nullptr, nullptr, nullptr };
+            k_sfsInitTiled<T, false><<<gridInit, kBlock, 0, c.stream>>>(P, c.ws, rzSlot, O, this->usePreconditioner ? 1 : 0, 0, T(0), T(0), tilesX, numTiles);
+            return;
+        }
         k_sfsInit<T><<<grid, kBlock, 0, c.stream>>>(P, this->usePreconditioner ? 1 : 0, c.ws, rzSlot, delta, r, pre, p);
+    }
+    bool pcgInitLM(const LaunchCtx& c, T* delta, T* r, T* pre, T* p, T* CtC, T* SSq, T* b, int rzSlot, T minDiag, T maxDiag, bool saveSSq) override {
+        if (!fusedHead) return false;
+        const SfsInitOut<T> O{ delta, r, pre, p, CtC, SSq, b };
+        k_sfsInitTiled<T, true><<<gridInit, kBlock, 0, c.stream>>>(P, c.ws, rzSlot, O, this->usePreconditioner ? 1 : 0, saveSSq ? 1 : 0, minDiag, maxDiag, tilesX, numTiles);
+        return true;
+    }
+    bool fuseModel = true;
+    int pcgLoopOnChip(const LaunchCtx& c, int L, bool lm, int resetPeriod, T qTol, T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC,
+                      bool* modelCostDone) override {
+        if (!loopTW || L < 2) return 0;
+        int withModel = (lm && fuseModel && modelCostDone) ? 1 : 0;
+        if (modelCostDone) *modelCostDone = withModel != 0;
+        ReduceWorkspace ws = c.ws;
+        unsigned long long* arrivals = loopWords + 2 * 4 * (kMaxLLCtas + 1); unsigned long long* seqWord = arrivals + 1;
+        int usePre = this->usePreconditioner ? 1 : 0, lmi = lm ? 1 : 0;
+        void* args[] = { (void*)&P, (void*)&ws, (void*)&loopWords, (void*)&arrivals, (void*)&seqWord, (void*)&L, (void*)&loopTW, (void*)&loopTH, (void*)&loopTilesX, (void*)&usePre, (void*)&lmi,
+                         (void*)&resetPeriod, (void*)&withModel, (void*)&qTol, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre, (void*)&b, (void*)&CtC };
+        OPT_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_sfsLoopResident<T, kLoopK>, dim3((unsigned)loopGrid), dim3(1024), args, loopSmem, c.stream));
+        return L;
     }
     void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot, const HaloPlan*) override {
         if (tiled) {
@@ -229,7 +453,10 @@ struct SfsOps : EnergyOps<T> {
         if (CtC) k_sfsApplyJTJ<T, true><<<grid, kBlock, 0, c.stream>>>(P, c.ws, dotSlot, x, out, CtC);
         else k_sfsApplyJTJ<T, false><<<grid, kBlock, 0, c.stream>>>(P, c.ws, dotSlot, x, out, nullptr);
     }
-    void cost(const LaunchCtx& c) override { k_sfsCost<T, false><<<grid, kBlock, 0, c.stream>>>(P, c.ws, kCost, nullptr); }
+    void cost(const LaunchCtx& c) override {
+        if (costFresh) { costFresh = false; return; }
+        k_sfsCost<T, false><<<grid, kBlock, 0, c.stream>>>(P, c.ws, kCost, nullptr);
+    }
     void modelCost(const LaunchCtx& c, const T* delta) override { k_sfsCost<T, true><<<grid, kBlock, 0, c.stream>>>(P, c.ws, kModelCost, delta); }
     void computeCtC(const LaunchCtx& c, T* CtC, T invRadius) override { k_sfsCtC<T><<<grid, kBlock, 0, c.stream>>>(P, CtC, invRadius); }
 };

@@ -1,0 +1,405 @@
+// sfs_tile.cuh -- tile-level building blocks of the shape_from_shading kernel set: the operators of sfs_device.cuh evaluated for a
+// tw x th tile of pixels out of staged planes instead of pixel by pixel out of global memory.
+//
+// Every operator of this energy is "one value per ROW (y = row . vec, or the row's residual F), then for every unknown u the sum over
+// the rows that read X(u) of coefficient x value" (sfsGather in sfs_device.cuh).  The per-pixel form re-derives each row value once per
+// unknown that row touches (5x for r_gR / r_gC, 5x3 for r_s); the tile form computes it once per row centre in (tile + 1-pixel ring):
+//     sp   [(th+4) x (tw+4)]   the vector the rows are applied to, tile + 2-pixel ring (0 outside the image)
+//     sc   [10][cells]         the r_gR / r_gC coefficients of the row centred at the cell          cells = (th+2) x (tw+2)
+//     sy   [5][cells]          the five row values (r_gR, r_gC, r_s x/y/z) of the row centred at the cell
+//     sfl  [cells]             flag byte of the cell (0 outside the image)
+//     sAx, sAy                 back-projection factors (x - u_x)/f_x, (y - u_y)/f_y of the columns / rows of tile + 2-pixel ring
+//     sd   [(th+4) x (tw+4)]   (whole-loop kernel only) a second vector plane: delta, for LM's residual-reset iterations
+// Used by k_sfsInitTiled (PCGInit1 + PCGComputeCtC + PCGFinalizeDiagonal in one pass) and by the whole-loop kernel k_sfsLoopResident
+// (energy_sfs.cu); the functions are plain host/device code so tests/host/sfs_tile_host.cpp can run both algorithms on the CPU, "thread"
+// by "thread", against the oracle (tests/test_sfs_host_parity.py).  Same products in the same order as sfsGather<T, MODE>.
+#pragma once
+#include <cstddef>
+#include "sfs_device.cuh"
+
+namespace optb {
+
+template <class T>
+struct SfsTileView {
+    int x0, y0, tw, th;          // image coordinates of the tile's first pixel, nominal extent
+    T* sp; T* sc; T* sy; unsigned char* sfl; T* sAx; T* sAy;
+    T* sd;                       // whole-loop kernel only: delta with a 2-pixel ring, for the residual-reset iterations (nullptr otherwise)
+    SFS_HD int RW() const { return tw + 2; }
+    SFS_HD int RH() const { return th + 2; }
+    SFS_HD int PW() const { return tw + 4; }
+    SFS_HD int PH() const { return th + 4; }
+    SFS_HD int cells() const { return (tw + 2) * (th + 2); }
+};
+// bytes of the planes above for a tw x th tile (sp, sc, sy, the two factor tables, then the flag bytes), each plane 16-byte aligned
+SFS_HD constexpr size_t sfsUp16(size_t v) { return (v + 15) / 16 * 16; }
+template <class T> SFS_HD constexpr size_t sfsTilePlaneBytes(int tw, int th, bool withDelta = false) {
+    return sfsUp16((size_t)(tw + 4) * (th + 4) * sizeof(T)) * (withDelta ? 2 : 1) + sfsUp16(10 * (size_t)(tw + 2) * (th + 2) * sizeof(T))
+         + sfsUp16(5 * (size_t)(tw + 2) * (th + 2) * sizeof(T)) + sfsUp16((size_t)(tw + 4) * sizeof(T)) + sfsUp16((size_t)(th + 4) * sizeof(T)) + sfsUp16((size_t)(tw + 2) * (th + 2));
+}
+template <class T> SFS_HD SfsTileView<T> sfsCarveTile(unsigned char* base, int x0, int y0, int tw, int th, bool withDelta = false) {
+    SfsTileView<T> V; V.x0 = x0; V.y0 = y0; V.tw = tw; V.th = th;
+    const size_t cells = (size_t)(tw + 2) * (th + 2), pcells = (size_t)(tw + 4) * (th + 4);
+    V.sp = reinterpret_cast<T*>(base); base += sfsUp16(pcells * sizeof(T));
+    V.sd = nullptr;
+    if (withDelta) { V.sd = reinterpret_cast<T*>(base); base += sfsUp16(pcells * sizeof(T)); }
+    V.sc = reinterpret_cast<T*>(base); base += sfsUp16(10 * cells * sizeof(T));
+    V.sy = reinterpret_cast<T*>(base); base += sfsUp16(5 * cells * sizeof(T));
+    V.sAx = reinterpret_cast<T*>(base); base += sfsUp16((size_t)(tw + 4) * sizeof(T));
+    V.sAy = reinterpret_cast<T*>(base); base += sfsUp16((size_t)(th + 4) * sizeof(T));
+    V.sfl = base;
+    return V;
+}
+
+// ---- staging (once per linearisation): factor tables, then flag byte + the ten coefficients of row cell c
+template <class T> SFS_HD void sfsTileFactors(const SfsData<T>& P, const SfsTileView<T>& V, int i) {   // i in [0, PW + PH)
+    if (i < V.PW()) V.sAx[i] = sfsAx(P, V.x0 - 2 + i);
+    else if (i < V.PW() + V.PH()) V.sAy[i - V.PW()] = sfsAy(P, V.y0 - 2 + (i - V.PW()));
+}
+template <class T> SFS_HD void sfsTileStageCell(const SfsData<T>& P, const SfsTileView<T>& V, int c) {
+    const int RW = V.RW(), cells = V.cells();
+    const int ly = c / RW, lx = c - ly * RW, gx = V.x0 - 1 + lx, gy = V.y0 - 1 + ly;
+    const long N = sfsN(P);
+    unsigned f = 0;
+    T co[10] = { T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0) };
+    if (sfsInImage(P, gx, gy)) {
+        const long ci = (long)gy * P.W + gx;
+        f = P.fl[ci];
+        if (f & kSfsInner) {
+            SFS_UNROLL for (int m = 0; m < 5; ++m) { co[m] = P.cR[(long)m * N + ci]; co[5 + m] = P.cC[(long)m * N + ci]; }
+        }
+    }
+    V.sfl[c] = (unsigned char)f;
+    SFS_UNROLL for (int k = 0; k < 10; ++k) V.sc[k * cells + c] = co[k];
+}
+
+// ---- row values of cell c:  y = row . sp   (rows with a zero coefficient contribute an exact 0 instead of being skipped)
+template <class T> SFS_HD void sfsTileRowsTimesVec(const SfsData<T>& P, const SfsTileView<T>& V, int c, const T* vec) {   // vec: V.sp or V.sd
+    const int RW = V.RW(), PW = V.PW(), cells = V.cells();
+    const int ly = c / RW, lx = c - ly * RW;
+    const unsigned f = V.sfl[c];
+    T y[5] = { T(0), T(0), T(0), T(0), T(0) };
+    if (f & kSfsInner) {
+        SFS_UNROLL for (int t = 0; t < 2; ++t)
+            SFS_UNROLL for (int m = 0; m < 5; ++m) y[t] += V.sc[(t * 5 + m) * cells + c] * vec[(ly + 1 + sfsDy(t, m)) * PW + lx + 1 + sfsDx(t, m)];
+    }
+    if (f & kSfsFlat) {
+        const T ax[3] = { V.sAx[lx], V.sAx[lx + 1], V.sAx[lx + 2] }, ay[3] = { V.sAy[ly], V.sAy[ly + 1], V.sAy[ly + 2] };   // columns gx-1..gx+1, rows gy-1..gy+1
+        SFS_UNROLL for (int m = 0; m < 5; ++m) {
+            const T pm = vec[(ly + 1 + sfsDy(2, m)) * PW + lx + 1 + sfsDx(2, m)];
+            y[2] += sfsCoefFromA(P, ax[1 + sfsDx(2, m)], m) * pm;
+            y[3] += sfsCoefFromA(P, ay[1 + sfsDy(2, m)], m) * pm;
+            y[4] += sfsCoefFromA(P, T(1), m) * pm;
+        }
+    }
+    SFS_UNROLL for (int k = 0; k < 5; ++k) V.sy[k * cells + c] = y[k];
+}
+// ---- row values of cell c:  y = F(row), the residuals at the current X (sfsFR, sfsFC, sfsFS of sfs_device.cuh, factors from the tables)
+template <class T> SFS_HD void sfsTileRowResiduals(const SfsData<T>& P, const SfsTileView<T>& V, int c) {
+    const int RW = V.RW(), cells = V.cells();
+    const int ly = c / RW, lx = c - ly * RW, gx = V.x0 - 1 + lx, gy = V.y0 - 1 + ly;
+    const unsigned f = V.sfl[c];
+    T y[5] = { T(0), T(0), T(0), T(0), T(0) };
+    if (f & (kSfsInner | kSfsFlat)) {   // either flag implies an in-image cell
+        const long ci = (long)gy * P.W + gx;
+        if (f & kSfsInner) {
+            const T Bc = P.B[ci];
+            y[0] = P.wg * ((Bc - P.B[ci + 1]) * T(P.eR[ci]));
+            y[1] = P.wg * ((Bc - P.B[ci + P.W]) * T(P.eC[ci]));
+        }
+        if (f & kSfsFlat) {
+            const T ax[3] = { V.sAx[lx], V.sAx[lx + 1], V.sAx[lx + 2] }, ay[3] = { V.sAy[ly], V.sAy[ly + 1], V.sAy[ly + 2] };
+            SFS_UNROLL for (int m = 0; m < 5; ++m) {
+                const T xm = P.X[ci + (long)sfsDy(2, m) * P.W + sfsDx(2, m)];
+                y[2] += sfsCoefFromA(P, ax[1 + sfsDx(2, m)], m) * xm;
+                y[3] += sfsCoefFromA(P, ay[1 + sfsDy(2, m)], m) * xm;
+                y[4] += sfsCoefFromA(P, T(1), m) * xm;
+            }
+        }
+    }
+    SFS_UNROLL for (int k = 0; k < 5; ++k) V.sy[k * cells + c] = y[k];
+}
+
+// ---- gathers for the tile pixel (ty, tx) (an INCLUDED pixel; the caller checks).  `first` is the r_p term:
+//      wp (wp x_u) for J^T J x, wp F_p(u) for J^T F.
+template <class T> SFS_HD T sfsTileGather(const SfsData<T>& P, const SfsTileView<T>& V, int ty, int tx, T first) {
+    const int RW = V.RW(), cells = V.cells();
+    T o = first;
+    SFS_UNROLL for (int t = 0; t < 2; ++t)
+        SFS_UNROLL for (int k = 0; k < 5; ++k) {                                  // u is dependency k of the row centred at u - offset_k
+            const int cc = (ty + 1 - sfsDy(t, k)) * RW + tx + 1 - sfsDx(t, k);
+            o += V.sc[(t * 5 + k) * cells + cc] * V.sy[t * cells + cc];
+        }
+    const T axu = V.sAx[tx + 2], ayu = V.sAy[ty + 2];                             // dependency k of the row centred at u - offset_k is u itself
+    SFS_UNROLL for (int k = 0; k < 5; ++k) {
+        const int cc = (ty + 1 - sfsDy(2, k)) * RW + tx + 1 - sfsDx(2, k);
+        o += sfsCoefFromA(P, axu, k) * V.sy[2 * cells + cc];
+        o += sfsCoefFromA(P, ayu, k) * V.sy[3 * cells + cc];
+        o += sfsCoefFromA(P, T(1), k) * V.sy[4 * cells + cc];
+    }
+    return o;
+}
+template <class T> SFS_HD T sfsTileGatherDiag(const SfsData<T>& P, const SfsTileView<T>& V, int ty, int tx) {   // diag J^T J, order of sfsGather<T, 2>
+    const int RW = V.RW(), cells = V.cells();
+    T acc = P.wp * P.wp;
+    SFS_UNROLL for (int t = 0; t < 2; ++t)
+        SFS_UNROLL for (int k = 0; k < 5; ++k) {
+            const T a = V.sc[(t * 5 + k) * cells + (ty + 1 - sfsDy(t, k)) * RW + tx + 1 - sfsDx(t, k)];
+            acc += a * a;
+        }
+    const T aU[3] = { V.sAx[tx + 2], V.sAy[ty + 2], T(1) };
+    SFS_UNROLL for (int k = 0; k < 5; ++k) {
+        if (!(V.sfl[(ty + 1 - sfsDy(2, k)) * RW + tx + 1 - sfsDx(2, k)] & kSfsFlat)) continue;
+        SFS_UNROLL for (int comp = 0; comp < 3; ++comp) { const T a = sfsCoefFromA(P, aU[comp], k); acc += a * a; }
+    }
+    return acc;
+}
+
+// =============================================================================================================================
+// PCGInit1 for one pixel out of the gathers above (+ PCGComputeCtC + PCGFinalizeDiagonal when LM): what k_sfsInit, k_sfsCtC and
+// k_lmFinalizeDiagonal (solver.cu) do in three passes over memory.  Returns the pixel's contribution to r . p.
+template <class T> SFS_HD T sfsGuardedInvertT(T v) { const T s = T(1) + sfsSqrt(v); return T(1) / (s * s); }   // CERES variant, solverGPUGaussNewton.t:323-332
+template <class T>
+struct SfsInitOut { T* delta; T* r; T* pre; T* p; T* CtC; T* SSq; T* b; };
+template <class T, bool LM>
+SFS_HD T sfsInitPixel(bool included, T jtf, T diag, long i, const SfsInitOut<T>& O, int usePre, int saveSSq, T radius, T minDiag, T maxDiag) {
+    T rr = T(0), pr = T(0);
+    if (included) { rr = -jtf; pr = sfsGuardedInvertT(usePre ? diag : T(1)); }   // PCGInit1 order (:379-385): without a preconditioner the constant 1 is inverted too
+    O.delta[i] = T(0); O.r[i] = rr;
+    if (!LM) { const T pp = pr * rr; O.pre[i] = pr; O.p[i] = pp; return rr * pp; }
+    // PCGSaveSSq (first nonlinear iteration, :1038-1041), then PCGFinalizeDiagonal (:631-664) as k_lmFinalizeDiagonal applies it
+    T ssq = saveSSq ? pr : O.SSq[i];
+    if (saveSSq) O.SSq[i] = pr;
+    else if (pr > T(0) && !(ssq > T(0))) { ssq = pr; O.SSq[i] = ssq; }
+    T acc = T(0);
+    if (pr > T(0) && ssq > T(0)) {
+        const T invRadius = T(1) / radius;
+        const T unclamped = (included ? diag : T(0)) * invRadius;
+        const T invS = T(1) / ssq;
+        const T clampMul = invS / radius;
+        const T mn = minDiag * clampMul, mx = maxDiag * clampMul;
+        const T c = unclamped < mn ? mn : (unclamped > mx ? mx : unclamped);
+        O.CtC[i] = c;
+        const T pr2 = T(1) / (c + radius * unclamped);
+        O.pre[i] = pr2; O.b[i] = rr;
+        const T pp = pr2 * rr;
+        O.p[i] = pp;
+        acc = rr * pp;
+    } else {
+        O.CtC[i] = T(0); O.pre[i] = T(0); O.b[i] = T(0); O.p[i] = T(0);
+    }
+    return acc;
+}
+
+// =============================================================================================================================
+// Whole PCG loop with the state of a tile on chip (k_sfsLoopResident).  One CTA per tile: the planes of SfsTileView hold the
+// direction p (tile + 2-pixel ring), the coefficients and the flags; delta, r, b, CtC, pre, z and Ap of a thread's (at most KMAX)
+// pixels live in registers.  Per PCG step only the ring of z crosses CTAs (through global memory / L2) plus two all-reduces.
+//   pixel q of thread tid:  c = tid + q * NT,  (ty, tx) = (c / tw, c % tw),  valid if c < tw * th and inside the image.
+template <class T, int KMAX>
+struct SfsLoopRegs { T delta[KMAX], r[KMAX], b[KMAX], ctc[KMAX], pre[KMAX], z[KMAX], ap[KMAX]; };
+
+template <class T> SFS_HD bool sfsLoopPixel(const SfsData<T>& P, const SfsTileView<T>& V, int c, int& ty, int& tx, long& gi) {
+    if (c >= V.tw * V.th) return false;
+    ty = c / V.tw; tx = c - ty * V.tw;
+    const int gx = V.x0 + tx, gy = V.y0 + ty;
+    if (gx >= P.W || gy >= P.H) return false;
+    gi = (long)gy * P.W + gx;
+    return true;
+}
+#if defined(__CUDA_ARCH__)
+#define SFS_LD_CG(ptr) __ldcg(ptr)
+#define SFS_ST_CG(ptr, v) __stcg(ptr, v)
+#else
+#define SFS_LD_CG(ptr) (*(ptr))
+#define SFS_ST_CG(ptr, v) (*(ptr) = (v))
+#endif
+
+// prologue: the direction with its ring, this thread's pixels
+template <class T, int KMAX>
+SFS_HD void sfsLoopLoad(const SfsData<T>& P, const SfsTileView<T>& V, SfsLoopRegs<T, KMAX>& R, int tid, int NT, const T* delta, const T* r, const T* b,
+                        const T* CtC, const T* pre, const T* p, int usePre, int lm) {
+    const int PW = V.PW(), pcells = PW * V.PH();
+    for (int c = tid; c < pcells; c += NT) {
+        const int ly = c / PW, lx = c - ly * PW, gx = V.x0 - 2 + lx, gy = V.y0 - 2 + ly;
+        V.sp[c] = sfsInImage(P, gx, gy) ? p[(long)gy * P.W + gx] : T(0);
+        if (V.sd) V.sd[c] = T(0);
+    }
+    SFS_UNROLL for (int q = 0; q < KMAX; ++q) {
+        int ty, tx; long gi;
+        R.delta[q] = R.r[q] = R.b[q] = R.ctc[q] = R.z[q] = R.ap[q] = T(0); R.pre[q] = T(1);
+        if (sfsLoopPixel(P, V, tid + q * NT, ty, tx, gi)) {
+            R.delta[q] = delta[gi]; R.r[q] = r[gi];
+            if (lm) { R.b[q] = b[gi]; R.ctc[q] = CtC[gi]; }
+            if (usePre) R.pre[q] = pre[gi];
+        }
+    }
+}
+// PCGStep3 (:537-550) for the thread's own pixels (z in registers) and, for the ring cells, from the z their owners published
+template <class T, int KMAX>
+SFS_HD void sfsLoopUpdateDirection(const SfsData<T>& P, const SfsTileView<T>& V, const SfsLoopRegs<T, KMAX>& R, int tid, int NT, T beta, const T* zGlobal) {
+    const int PW = V.PW(), PH = V.PH();
+    SFS_UNROLL for (int q = 0; q < KMAX; ++q) {
+        int ty, tx; long gi;
+        if (sfsLoopPixel(P, V, tid + q * NT, ty, tx, gi)) { const int cc = (ty + 2) * PW + tx + 2; V.sp[cc] = R.z[q] + beta * V.sp[cc]; }
+    }
+    // ring: two rows above, two below, two columns left and right of the tile
+    const int nRing = 4 * PW + 4 * V.th;
+    for (int j = tid; j < nRing; j += NT) {
+        int ly, lx;
+        if (j < 2 * PW) { ly = j / PW; lx = j - ly * PW; }
+        else if (j < 4 * PW) { const int jj = j - 2 * PW; ly = jj / PW; lx = jj - ly * PW; ly += PH - 2; }
+        else { const int jj = j - 4 * PW; ly = 2 + (jj >> 2); const int s = jj & 3; lx = s < 2 ? s : PW - 4 + s; }
+        const int gx = V.x0 - 2 + lx, gy = V.y0 - 2 + ly;
+        if (sfsInImage(P, gx, gy)) { const int cc = ly * PW + lx; V.sp[cc] = SFS_LD_CG(zGlobal + (long)gy * P.W + gx) + beta * V.sp[cc]; }
+    }
+}
+// PCGStep1 (:421-434), second half: Ap for the thread's pixels out of the row values; returns the thread's part of p . Ap
+template <class T, int KMAX>
+SFS_HD T sfsLoopApply(const SfsData<T>& P, const SfsTileView<T>& V, SfsLoopRegs<T, KMAX>& R, int tid, int NT) {
+    const int PW = V.PW(), RW = V.RW();
+    T acc = T(0);
+    SFS_UNROLL for (int q = 0; q < KMAX; ++q) {
+        int ty, tx; long gi;
+        T o = T(0);
+        if (sfsLoopPixel(P, V, tid + q * NT, ty, tx, gi) && (V.sfl[(ty + 1) * RW + tx + 1] & kSfsIncluded)) {
+            const T xi = V.sp[(ty + 2) * PW + tx + 2];
+            o = sfsTileGather(P, V, ty, tx, P.wp * (P.wp * xi));
+            o += R.ctc[q] * xi;                                   // LM: + CtC p (0 for Gauss-Newton)
+            acc += xi * o;
+        }
+        R.ap[q] = o;
+    }
+    return acc;
+}
+// PCGStep2 (:446-489) for the thread's pixels; pixels within two of the tile's border publish their z for the neighbouring tiles' rings
+template <class T, int KMAX>
+SFS_HD void sfsLoopStep2(const SfsData<T>& P, const SfsTileView<T>& V, SfsLoopRegs<T, KMAX>& R, int tid, int NT, T alpha, int usePre, T* zGlobal, T& accRz, T& accQ) {
+    const int PW = V.PW();
+    SFS_UNROLL for (int q = 0; q < KMAX; ++q) {
+        int ty, tx; long gi;
+        if (sfsLoopPixel(P, V, tid + q * NT, ty, tx, gi)) {
+            const T d = R.delta[q] + alpha * V.sp[(ty + 2) * PW + tx + 2];
+            const T rr = R.r[q] - alpha * R.ap[q];
+            const T zz = usePre ? R.pre[q] * rr : rr;
+            R.delta[q] = d; R.r[q] = rr; R.z[q] = zz;
+            accRz += zz * rr;
+            accQ += T(0.5) * (d * (rr + R.b[q]));
+            if (ty < 2 || ty >= V.th - 2 || tx < 2 || tx >= V.tw - 2) SFS_ST_CG(zGlobal + gi, zz);
+        }
+    }
+}
+// ---- residual-reset iteration (LM, every residual_reset_period-th iteration; :1077-1083) in three pieces:
+// PCGStep2_1stHalf (:491-503): delta += alpha p; the new delta goes into the tile's delta plane and, for pixels within two of the border,
+// to the plan's delta vector (free during the kernel) for the neighbouring tiles' rings
+template <class T, int KMAX>
+SFS_HD void sfsLoopResetFirstHalf(const SfsData<T>& P, const SfsTileView<T>& V, SfsLoopRegs<T, KMAX>& R, int tid, int NT, T alpha, T* dGlobal) {
+    const int PW = V.PW();
+    SFS_UNROLL for (int q = 0; q < KMAX; ++q) {
+        int ty, tx; long gi;
+        if (sfsLoopPixel(P, V, tid + q * NT, ty, tx, gi)) {
+            const int cc = (ty + 2) * PW + tx + 2;
+            const T d = R.delta[q] + alpha * V.sp[cc];
+            R.delta[q] = d; V.sd[cc] = d;
+            if (ty < 2 || ty >= V.th - 2 || tx < 2 || tx >= V.tw - 2) SFS_ST_CG(dGlobal + gi, d);
+        }
+    }
+}
+// the ring of the delta plane from what the neighbouring tiles published (after a grid barrier that released it)
+template <class T>
+SFS_HD void sfsLoopFetchRing(const SfsData<T>& P, const SfsTileView<T>& V, int tid, int NT, T* plane, const T* vGlobal) {
+    const int PW = V.PW(), PH = V.PH();
+    const int nRing = 4 * PW + 4 * V.th;
+    for (int j = tid; j < nRing; j += NT) {
+        int ly, lx;
+        if (j < 2 * PW) { ly = j / PW; lx = j - ly * PW; }
+        else if (j < 4 * PW) { const int jj = j - 2 * PW; ly = jj / PW; lx = jj - ly * PW; ly += PH - 2; }
+        else { const int jj = j - 4 * PW; ly = 2 + (jj >> 2); const int s = jj & 3; lx = s < 2 ? s : PW - 4 + s; }
+        const int gx = V.x0 - 2 + lx, gy = V.y0 - 2 + ly;
+        if (sfsInImage(P, gx, gy)) plane[ly * PW + lx] = SFS_LD_CG(vGlobal + (long)gy * P.W + gx);
+    }
+}
+// A delta out of the row values of the delta plane, then PCGStep2_2ndHalf (:505-534): r = b - A delta, z = pre r, r.z and q
+template <class T, int KMAX>
+SFS_HD void sfsLoopResetSecondHalf(const SfsData<T>& P, const SfsTileView<T>& V, SfsLoopRegs<T, KMAX>& R, int tid, int NT, int usePre, T* zGlobal, T& accRz, T& accQ) {
+    const int PW = V.PW(), RW = V.RW();
+    SFS_UNROLL for (int q = 0; q < KMAX; ++q) {
+        int ty, tx; long gi;
+        if (sfsLoopPixel(P, V, tid + q * NT, ty, tx, gi)) {
+            T ad = T(0);
+            if (V.sfl[(ty + 1) * RW + tx + 1] & kSfsIncluded) {
+                const T di = V.sd[(ty + 2) * PW + tx + 2];
+                ad = sfsTileGather(P, V, ty, tx, P.wp * (P.wp * di));
+                ad += R.ctc[q] * di;
+            }
+            const T rr = R.b[q] - ad;
+            const T zz = usePre ? R.pre[q] * rr : rr;
+            R.r[q] = rr; R.z[q] = zz;
+            accRz += zz * rr;
+            accQ += T(0.5) * (R.delta[q] * (rr + R.b[q]));
+            if (ty < 2 || ty >= V.th - 2 || tx < 2 || tx >= V.tw - 2) SFS_ST_CG(zGlobal + gi, zz);
+        }
+    }
+}
+// ---- computeModelCost (:666-678) at the end of the loop: delta into the delta plane (+ tile-edge publish, as in the reset iteration), then
+// 1/2 sum (F + J delta)^2 over the rows centred at the thread's included pixels, J delta taken from the row values of the delta plane
+template <class T, int KMAX>
+SFS_HD void sfsLoopPublishDelta(const SfsData<T>& P, const SfsTileView<T>& V, const SfsLoopRegs<T, KMAX>& R, int tid, int NT, T* dGlobal) {
+    const int PW = V.PW();
+    SFS_UNROLL for (int q = 0; q < KMAX; ++q) {
+        int ty, tx; long gi;
+        if (sfsLoopPixel(P, V, tid + q * NT, ty, tx, gi)) {
+            V.sd[(ty + 2) * PW + tx + 2] = R.delta[q];
+            if (ty < 2 || ty >= V.th - 2 || tx < 2 || tx >= V.tw - 2) SFS_ST_CG(dGlobal + gi, R.delta[q]);
+        }
+    }
+}
+template <class T, int KMAX>
+SFS_HD T sfsLoopModelCost(const SfsData<T>& P, const SfsTileView<T>& V, const SfsLoopRegs<T, KMAX>& R, int tid, int NT) {
+    const int RW = V.RW(), cells = V.cells();
+    T acc = T(0);
+    SFS_UNROLL for (int q = 0; q < KMAX; ++q) {
+        int ty, tx; long gi;
+        if (!sfsLoopPixel(P, V, tid + q * NT, ty, tx, gi)) continue;
+        const int cc = (ty + 1) * RW + tx + 1;
+        const unsigned f = V.sfl[cc];
+        if (!(f & kSfsIncluded)) continue;
+        T e = T(0);
+        { const T r = sfsFP(P, gi) + P.wp * R.delta[q]; e += r * r; }
+        if (f & kSfsInner) {
+            const T Bc = P.B[gi];
+            const T r0 = P.wg * ((Bc - P.B[gi + 1]) * T(P.eR[gi])) + V.sy[cc];
+            const T r1 = P.wg * ((Bc - P.B[gi + P.W]) * T(P.eC[gi])) + V.sy[cells + cc];
+            e += r0 * r0; e += r1 * r1;
+        }
+        if (f & kSfsFlat) {
+            const int lx = tx + 1, ly = ty + 1;   // the pixel's row cell; factor tables are indexed like the vector planes
+            const T ax[3] = { V.sAx[lx], V.sAx[lx + 1], V.sAx[lx + 2] }, ay[3] = { V.sAy[ly], V.sAy[ly + 1], V.sAy[ly + 2] };
+            T fs[3] = { T(0), T(0), T(0) };
+            SFS_UNROLL for (int m = 0; m < 5; ++m) {
+                const T xm = P.X[gi + (long)sfsDy(2, m) * P.W + sfsDx(2, m)];
+                fs[0] += sfsCoefFromA(P, ax[1 + sfsDx(2, m)], m) * xm;
+                fs[1] += sfsCoefFromA(P, ay[1 + sfsDy(2, m)], m) * xm;
+                fs[2] += sfsCoefFromA(P, T(1), m) * xm;
+            }
+            SFS_UNROLL for (int comp = 0; comp < 3; ++comp) { const T r = fs[comp] + V.sy[(2 + comp) * cells + cc]; e += r * r; }
+        }
+        acc += T(0.5) * e;
+    }
+    return acc;
+}
+// epilogue: the last PCGStep3 and the state back to the plan's vectors
+template <class T, int KMAX>
+SFS_HD void sfsLoopStore(const SfsData<T>& P, const SfsTileView<T>& V, const SfsLoopRegs<T, KMAX>& R, int tid, int NT, bool stepped, T beta,
+                         T* delta, T* r, T* z, T* p, T* Ap) {
+    const int PW = V.PW();
+    SFS_UNROLL for (int q = 0; q < KMAX; ++q) {
+        int ty, tx; long gi;
+        if (sfsLoopPixel(P, V, tid + q * NT, ty, tx, gi)) {
+            T pp = V.sp[(ty + 2) * PW + tx + 2];
+            if (stepped) pp = R.z[q] + beta * pp;
+            p[gi] = pp; delta[gi] = R.delta[q]; r[gi] = R.r[q]; z[gi] = R.z[q]; Ap[gi] = R.ap[q];
+        }
+    }
+}
+
+}  // namespace optb

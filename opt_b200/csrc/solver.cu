@@ -260,6 +260,10 @@ __global__ void k_lmZeta(ReduceWorkspace ws, int lIter, T qTol) {
 template <class T> __global__ void __launch_bounds__(kBlock) k_axpyInto(long n, T* __restrict__ x, const T* __restrict__ d) {   // PCGLinearUpdate :552-557
     for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long)gridDim.x * kBlock) x[i] = x[i] + d[i];
 }
+// LM: savePreviousUnknowns + PCGLinearUpdate in one pass (:1108-1113, :552-557)
+template <class T> __global__ void __launch_bounds__(kBlock) k_saveAndUpdate(long n, T* __restrict__ saved, T* __restrict__ x, const T* __restrict__ d) {
+    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long)gridDim.x * kBlock) { const T v = x[i]; saved[i] = v; x[i] = v + d[i]; }
+}
 template <class T> __global__ void __launch_bounds__(kBlock) k_copy(long n, T* __restrict__ dst, const T* __restrict__ src) {
     for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long)gridDim.x * kBlock) dst[i] = src[i];
 }
@@ -420,6 +424,7 @@ struct Plan : PlanBase {
         // not cost the fast path: by default the table has one row per REGION (PCGInit1, the whole PCG loop, update, cost);
         // OPTB_TIMING_TABLE=1 switches to one row per kernel by issuing the per-step kernels individually.
         if (collectTiming) { timingOn = true; if (getenv("OPTB_TIMING_TABLE")) { timingFine = true; useGraph = false; useFusion = false; persistentMode = 0; } }
+        useOnChipLoop = persistentMode != 0;   // OPTB_PERSISTENT=0: kernel-per-step loops only
         if (verbosity > 1) printf("opt_b200: plan %s %s %s: %ld unknowns (padded), %d SMs\n", E->name(), lm ? "LM" : "GN", sizeof(T) == 8 ? "fp64" : "fp32", n, numSMs);
     }
     ~Plan() override {
@@ -679,7 +684,17 @@ struct Plan : PlanBase {
         bool pending = false;
         T *cur = p, *alt = p2;
         const bool kernelHalo = world > 1 && fuse && E->inKernelHalo();   // z / p0 halos move inside the J^T J kernels
-        for (int l = 0; l < L; ++l) {
+        // single GPU: the loop as ONE launch with its state on chip, where the energy offers it (shape_from_shading: 3 launches per PCG
+        // step otherwise, each bound by its own launch / drain latency at 640x480); what it does not cover is emitted kernel by kernel
+        int l0 = 0;
+        loopDidModelCost = false;
+        if (world == 1 && useOnChipLoop && !timingFine) {
+            bool mc = false;
+            l0 = E->pcgLoopOnChip(c, L, lm, lm ? sp.residual_reset_period : 0, (T)sp.q_tolerance, delta, r, z, cur, Ap, pre, b, ctc, (lm && maxLinIters < 0) ? &mc : nullptr);
+            if (l0 > 0) ++launches;
+            loopDidModelCost = l0 == L && mc;
+        }
+        for (int l = l0; l < L; ++l) {
             int rzOld = l & 1, rzNew = (l + 1) & 1;
             if (pending) {
                 // Step3 of iteration l-1 (beta = rz[rzOld_now]/rz[rzNew_now^...]) fused into this Step1
@@ -822,7 +837,7 @@ struct Plan : PlanBase {
     // the fingerprint of its by-value arguments changes (as for the loop graph).  The reference issues ~15 + 3 L launches and one blocking
     // copy per PCG step here; for shape_from_shading (L = 10) the launches outside the loop were 45 % of an iteration.
     cudaGraphExec_t iterExec = nullptr; unsigned long long iterKey = 0; int iterLaunchCount = 0; T* iterPFinal = nullptr;
-    bool useIterGraph = true, lastLoopPersistent = false;
+    bool useIterGraph = true, lastLoopPersistent = false, useOnChipLoop = true, loopDidModelCost = false;
     double* hRadius = nullptr;
     void uploadRadius() {
         if (!hRadius) OPT_CUDA_CHECK(cudaMallocHost((void**)&hRadius, sizeof(double)));
@@ -832,8 +847,10 @@ struct Plan : PlanBase {
     void enqueueIterationForCapture(int L) {   // the launch sequence of step() without its timing hooks; nIter >= 1 (no PCGSaveSSq)
         LaunchCtx c = ctx();
         if (lm) OPT_CUDA_CHECK(cudaMemcpyAsync(ws.scalars + kRadius, hRadius, sizeof(double), cudaMemcpyHostToDevice, stream));
-        E->pcgInit(c, delta, r, pre, p, kRz0); ++launches;
-        if (lm) {
+        const bool fusedHead = lm && world == 1 && E->pcgInitLM(c, delta, r, pre, p, CtC, SSq, b, kRz0, min_lm_diagonal, max_lm_diagonal, false);
+        if (fusedHead) ++launches;
+        else { E->pcgInit(c, delta, r, pre, p, kRz0); ++launches; }
+        if (lm && !fusedHead) {
             E->computeCtC(c, CtC, T(1)); ++launches;
             k_lmFinalizeDiagonal<T><<<gridStream, kBlock, 0, stream>>>(winScalar.n ? winScalar.total : n, winScalar, ws, ownScalar, kRz0, CtC, SSq, pre, r, b, p, delta, min_lm_diagonal, max_lm_diagonal); ++launches;
             k_copyScalar<<<1, 1, 0, stream>>>(ws, kQPrev, kQ);
@@ -845,11 +862,13 @@ struct Plan : PlanBase {
         OPT_CUDA_CHECK(cudaEventRecordWithFlags(evLoop0, stream, cudaEventRecordExternal));
         emitLoop(L, fuse);   // (the one-kernel loops are not captured: their reduction sequence numbers are launch arguments -- see launchIterationGraph)
         OPT_CUDA_CHECK(cudaEventRecordWithFlags(evLoop1, stream, cudaEventRecordExternal));
-        if (lm) {
-            E->modelCost(c, delta); ++launches;
-            for (auto& u : E->unknowns) { long cnt = u.elements * u.channels; k_copy<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, prevX + u.offset, (const T*)u.user); ++launches; }
+        if (lm && !loopDidModelCost) { E->modelCost(c, delta); ++launches; }
+        for (auto& u : E->unknowns) {
+            long cnt = u.elements * u.channels;
+            if (lm) k_saveAndUpdate<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, prevX + u.offset, (T*)u.user, delta + u.offset);
+            else k_axpyInto<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, (T*)u.user, delta + u.offset);
+            ++launches;
         }
-        for (auto& u : E->unknowns) { long cnt = u.elements * u.channels; k_axpyInto<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, (T*)u.user, delta + u.offset); ++launches; }
         E->precompute(c);
         E->cost(c); ++launches;
         if (world > 1) { k_finalizeScalars<<<1, 32, 0, stream>>>(ws, (1u << kRz0) | (1u << kRz1) | (1u << kPAp) | (1u << kCost) | (1u << kModelCost) | (1u << kQ)); ++launches; }
@@ -915,12 +934,15 @@ struct Plan : PlanBase {
                 return decide((T)hScalars[kCost], c);
             }
         }
+        if (lm) uploadRadius();
         tBegin("PCGInit1");
-        E->pcgInit(c, delta, r, pre, p, kRz0); ++launches;          // PCGInit1 (+_Graph,+_Finish)
+        // one launch for PCGInit1 and the LM head (:1038-1053) where the energy offers it
+        const bool fusedHead = lm && world == 1 && E->pcgInitLM(c, delta, r, pre, p, CtC, SSq, b, kRz0, min_lm_diagonal, max_lm_diagonal, nIter == 0);
+        if (!fusedHead) E->pcgInit(c, delta, r, pre, p, kRz0);          // PCGInit1 (+_Graph,+_Finish)
+        ++launches;
         tEnd();
-        if (lm) {   // :1038-1053
+        if (lm && !fusedHead) {   // :1038-1053
             if (nIter == 0) { k_copy<T><<<gridStream, kBlock, 0, stream>>>(n, SSq, pre); ++launches; }   // PCGSaveSSq
-            uploadRadius();
             E->computeCtC(c, CtC, T(1)); ++launches;
             k_lmFinalizeDiagonal<T><<<gridStream, kBlock, 0, stream>>>(winScalar.n ? winScalar.total : n, winScalar, ws, ownScalar, kRz0, CtC, SSq, pre, r, b, p, delta, min_lm_diagonal, max_lm_diagonal); ++launches;
             k_copyScalar<<<1, 1, 0, stream>>>(ws, kQPrev, kQ);          // Q0 = fetchQ
@@ -933,14 +955,13 @@ struct Plan : PlanBase {
         runLoop(L);
         if (!timingFine) tEnd();
         if (maxLinIters >= 0) { OPT_CUDA_CHECK(cudaStreamSynchronize(stream)); return 1; }   // debug hook: PCG state left for inspection
-        if (lm) {   // :1108-1113
-            E->modelCost(c, delta); ++launches;
-            for (auto& u : E->unknowns) { long cnt = u.elements * u.channels; k_copy<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, prevX + u.offset, (const T*)u.user); ++launches; }   // savePreviousUnknowns
-        }
+        if (lm && !loopDidModelCost) { E->modelCost(c, delta); ++launches; }   // :1108-1113 (the one-launch loop may have left it already)
         tBegin("PCGLinearUpdate");
-        for (auto& u : E->unknowns) {   // PCGLinearUpdate :552-557 (delta is 0 on excluded entries)
+        for (auto& u : E->unknowns) {   // LM: savePreviousUnknowns, then PCGLinearUpdate :552-557 (delta is 0 on excluded entries)
             long cnt = u.elements * u.channels;
-            k_axpyInto<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, (T*)u.user, delta + u.offset); ++launches;
+            if (lm) k_saveAndUpdate<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, prevX + u.offset, (T*)u.user, delta + u.offset);
+            else k_axpyInto<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, (T*)u.user, delta + u.offset);
+            ++launches;
         }
         tEnd();
         E->precompute(c);

@@ -94,6 +94,19 @@ struct EnergyOps {
     // haloZ != nullptr: multi-GPU (the plan's halo description of z, host copy); p's halo rows have been exchanged by the caller.
     virtual bool pcgLoop(const LaunchCtx&, int /*L*/, bool /*force*/, T* /*delta*/, T* /*r*/, T* /*z*/, T* /*p*/, T* /*p2*/, T* /*Ap*/,
                          const T* /*pre*/, T** /*pFinal*/, const HaloPlan* /*haloZ*/ = nullptr) { return false; }
+    // optional, single GPU: PCGInit1 AND the LM head that follows it (PCGSaveSSq at the first nonlinear iteration, PCGComputeCtC,
+    // PCGFinalizeDiagonal, Q0 = q, early-out flag = 0; solverGPUGaussNewton.t:1038-1053) in one launch.  The trust-region radius is read
+    // from scalars[kRadius].  Returns false (nothing launched) when not implemented.
+    virtual bool pcgInitLM(const LaunchCtx&, T* /*delta*/, T* /*r*/, T* /*pre*/, T* /*p*/, T* /*CtC*/, T* /*SSq*/, T* /*b*/, int /*rzSlot*/,
+                           T /*minDiag*/, T /*maxDiag*/, bool /*saveSSq*/) { return false; }
+    // optional, single GPU: the L iterations of the PCG loop (LM: with the residual reset every resetPeriod-th iteration and the zeta
+    // early-out) as one capturable launch with the state on chip; in place on the plan's vectors, scalars (rz pair, p.Ap, q, Q0,
+    // early-out flag) left exactly as L iterations of the kernel-per-step loop leave them.  Returns the number of iterations covered
+    // (0: not implemented / does not fit; the caller emits the rest kernel by kernel).
+    // modelCostDone != nullptr (LM, the call covers the whole loop): the kernel may also leave computeModelCost (:666-678) of the delta
+    // it found in scalars[kModelCost] and says so there; the caller then skips modelCost().
+    virtual int pcgLoopOnChip(const LaunchCtx&, int /*L*/, bool /*lm*/, int /*resetPeriod*/, T /*qTolerance*/, T* /*delta*/, T* /*r*/, T* /*z*/, T* /*p*/, T* /*Ap*/,
+                              const T* /*pre*/, const T* /*b*/, const T* /*CtC*/, bool* /*modelCostDone*/) { return 0; }
     // computeCost (+_Graph): scalars[kCost] = 1/2 sum r^2
     virtual void cost(const LaunchCtx& c) = 0;
     // LM: CtC <- diag(J^T J)/radius (PCGComputeCtC), scalars[kModelCost] = 1/2 sum (r + J delta)^2

@@ -221,12 +221,13 @@ __global__ void __launch_bounds__(kBlock) k_sfsInitTiled(SfsData<T> P, ReduceWor
 // two all-reduces (p.Ap; then r.z and q in one round).  LM: zeta = (l+1)(Q1-Q0)/Q1 < q_tolerance ends the loop in every CTA at once
 // (they all hold the same reduced q); the flag word tells the per-step kernels of a following residual-reset iteration to do nothing.
 // The reduction sequence number lives in device memory (seqWord) so that the launch is replayable from a captured graph.
-template <class T, int KMAX>
-__global__ void __launch_bounds__(1024, 1) k_sfsLoopResident(SfsData<T> P, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long* arrivals, unsigned long long* seqWord,
+// Tail (LM): computeModelCost of the delta found (one more tile-edge exchange of delta, the rows applied to it, F + J delta summed) and
+// the update of the unknowns, so that a nonlinear iteration is head + this kernel + precompute/cost.
+template <class T, int KMAX, int NT>
+__global__ void __launch_bounds__(NT, 1) k_sfsLoopResident(SfsData<T> P, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long* arrivals, unsigned long long* seqWord,
                                                              int L, int tw, int th, int tilesX, int usePre, int lm, int resetPeriod, int withModelCost, T qTol,
-                                                             T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC) {
+                                                             T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC, T* xUpdate, T* xSaved) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    constexpr int NT = 1024;
     const int tid = threadIdx.x;
     const SfsTileView<T> V = sfsCarveTile<T>(smemRaw, ((int)blockIdx.x % tilesX) * tw, ((int)blockIdx.x / tilesX) * th, tw, th, true);
     SfsLoopRegs<T, KMAX> R;
@@ -288,7 +289,9 @@ __global__ void __launch_bounds__(1024, 1) k_sfsLoopResident(SfsData<T> P, Reduc
     }
     T beta = T(0);
     { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
-    sfsLoopStore<T, KMAX>(P, V, R, tid, NT, done > 0, beta, delta, r, z, p, Ap);
+    // xUpdate: savePreviousUnknowns + PCGLinearUpdate (:1108-1113, :552-557) for the tile as well -- nobody reads X any more (the model cost's
+    // rows did, across tiles, but every CTA is past its all-reduce)
+    sfsLoopStore<T, KMAX>(P, V, R, tid, NT, done > 0, beta, delta, r, z, p, Ap, xUpdate, xSaved);
     if (blockIdx.x == 0 && tid == 0 && done > 0) {   // leave the scalars as the kernel-per-step loop does (iteration l reads rz[l&1], writes rz[(l+1)&1])
         ws.scalars[kPAp] = dPAp; ws.scalars[done & 1] = dRz; ws.scalars[(done + 1) & 1] = dRzPrev;
         if (lm) { ws.scalars[kQ] = dQ; ws.scalars[kQPrev] = (double)Q0; if (broke >= 0) ws.scalars[kFlags] = 1.0 + broke; }
@@ -337,19 +340,27 @@ struct SfsOps : EnergyOps<T> {
         fusedHead = tiled && !getenv("OPTB_SFS_NO_FUSED_INIT");
         fuseCost = !getenv("OPTB_SFS_NO_FUSED_COST");
         fuseModel = !getenv("OPTB_SFS_NO_FUSED_MODEL");
+        fuseUpdate = !getenv("OPTB_SFS_NO_FUSED_UPDATE");
         if (tiled && !getenv("OPTB_SFS_NO_RESIDENT")) setUpResidentLoop(dev, sms);
     }
     int tilesX = 0, numTiles = 0, gridTiled = 1, gridInit = 1; bool tiled = true, fusedHead = true;
     // ---- whole-loop kernel: tile shape, shared memory, reduction words (all fixed for the life of the plan)
     static constexpr int kLoopK = 3;              // pixels per thread
-    int loopTW = 0, loopTH = 0, loopTilesX = 0, loopGrid = 0; size_t loopSmem = 0;
+    int loopTW = 0, loopTH = 0, loopTilesX = 0, loopGrid = 0, loopNT = 1024; size_t loopSmem = 0;
+    const void* loopFn() const {
+        return loopNT == 768 ? (const void*)k_sfsLoopResident<T, kLoopK, 768> : (loopNT == 832 ? (const void*)k_sfsLoopResident<T, kLoopK, 832> : (const void*)k_sfsLoopResident<T, kLoopK, 1024>);
+    }
     unsigned long long* loopWords = nullptr;      // [2 parities][kMaxLLCtas + 1][4] reduction words, arrival counter, sequence word
     void setUpResidentLoop(int dev, int sms) {
         int coop = 0, maxSmem = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (!coop) return;
-        const void* fn = (const void*)k_sfsLoopResident<T, kLoopK>;
+        // threads per CTA: 1024 leaves the third pixel round of a 64x35 tile 19 % full; 832 and 768 fill their three rounds better with fewer
+        // warps to hide latency (A/B on hardware: OPTB_SFS_LOOP_NT)
+        loopNT = 1024;
+        if (const char* e = getenv("OPTB_SFS_LOOP_NT")) { const int v = atoi(e); if (v == 768 || v == 832 || v == 1024) loopNT = v; }
+        const void* fn = loopFn();
         cudaFuncAttributes fa{};
         if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) { cudaGetLastError(); return; }
         // one tile per SM at most; tile widths in multiples of 32 (warp = one tile row segment), the squarest shape that fits wins:
@@ -360,7 +371,7 @@ struct SfsOps : EnergyOps<T> {
             if (tx > sms || tx > kMaxLLCtas) continue;
             int th = (P.H + sms / tx - 1) / (sms / tx);
             if (th < 4) th = 4;
-            if ((long)tw * th > (long)kLoopK * 1024) continue;
+            if ((long)tw * th > (long)kLoopK * loopNT) continue;
             const size_t bytes = sfsTilePlaneBytes<T>(tw, th, true);
             if (bytes + fa.sharedSizeBytes > (size_t)maxSmem) continue;
             const long cost = (long)(tw + 2) * (th + 2) + (long)(tw + 4) * (th + 4);
@@ -369,7 +380,7 @@ struct SfsOps : EnergyOps<T> {
         if (best < 0) { loopTW = 0; return; }
         int occ = 0;
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)loopSmem) != cudaSuccess
-            || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 1024, loopSmem) != cudaSuccess || occ < 1 || loopGrid > sms * occ || loopGrid > kMaxLLCtas) {
+            || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, loopNT, loopSmem) != cudaSuccess || occ < 1 || loopGrid > sms * occ || loopGrid > kMaxLLCtas) {
             cudaGetLastError(); loopTW = 0; return;
         }
         // a cooperative launch inside a stream capture must work: the loop kernel is a node of the plan's PCG-loop / iteration graphs
@@ -397,7 +408,7 @@ struct SfsOps : EnergyOps<T> {
     ~SfsOps() override { cudaFree(P.B); cudaFree(P.dB); cudaFree(P.cR); cudaFree(P.cC); cudaFree(P.fl); cudaFree(loopWords); }
     const char* name() const override { return "shape_from_shading"; }
     bool capturable() const override { return true; }
-    unsigned long long captureKey() const override { const int shape[] = { loopTW, loopTH, (int)fusedHead, (int)tiled, (int)fuseCost, (int)fuseModel }; return EnergyOps<T>::hashBytes(shape, sizeof(shape), EnergyOps<T>::hashValue(P)); }
+    unsigned long long captureKey() const override { const int shape[] = { loopTW, loopTH, loopNT, (int)fusedHead, (int)tiled, (int)fuseCost, (int)fuseModel, (int)fuseUpdate }; return EnergyOps<T>::hashBytes(shape, sizeof(shape), EnergyOps<T>::hashValue(P)); }
     void bind(void** q) override {   // positions: shape_from_shading.t:5-28 (all scalar Params are float, cast to opt_float on use, o.t:1699)
         auto f = [&](int k) { return (T) * (const float*)q[k]; };
         costFresh = false;
@@ -430,18 +441,21 @@ struct SfsOps : EnergyOps<T> {
         k_sfsInitTiled<T, true><<<gridInit, kBlock, 0, c.stream>>>(P, c.ws, rzSlot, O, this->usePreconditioner ? 1 : 0, saveSSq ? 1 : 0, minDiag, maxDiag, tilesX, numTiles);
         return true;
     }
-    bool fuseModel = true;
+    bool fuseModel = true, fuseUpdate = true;
     int pcgLoopOnChip(const LaunchCtx& c, int L, bool lm, int resetPeriod, T qTol, T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC,
-                      bool* modelCostDone) override {
+                      bool* modelCostDone, T* prevX, bool* updateDone) override {
         if (!loopTW || L < 2) return 0;
         int withModel = (lm && fuseModel && modelCostDone) ? 1 : 0;
         if (modelCostDone) *modelCostDone = withModel != 0;
+        T* xUpdate = (updateDone && fuseUpdate && (!lm || prevX)) ? const_cast<T*>(P.X) : nullptr;   // the one unknown array of this energy, offset 0 in the plan's vectors
+        T* xSaved = lm ? prevX : nullptr;
+        if (updateDone) *updateDone = xUpdate != nullptr;
         ReduceWorkspace ws = c.ws;
         unsigned long long* arrivals = loopWords + 2 * 4 * (kMaxLLCtas + 1); unsigned long long* seqWord = arrivals + 1;
         int usePre = this->usePreconditioner ? 1 : 0, lmi = lm ? 1 : 0;
         void* args[] = { (void*)&P, (void*)&ws, (void*)&loopWords, (void*)&arrivals, (void*)&seqWord, (void*)&L, (void*)&loopTW, (void*)&loopTH, (void*)&loopTilesX, (void*)&usePre, (void*)&lmi,
-                         (void*)&resetPeriod, (void*)&withModel, (void*)&qTol, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre, (void*)&b, (void*)&CtC };
-        OPT_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_sfsLoopResident<T, kLoopK>, dim3((unsigned)loopGrid), dim3(1024), args, loopSmem, c.stream));
+                         (void*)&resetPeriod, (void*)&withModel, (void*)&qTol, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre, (void*)&b, (void*)&CtC, (void*)&xUpdate, (void*)&xSaved };
+        OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(loopFn(), dim3((unsigned)loopGrid), dim3((unsigned)loopNT), args, loopSmem, c.stream));
         return L;
     }
     void applyJTJ(const LaunchCtx& c, const T* x, T* out, const T* CtC, int dotSlot, const HaloPlan*) override {

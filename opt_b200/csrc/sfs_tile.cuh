@@ -24,12 +24,15 @@ struct SfsTileView {
     int x0, y0, tw, th;          // image coordinates of the tile's first pixel, nominal extent
     T* sp; T* sc; T* sy; unsigned char* sfl; T* sAx; T* sAy;
     T* sd;                       // whole-loop kernel only: delta with a 2-pixel ring, for the residual-reset iterations (nullptr otherwise)
+    unsigned mTW, mRW, mPW;      // ceil(2^32 / d) for d = tw, tw + 2, tw + 4: index -> (row, column) without an integer division (exact below 2^16)
     SFS_HD int RW() const { return tw + 2; }
     SFS_HD int RH() const { return th + 2; }
     SFS_HD int PW() const { return tw + 4; }
     SFS_HD int PH() const { return th + 4; }
     SFS_HD int cells() const { return (tw + 2) * (th + 2); }
 };
+SFS_HD unsigned sfsMagic(int d) { return (unsigned)((0x100000000ull + (unsigned long long)d - 1ull) / (unsigned long long)d); }
+SFS_HD int sfsFastDiv(int c, unsigned magic) { return (int)(((unsigned long long)(unsigned)c * magic) >> 32); }   // c / d for 0 <= c < 2^16, 2 <= d < 2^16
 // bytes of the planes above for a tw x th tile (sp, sc, sy, the two factor tables, then the flag bytes), each plane 16-byte aligned
 SFS_HD constexpr size_t sfsUp16(size_t v) { return (v + 15) / 16 * 16; }
 template <class T> SFS_HD constexpr size_t sfsTilePlaneBytes(int tw, int th, bool withDelta = false) {
@@ -38,6 +41,7 @@ template <class T> SFS_HD constexpr size_t sfsTilePlaneBytes(int tw, int th, boo
 }
 template <class T> SFS_HD SfsTileView<T> sfsCarveTile(unsigned char* base, int x0, int y0, int tw, int th, bool withDelta = false) {
     SfsTileView<T> V; V.x0 = x0; V.y0 = y0; V.tw = tw; V.th = th;
+    V.mTW = sfsMagic(tw); V.mRW = sfsMagic(tw + 2); V.mPW = sfsMagic(tw + 4);
     const size_t cells = (size_t)(tw + 2) * (th + 2), pcells = (size_t)(tw + 4) * (th + 4);
     V.sp = reinterpret_cast<T*>(base); base += sfsUp16(pcells * sizeof(T));
     V.sd = nullptr;
@@ -57,7 +61,7 @@ template <class T> SFS_HD void sfsTileFactors(const SfsData<T>& P, const SfsTile
 }
 template <class T> SFS_HD void sfsTileStageCell(const SfsData<T>& P, const SfsTileView<T>& V, int c) {
     const int RW = V.RW(), cells = V.cells();
-    const int ly = c / RW, lx = c - ly * RW, gx = V.x0 - 1 + lx, gy = V.y0 - 1 + ly;
+    const int ly = sfsFastDiv(c, V.mRW), lx = c - ly * RW, gx = V.x0 - 1 + lx, gy = V.y0 - 1 + ly;
     const long N = sfsN(P);
     unsigned f = 0;
     T co[10] = { T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0) };
@@ -75,20 +79,26 @@ template <class T> SFS_HD void sfsTileStageCell(const SfsData<T>& P, const SfsTi
 // ---- row values of cell c:  y = row . sp   (rows with a zero coefficient contribute an exact 0 instead of being skipped)
 template <class T> SFS_HD void sfsTileRowsTimesVec(const SfsData<T>& P, const SfsTileView<T>& V, int c, const T* vec) {   // vec: V.sp or V.sd
     const int RW = V.RW(), PW = V.PW(), cells = V.cells();
-    const int ly = c / RW, lx = c - ly * RW;
+    const int ly = sfsFastDiv(c, V.mRW), lx = c - ly * RW;
     const unsigned f = V.sfl[c];
     T y[5] = { T(0), T(0), T(0), T(0), T(0) };
-    if (f & kSfsInner) {
-        SFS_UNROLL for (int t = 0; t < 2; ++t)
-            SFS_UNROLL for (int m = 0; m < 5; ++m) y[t] += V.sc[(t * 5 + m) * cells + c] * vec[(ly + 1 + sfsDy(t, m)) * PW + lx + 1 + sfsDx(t, m)];
-    }
-    if (f & kSfsFlat) {
-        const T ax[3] = { V.sAx[lx], V.sAx[lx + 1], V.sAx[lx + 2] }, ay[3] = { V.sAy[ly], V.sAy[ly + 1], V.sAy[ly + 2] };   // columns gx-1..gx+1, rows gy-1..gy+1
-        SFS_UNROLL for (int m = 0; m < 5; ++m) {
-            const T pm = vec[(ly + 1 + sfsDy(2, m)) * PW + lx + 1 + sfsDx(2, m)];
-            y[2] += sfsCoefFromA(P, ax[1 + sfsDx(2, m)], m) * pm;
-            y[3] += sfsCoefFromA(P, ay[1 + sfsDy(2, m)], m) * pm;
-            y[4] += sfsCoefFromA(P, T(1), m) * pm;
+    if (f & (kSfsInner | kSfsFlat)) {
+        // the seven entries the three row types read between them (dependency tables of sfs_device.cuh), loaded once
+        const T* v0 = vec + (ly + 1) * PW + lx + 1;
+        const T c00 = v0[0], cm0 = v0[-1], cp0 = v0[1], c0m = v0[-PW], c0p = v0[PW], cpm = v0[1 - PW], cmp = v0[PW - 1];
+        if (f & kSfsInner) {
+            const T* a = V.sc + c;   // r_gR: (0,0) (-1,0) (0,-1) (1,0) (1,-1)     r_gC: (0,0) (-1,0) (0,-1) (0,1) (-1,1)
+            y[0] += a[0] * c00; y[0] += a[cells] * cm0; y[0] += a[2 * cells] * c0m; y[0] += a[3 * cells] * cp0; y[0] += a[4 * cells] * cpm;
+            y[1] += a[5 * cells] * c00; y[1] += a[6 * cells] * cm0; y[1] += a[7 * cells] * c0m; y[1] += a[8 * cells] * c0p; y[1] += a[9 * cells] * cmp;
+        }
+        if (f & kSfsFlat) {                                                        // r_s: (0,0) (-1,0) (0,-1) (1,0) (0,1)
+            const T ax[3] = { V.sAx[lx], V.sAx[lx + 1], V.sAx[lx + 2] }, ay[3] = { V.sAy[ly], V.sAy[ly + 1], V.sAy[ly + 2] };   // columns gx-1..gx+1, rows gy-1..gy+1
+            const T pm[5] = { c00, cm0, c0m, cp0, c0p };
+            SFS_UNROLL for (int m = 0; m < 5; ++m) {
+                y[2] += sfsCoefFromA(P, ax[1 + sfsDx(2, m)], m) * pm[m];
+                y[3] += sfsCoefFromA(P, ay[1 + sfsDy(2, m)], m) * pm[m];
+                y[4] += sfsCoefFromA(P, T(1), m) * pm[m];
+            }
         }
     }
     SFS_UNROLL for (int k = 0; k < 5; ++k) V.sy[k * cells + c] = y[k];
@@ -96,7 +106,7 @@ template <class T> SFS_HD void sfsTileRowsTimesVec(const SfsData<T>& P, const Sf
 // ---- row values of cell c:  y = F(row), the residuals at the current X (sfsFR, sfsFC, sfsFS of sfs_device.cuh, factors from the tables)
 template <class T> SFS_HD void sfsTileRowResiduals(const SfsData<T>& P, const SfsTileView<T>& V, int c) {
     const int RW = V.RW(), cells = V.cells();
-    const int ly = c / RW, lx = c - ly * RW, gx = V.x0 - 1 + lx, gy = V.y0 - 1 + ly;
+    const int ly = sfsFastDiv(c, V.mRW), lx = c - ly * RW, gx = V.x0 - 1 + lx, gy = V.y0 - 1 + ly;
     const unsigned f = V.sfl[c];
     T y[5] = { T(0), T(0), T(0), T(0), T(0) };
     if (f & (kSfsInner | kSfsFlat)) {   // either flag implies an in-image cell
@@ -200,7 +210,7 @@ struct SfsLoopRegs { T delta[KMAX], r[KMAX], b[KMAX], ctc[KMAX], pre[KMAX], z[KM
 
 template <class T> SFS_HD bool sfsLoopPixel(const SfsData<T>& P, const SfsTileView<T>& V, int c, int& ty, int& tx, long& gi) {
     if (c >= V.tw * V.th) return false;
-    ty = c / V.tw; tx = c - ty * V.tw;
+    ty = sfsFastDiv(c, V.mTW); tx = c - ty * V.tw;
     const int gx = V.x0 + tx, gy = V.y0 + ty;
     if (gx >= P.W || gy >= P.H) return false;
     gi = (long)gy * P.W + gx;
@@ -220,7 +230,7 @@ SFS_HD void sfsLoopLoad(const SfsData<T>& P, const SfsTileView<T>& V, SfsLoopReg
                         const T* CtC, const T* pre, const T* p, int usePre, int lm) {
     const int PW = V.PW(), pcells = PW * V.PH();
     for (int c = tid; c < pcells; c += NT) {
-        const int ly = c / PW, lx = c - ly * PW, gx = V.x0 - 2 + lx, gy = V.y0 - 2 + ly;
+        const int ly = sfsFastDiv(c, V.mPW), lx = c - ly * PW, gx = V.x0 - 2 + lx, gy = V.y0 - 2 + ly;
         V.sp[c] = sfsInImage(P, gx, gy) ? p[(long)gy * P.W + gx] : T(0);
         if (V.sd) V.sd[c] = T(0);
     }
@@ -246,8 +256,8 @@ SFS_HD void sfsLoopUpdateDirection(const SfsData<T>& P, const SfsTileView<T>& V,
     const int nRing = 4 * PW + 4 * V.th;
     for (int j = tid; j < nRing; j += NT) {
         int ly, lx;
-        if (j < 2 * PW) { ly = j / PW; lx = j - ly * PW; }
-        else if (j < 4 * PW) { const int jj = j - 2 * PW; ly = jj / PW; lx = jj - ly * PW; ly += PH - 2; }
+        if (j < 2 * PW) { ly = j >= PW ? 1 : 0; lx = j - ly * PW; }
+        else if (j < 4 * PW) { const int jj = j - 2 * PW; ly = jj >= PW ? 1 : 0; lx = jj - ly * PW; ly += PH - 2; }
         else { const int jj = j - 4 * PW; ly = 2 + (jj >> 2); const int s = jj & 3; lx = s < 2 ? s : PW - 4 + s; }
         const int gx = V.x0 - 2 + lx, gy = V.y0 - 2 + ly;
         if (sfsInImage(P, gx, gy)) { const int cc = ly * PW + lx; V.sp[cc] = SFS_LD_CG(zGlobal + (long)gy * P.W + gx) + beta * V.sp[cc]; }
@@ -311,8 +321,8 @@ SFS_HD void sfsLoopFetchRing(const SfsData<T>& P, const SfsTileView<T>& V, int t
     const int nRing = 4 * PW + 4 * V.th;
     for (int j = tid; j < nRing; j += NT) {
         int ly, lx;
-        if (j < 2 * PW) { ly = j / PW; lx = j - ly * PW; }
-        else if (j < 4 * PW) { const int jj = j - 2 * PW; ly = jj / PW; lx = jj - ly * PW; ly += PH - 2; }
+        if (j < 2 * PW) { ly = j >= PW ? 1 : 0; lx = j - ly * PW; }
+        else if (j < 4 * PW) { const int jj = j - 2 * PW; ly = jj >= PW ? 1 : 0; lx = jj - ly * PW; ly += PH - 2; }
         else { const int jj = j - 4 * PW; ly = 2 + (jj >> 2); const int s = jj & 3; lx = s < 2 ? s : PW - 4 + s; }
         const int gx = V.x0 - 2 + lx, gy = V.y0 - 2 + ly;
         if (sfsInImage(P, gx, gy)) plane[ly * PW + lx] = SFS_LD_CG(vGlobal + (long)gy * P.W + gx);
@@ -390,7 +400,7 @@ SFS_HD T sfsLoopModelCost(const SfsData<T>& P, const SfsTileView<T>& V, const Sf
 // epilogue: the last PCGStep3 and the state back to the plan's vectors
 template <class T, int KMAX>
 SFS_HD void sfsLoopStore(const SfsData<T>& P, const SfsTileView<T>& V, const SfsLoopRegs<T, KMAX>& R, int tid, int NT, bool stepped, T beta,
-                         T* delta, T* r, T* z, T* p, T* Ap) {
+                         T* delta, T* r, T* z, T* p, T* Ap, T* X = nullptr, T* prevX = nullptr) {   // X != nullptr: savePreviousUnknowns (prevX) + PCGLinearUpdate too
     const int PW = V.PW();
     SFS_UNROLL for (int q = 0; q < KMAX; ++q) {
         int ty, tx; long gi;
@@ -398,6 +408,7 @@ SFS_HD void sfsLoopStore(const SfsData<T>& P, const SfsTileView<T>& V, const Sfs
             T pp = V.sp[(ty + 2) * PW + tx + 2];
             if (stepped) pp = R.z[q] + beta * pp;
             p[gi] = pp; delta[gi] = R.delta[q]; r[gi] = R.r[q]; z[gi] = R.z[q]; Ap[gi] = R.ap[q];
+            if (X) { const T x = X[gi]; if (prevX) prevX[gi] = x; X[gi] = x + R.delta[q]; }
         }
     }
 }

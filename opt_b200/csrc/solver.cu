@@ -687,12 +687,15 @@ struct Plan : PlanBase {
         // single GPU: the loop as ONE launch with its state on chip, where the energy offers it (shape_from_shading: 3 launches per PCG
         // step otherwise, each bound by its own launch / drain latency at 640x480); what it does not cover is emitted kernel by kernel
         int l0 = 0;
-        loopDidModelCost = false;
+        loopDidModelCost = false; loopDidUpdate = false;
         if (world == 1 && useOnChipLoop && !timingFine) {
-            bool mc = false;
-            l0 = E->pcgLoopOnChip(c, L, lm, lm ? sp.residual_reset_period : 0, (T)sp.q_tolerance, delta, r, z, cur, Ap, pre, b, ctc, (lm && maxLinIters < 0) ? &mc : nullptr);
+            bool mc = false, up = false;
+            const bool whole = maxLinIters < 0;   // (the debug hook leaves the PCG state for inspection: no model cost, no update)
+            l0 = E->pcgLoopOnChip(c, L, lm, lm ? sp.residual_reset_period : 0, (T)sp.q_tolerance, delta, r, z, cur, Ap, pre, b, ctc, (lm && whole) ? &mc : nullptr,
+                                  lm ? prevX : nullptr, whole ? &up : nullptr);
             if (l0 > 0) ++launches;
-            loopDidModelCost = l0 == L && mc;
+            if (l0 > 0 && l0 != L && (mc || up)) { fprintf(stderr, "opt_b200: pcgLoopOnChip covered %d of %d iterations but ran its tail\n", l0, L); exit(2); }
+            loopDidModelCost = l0 == L && mc; loopDidUpdate = l0 == L && up;
         }
         for (int l = l0; l < L; ++l) {
             int rzOld = l & 1, rzNew = (l + 1) & 1;
@@ -837,7 +840,7 @@ struct Plan : PlanBase {
     // the fingerprint of its by-value arguments changes (as for the loop graph).  The reference issues ~15 + 3 L launches and one blocking
     // copy per PCG step here; for shape_from_shading (L = 10) the launches outside the loop were 45 % of an iteration.
     cudaGraphExec_t iterExec = nullptr; unsigned long long iterKey = 0; int iterLaunchCount = 0; T* iterPFinal = nullptr;
-    bool useIterGraph = true, lastLoopPersistent = false, useOnChipLoop = true, loopDidModelCost = false;
+    bool useIterGraph = true, lastLoopPersistent = false, useOnChipLoop = true, loopDidModelCost = false, loopDidUpdate = false;
     double* hRadius = nullptr;
     void uploadRadius() {
         if (!hRadius) OPT_CUDA_CHECK(cudaMallocHost((void**)&hRadius, sizeof(double)));
@@ -863,7 +866,7 @@ struct Plan : PlanBase {
         emitLoop(L, fuse);   // (the one-kernel loops are not captured: their reduction sequence numbers are launch arguments -- see launchIterationGraph)
         OPT_CUDA_CHECK(cudaEventRecordWithFlags(evLoop1, stream, cudaEventRecordExternal));
         if (lm && !loopDidModelCost) { E->modelCost(c, delta); ++launches; }
-        for (auto& u : E->unknowns) {
+        if (!loopDidUpdate) for (auto& u : E->unknowns) {
             long cnt = u.elements * u.channels;
             if (lm) k_saveAndUpdate<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, prevX + u.offset, (T*)u.user, delta + u.offset);
             else k_axpyInto<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, (T*)u.user, delta + u.offset);
@@ -957,7 +960,7 @@ struct Plan : PlanBase {
         if (maxLinIters >= 0) { OPT_CUDA_CHECK(cudaStreamSynchronize(stream)); return 1; }   // debug hook: PCG state left for inspection
         if (lm && !loopDidModelCost) { E->modelCost(c, delta); ++launches; }   // :1108-1113 (the one-launch loop may have left it already)
         tBegin("PCGLinearUpdate");
-        for (auto& u : E->unknowns) {   // LM: savePreviousUnknowns, then PCGLinearUpdate :552-557 (delta is 0 on excluded entries)
+        if (!loopDidUpdate) for (auto& u : E->unknowns) {   // LM: savePreviousUnknowns, then PCGLinearUpdate :552-557 (delta is 0 on excluded entries)
             long cnt = u.elements * u.channels;
             if (lm) k_saveAndUpdate<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, prevX + u.offset, (T*)u.user, delta + u.offset);
             else k_axpyInto<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, (T*)u.user, delta + u.offset);

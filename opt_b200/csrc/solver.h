@@ -104,9 +104,10 @@ struct EnergyOps {
     // early-out flag) left exactly as L iterations of the kernel-per-step loop leave them.  Returns the number of iterations covered
     // (0: not implemented / does not fit; the caller emits the rest kernel by kernel).
     // modelCostDone != nullptr (LM, the call covers the whole loop): the kernel may also leave computeModelCost (:666-678) of the delta
-    // it found in scalars[kModelCost] and says so there; the caller then skips modelCost().
+    // it found in scalars[kModelCost] and says so there; the caller then skips modelCost().  updateDone != nullptr: likewise for
+    // savePreviousUnknowns (LM, into prevX, laid out like the plan's vectors) + PCGLinearUpdate of every unknown array.
     virtual int pcgLoopOnChip(const LaunchCtx&, int /*L*/, bool /*lm*/, int /*resetPeriod*/, T /*qTolerance*/, T* /*delta*/, T* /*r*/, T* /*z*/, T* /*p*/, T* /*Ap*/,
-                              const T* /*pre*/, const T* /*b*/, const T* /*CtC*/, bool* /*modelCostDone*/) { return 0; }
+                              const T* /*pre*/, const T* /*b*/, const T* /*CtC*/, bool* /*modelCostDone*/, T* /*prevX*/, bool* /*updateDone*/) { return 0; }
     // computeCost (+_Graph): scalars[kCost] = 1/2 sum r^2
     virtual void cost(const LaunchCtx& c) = 0;
     // LM: CtC <- diag(J^T J)/radius (PCGComputeCtC), scalars[kModelCost] = 1/2 sum (r + J delta)^2

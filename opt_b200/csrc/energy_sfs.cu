@@ -181,6 +181,24 @@ __global__ void __launch_bounds__(kBlock) k_sfsApplyJTJTiled(SfsData<T> P, Reduc
     }
     if (dotSlot >= 0) gridReduceTo<kBlock>((double)acc, ws, dotSlot);
 }
+// ------------------------------------------------------------------------------------ precompute + computeCost, tiled
+// kernels.precompute (:607-614) and computeCost (:580-592) in one pass over 32x8 tiles (sfsPreCell / sfsPrePixel in sfs_tile.cuh): dB never
+// goes through global memory and the three launches of the per-pixel path (k_sfsPrecomputeB, k_sfsBuildRows, k_sfsCost) become one.
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_sfsPrecomputeTiled(SfsData<T> P, ReduceWorkspace ws, int slot, int tilesX, int numTiles) {
+    __shared__ __align__(16) unsigned char planes[sfsPrePlaneBytes<T>(kSfsTW, kSfsTH)];
+    const int tid = threadIdx.x, tx = tid % kSfsTW, ty = tid / kSfsTW;
+    T acc = T(0);
+    for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        const SfsPreView<T> V = sfsCarvePre<T>(planes, (tile % tilesX) * kSfsTW, (tile / tilesX) * kSfsTH, kSfsTW, kSfsTH);
+        __syncthreads();   // the previous tile's pixels are done with the planes
+        for (int c = tid; c < V.bcells(); c += kBlock) sfsPreCell(P, V, c);
+        __syncthreads();
+        if (V.x0 + tx < P.W && V.y0 + ty < P.H) acc += sfsPrePixel(P, V, ty, tx);
+    }
+    gridReduceTo<kBlock>((double)acc, ws, slot);
+}
+
 // ------------------------------------------------------------------------------------ PCGInit1 (+ LM head), tiled
 // One pass over 32x8 tiles: the residual of every row centred in tile + 1-pixel ring is formed ONCE (the per-pixel k_sfsInit forms each
 // 5 / 15 times), then every pixel gathers -J^T F and diag J^T J from shared memory and finishes PCGInit1; LM: PCGSaveSSq (first
@@ -216,34 +234,49 @@ __global__ void __launch_bounds__(kBlock) k_sfsInitTiled(SfsData<T> P, ReduceWor
 
 // ------------------------------------------------------------------------------------ whole PCG loop, state on chip
 // L iterations of PCGStep1/2/3 (:1056-1102) from the state PCGInit1 (+ FinalizeDiagonal) left, as one cooperative kernel: one CTA per
-// tw x th tile (sfs_tile.cuh).  Per iteration only the z of pixels within two of a tile border crosses CTAs (published to the plan's z
-// vector before the r.z all-reduce, which releases it; read back into the neighbours' rings at the top of the next iteration) plus the
-// two all-reduces (p.Ap; then r.z and q in one round).  LM: zeta = (l+1)(Q1-Q0)/Q1 < q_tolerance ends the loop in every CTA at once
+// tw x th tile (sfs_tile.cuh).  Per iteration only the z of pixels within two of a tile border crosses CTAs (as tagged 8-byte words the
+// neighbours poll at the top of the next iteration: no fence, no barrier) plus the two all-reduces (p.Ap; then r.z and q in one round).  LM: zeta = (l+1)(Q1-Q0)/Q1 < q_tolerance ends the loop in every CTA at once
 // (they all hold the same reduced q); the flag word tells the per-step kernels of a following residual-reset iteration to do nothing.
 // The reduction sequence number lives in device memory (seqWord) so that the launch is replayable from a captured graph.
 // Tail (LM): computeModelCost of the delta found (one more tile-edge exchange of delta, the rows applied to it, F + J delta summed) and
 // the update of the unknowns, so that a nonlinear iteration is head + this kernel + precompute/cost.
+template <class T> struct SfsLoopHead { int on, saveSSq; T minDiag, maxDiag; T* SSq; T* pre; T* CtC; T* b; };   // the LM head inside the loop kernel (on = 0: the vectors come from memory)
 template <class T, int KMAX, int NT>
 __global__ void __launch_bounds__(NT, 1) k_sfsLoopResident(SfsData<T> P, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long* arrivals, unsigned long long* seqWord,
+                                                           unsigned long long* zLL, unsigned long long* dLL,
                                                              int L, int tw, int th, int tilesX, int usePre, int lm, int resetPeriod, int withModelCost, T qTol,
-                                                             T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC, T* xUpdate, T* xSaved) {
+                                                             T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC, T* xUpdate, T* xSaved, SfsLoopHead<T> head) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int tid = threadIdx.x;
     const SfsTileView<T> V = sfsCarveTile<T>(smemRaw, ((int)blockIdx.x % tilesX) * tw, ((int)blockIdx.x / tilesX) * th, tw, th, true);
     SfsLoopRegs<T, KMAX> R;
+    unsigned long long k = ldVolatileU64(seqWord);   // written by the previous launch on this stream; every CTA reads it before the first all-reduce can complete
+    double dRz = 0.0, dRzPrev = 0.0, dPAp = 0.0, dQ = 0.0, unused = 0.0;
+    T Q0 = T(0);
+    int done = 0, broke = -1;
     for (int i = tid; i < V.PW() + V.PH(); i += NT) sfsTileFactors(P, V, i);
     for (int c = tid; c < V.cells(); c += NT) sfsTileStageCell(P, V, c);
-    sfsLoopLoad<T, KMAX>(P, V, R, tid, NT, delta, r, b, CtC, pre, p, usePre, lm);
-    unsigned long long k = ldVolatileU64(seqWord);   // written by the previous launch on this stream; every CTA reads it before the first all-reduce can complete
-    double dRz = ws.scalars[kRz0], dRzPrev = 0.0, dPAp = 0.0, dQ = 0.0, unused = 0.0;
-    T Q0 = lm ? (T)ws.scalars[kQPrev] : T(0);
-    int done = 0, broke = -1;
-    __syncthreads();
+    if (head.on) {
+        // the nonlinear iteration's head on the tile (what k_sfsInitTiled does over the image): residuals of the staged rows, then
+        // -J^T F, diag J^T J and the LM diagonal / preconditioner / first direction per pixel, straight into the loop state
+        for (int c = tid; c < (V.PW()) * (V.PH()); c += NT) { V.sp[c] = T(0); V.sd[c] = T(0); }
+        __syncthreads();
+        for (int c = tid; c < V.cells(); c += NT) sfsTileRowResiduals(P, V, c);
+        __syncthreads();
+        const T a0 = sfsLoopHead<T, KMAX>(P, V, R, tid, NT, usePre, head.saveSSq, (T)ws.scalars[kRadius], head.minDiag, head.maxDiag, head.SSq, zLL, sfsEdgeTag(k, 0));
+        sfsLoopFetchRing<T>(P, V, tid, NT, V.sp, zLL, sfsEdgeTag(k, 0));   // the neighbours' first direction on the ring
+        gridAllReduce2LL<NT, false, false>((double)a0, 0.0, llWords, arrivals, ++k, ws.comm, 0, dRz, unused);   // r . p (its barriers also order the planes)
+    } else {
+        sfsLoopLoad<T, KMAX>(P, V, R, tid, NT, delta, r, b, CtC, pre, p, usePre, lm);
+        dRz = ws.scalars[kRz0];
+        Q0 = lm ? (T)ws.scalars[kQPrev] : T(0);
+        __syncthreads();
+    }
     for (int l = 0; l < L; ++l) {
         if (l > 0) {   // PCGStep3 of iteration l - 1
             T beta = T(0);
             { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
-            sfsLoopUpdateDirection<T, KMAX>(P, V, R, tid, NT, beta, z);
+            sfsLoopUpdateDirection<T, KMAX>(P, V, R, tid, NT, beta, zLL, sfsEdgeTag(k - 1, 1));   // the z published before the last all-reduce
             __syncthreads();
         }
         for (int c = tid; c < V.cells(); c += NT) sfsTileRowsTimesVec(P, V, c, V.sp);
@@ -254,19 +287,17 @@ __global__ void __launch_bounds__(NT, 1) k_sfsLoopResident(SfsData<T> P, ReduceW
         { const T num = (T)dRz, den = (T)dPAp; if (den > T(0)) alpha = num / den; }
         T accRz = T(0), accQ = T(0);
         if (lm && resetPeriod > 0 && ((l + 1) % resetPeriod) == 0) {   // residual reset (:1077-1083): r = b - A delta instead of r -= alpha A p
-            double u0, u1;
-            sfsLoopResetFirstHalf<T, KMAX>(P, V, R, tid, NT, alpha, delta);
-            gridAllReduce2LL<NT, false, true>(0.0, 0.0, llWords, arrivals, ++k, ws.comm, 0, u0, u1);   // grid barrier that releases the tile-edge delta
-            sfsLoopFetchRing<T>(P, V, tid, NT, V.sd, delta);
+            sfsLoopResetFirstHalf<T, KMAX>(P, V, R, tid, NT, alpha, dLL, sfsEdgeTag(k, 2));
+            sfsLoopFetchRing<T>(P, V, tid, NT, V.sd, dLL, sfsEdgeTag(k, 2));   // waits word by word for the neighbours' delta
             __syncthreads();
             for (int c = tid; c < V.cells(); c += NT) sfsTileRowsTimesVec(P, V, c, V.sd);
             __syncthreads();
-            sfsLoopResetSecondHalf<T, KMAX>(P, V, R, tid, NT, usePre, z, accRz, accQ);
+            sfsLoopResetSecondHalf<T, KMAX>(P, V, R, tid, NT, usePre, zLL, sfsEdgeTag(k, 1), accRz, accQ);
         } else {
-            sfsLoopStep2<T, KMAX>(P, V, R, tid, NT, alpha, usePre, z, accRz, accQ);
+            sfsLoopStep2<T, KMAX>(P, V, R, tid, NT, alpha, usePre, zLL, sfsEdgeTag(k, 1), accRz, accQ);
         }
         dRzPrev = dRz;
-        gridAllReduce2LL<NT, false, true>((double)accRz, (double)accQ, llWords, arrivals, ++k, ws.comm, 0, dRz, dQ);   // releases the tile-edge z
+        gridAllReduce2LL<NT, false, false>((double)accRz, (double)accQ, llWords, arrivals, ++k, ws.comm, 0, dRz, dQ);
         done = l + 1;
         if (lm) {
             const T Q1 = (T)dQ;
@@ -276,10 +307,9 @@ __global__ void __launch_bounds__(NT, 1) k_sfsLoopResident(SfsData<T> P, ReduceW
         }
     }
     if (withModelCost) {   // computeModelCost (:666-678) for the delta just found: its rows need delta on a 1-pixel ring
-        double u0, u1, dModel;
-        sfsLoopPublishDelta<T, KMAX>(P, V, R, tid, NT, delta);
-        gridAllReduce2LL<NT, false, true>(0.0, 0.0, llWords, arrivals, ++k, ws.comm, 0, u0, u1);   // grid barrier that releases the tile-edge delta
-        sfsLoopFetchRing<T>(P, V, tid, NT, V.sd, delta);
+        double u1, dModel;
+        sfsLoopPublishDelta<T, KMAX>(P, V, R, tid, NT, dLL, sfsEdgeTag(k, 3));
+        sfsLoopFetchRing<T>(P, V, tid, NT, V.sd, dLL, sfsEdgeTag(k, 3));
         __syncthreads();
         for (int c = tid; c < V.cells(); c += NT) sfsTileRowsTimesVec(P, V, c, V.sd);
         __syncthreads();
@@ -291,10 +321,10 @@ __global__ void __launch_bounds__(NT, 1) k_sfsLoopResident(SfsData<T> P, ReduceW
     { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
     // xUpdate: savePreviousUnknowns + PCGLinearUpdate (:1108-1113, :552-557) for the tile as well -- nobody reads X any more (the model cost's
     // rows did, across tiles, but every CTA is past its all-reduce)
-    sfsLoopStore<T, KMAX>(P, V, R, tid, NT, done > 0, beta, delta, r, z, p, Ap, xUpdate, xSaved);
+    sfsLoopStore<T, KMAX>(P, V, R, tid, NT, done > 0, beta, delta, r, z, p, Ap, xUpdate, xSaved, head.on ? head.pre : nullptr, head.CtC, head.b);
     if (blockIdx.x == 0 && tid == 0 && done > 0) {   // leave the scalars as the kernel-per-step loop does (iteration l reads rz[l&1], writes rz[(l+1)&1])
         ws.scalars[kPAp] = dPAp; ws.scalars[done & 1] = dRz; ws.scalars[(done + 1) & 1] = dRzPrev;
-        if (lm) { ws.scalars[kQ] = dQ; ws.scalars[kQPrev] = (double)Q0; if (broke >= 0) ws.scalars[kFlags] = 1.0 + broke; }
+        if (lm) { ws.scalars[kQ] = dQ; ws.scalars[kQPrev] = (double)Q0; if (broke >= 0) ws.scalars[kFlags] = 1.0 + broke; else if (head.on) ws.scalars[kFlags] = 0.0; }
         *seqWord = k;
     }
 }
@@ -339,18 +369,23 @@ struct SfsOps : EnergyOps<T> {
           gridInit = (int)std::min<long>(std::min<long>(numTiles, (long)sms * o2), kMaxPartials); }
         fusedHead = tiled && !getenv("OPTB_SFS_NO_FUSED_INIT");
         fuseCost = !getenv("OPTB_SFS_NO_FUSED_COST");
+        fusePre = fuseCost && !getenv("OPTB_SFS_NO_FUSED_PRECOMPUTE");
+        { int o3 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, (const void*)k_sfsPrecomputeTiled<T>, kBlock, 0); if (o3 < 1) o3 = 1;
+          gridPre = (int)std::min<long>(std::min<long>(numTiles, (long)sms * o3), kMaxPartials); }
         fuseModel = !getenv("OPTB_SFS_NO_FUSED_MODEL");
         fuseUpdate = !getenv("OPTB_SFS_NO_FUSED_UPDATE");
+        fuseHeadInLoop = !getenv("OPTB_SFS_NO_HEAD_IN_LOOP");
         if (tiled && !getenv("OPTB_SFS_NO_RESIDENT")) setUpResidentLoop(dev, sms);
     }
     int tilesX = 0, numTiles = 0, gridTiled = 1, gridInit = 1; bool tiled = true, fusedHead = true;
     // ---- whole-loop kernel: tile shape, shared memory, reduction words (all fixed for the life of the plan)
     static constexpr int kLoopK = 3;              // pixels per thread
-    int loopTW = 0, loopTH = 0, loopTilesX = 0, loopGrid = 0, loopNT = 1024; size_t loopSmem = 0;
+    int loopTW = 0, loopTH = 0, loopTilesX = 0, loopGrid = 0, loopNT = 768; size_t loopSmem = 0;
     const void* loopFn() const {
         return loopNT == 768 ? (const void*)k_sfsLoopResident<T, kLoopK, 768> : (loopNT == 832 ? (const void*)k_sfsLoopResident<T, kLoopK, 832> : (const void*)k_sfsLoopResident<T, kLoopK, 1024>);
     }
     unsigned long long* loopWords = nullptr;      // [2 parities][kMaxLLCtas + 1][4] reduction words, arrival counter, sequence word
+    unsigned long long* loopEdge = nullptr;       // tile-edge exchange words: z, then delta
     void setUpResidentLoop(int dev, int sms) {
         int coop = 0, maxSmem = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
@@ -358,7 +393,7 @@ struct SfsOps : EnergyOps<T> {
         if (!coop) return;
         // threads per CTA: 1024 leaves the third pixel round of a 64x35 tile 19 % full; 832 and 768 fill their three rounds better with fewer
         // warps to hide latency (A/B on hardware: OPTB_SFS_LOOP_NT)
-        loopNT = 1024;
+        loopNT = 768;   // measured at 640x480: 15.4 us per PCG step against 15.6 (832) and 16.2 (1024)
         if (const char* e = getenv("OPTB_SFS_LOOP_NT")) { const int v = atoi(e); if (v == 768 || v == 832 || v == 1024) loopNT = v; }
         const void* fn = loopFn();
         cudaFuncAttributes fa{};
@@ -404,11 +439,14 @@ struct SfsOps : EnergyOps<T> {
         constexpr size_t words = 2 * 4 * (kMaxLLCtas + 1) + 2;
         OPT_CUDA_CHECK(cudaMalloc((void**)&loopWords, sizeof(unsigned long long) * words));
         OPT_CUDA_CHECK(cudaMemset(loopWords, 0, sizeof(unsigned long long) * words));
+        const size_t edgeWords = (size_t)N * LLWords<T>::N;   // tile-edge words of z and of delta, indexed like the image (tag 0 = never written)
+        OPT_CUDA_CHECK(cudaMalloc((void**)&loopEdge, sizeof(unsigned long long) * 2 * edgeWords));
+        OPT_CUDA_CHECK(cudaMemset(loopEdge, 0, sizeof(unsigned long long) * 2 * edgeWords));
     }
-    ~SfsOps() override { cudaFree(P.B); cudaFree(P.dB); cudaFree(P.cR); cudaFree(P.cC); cudaFree(P.fl); cudaFree(loopWords); }
+    ~SfsOps() override { cudaFree(P.B); cudaFree(P.dB); cudaFree(P.cR); cudaFree(P.cC); cudaFree(P.fl); cudaFree(loopWords); cudaFree(loopEdge); }
     const char* name() const override { return "shape_from_shading"; }
     bool capturable() const override { return true; }
-    unsigned long long captureKey() const override { const int shape[] = { loopTW, loopTH, loopNT, (int)fusedHead, (int)tiled, (int)fuseCost, (int)fuseModel, (int)fuseUpdate }; return EnergyOps<T>::hashBytes(shape, sizeof(shape), EnergyOps<T>::hashValue(P)); }
+    unsigned long long captureKey() const override { const int shape[] = { loopTW, loopTH, loopNT, (int)fusedHead, (int)tiled, (int)fuseCost, (int)fusePre, (int)fuseModel, (int)fuseUpdate, (int)fuseHeadInLoop }; return EnergyOps<T>::hashBytes(shape, sizeof(shape), EnergyOps<T>::hashValue(P)); }
     void bind(void** q) override {   // positions: shape_from_shading.t:5-28 (all scalar Params are float, cast to opt_float on use, o.t:1699)
         auto f = [&](int k) { return (T) * (const float*)q[k]; };
         costFresh = false;
@@ -421,8 +459,9 @@ struct SfsOps : EnergyOps<T> {
     }
     // precompute also leaves the cost of the X it linearised at in scalars[kCost]; the cost() that follows it (every call site in
     // solver.cu pairs them) is then free
-    bool fuseCost = true, costFresh = false;
+    bool fuseCost = true, fusePre = true, costFresh = false; int gridPre = 1;
     void precompute(const LaunchCtx& c) override {
+        if (fusePre) { k_sfsPrecomputeTiled<T><<<gridPre, kBlock, 0, c.stream>>>(P, c.ws, kCost, tilesX, numTiles); costFresh = true; return; }
         k_sfsPrecomputeB<T><<<grid, kBlock, 0, c.stream>>>(P);
         if (fuseCost) { k_sfsBuildRowsCost<T><<<grid, kBlock, 0, c.stream>>>(P, c.ws, kCost); costFresh = true; }
         else k_sfsBuildRows<T><<<grid, kBlock, 0, c.stream>>>(P);
@@ -442,19 +481,26 @@ struct SfsOps : EnergyOps<T> {
         return true;
     }
     bool fuseModel = true, fuseUpdate = true;
+    bool fuseHeadInLoop = true;
+    bool pcgLoopTakesHead(int L, bool lm) override { return loopTW && L >= 2 && lm && fuseHeadInLoop && fusedHead; }
     int pcgLoopOnChip(const LaunchCtx& c, int L, bool lm, int resetPeriod, T qTol, T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC,
-                      bool* modelCostDone, T* prevX, bool* updateDone) override {
-        if (!loopTW || L < 2) return 0;
+                      bool* modelCostDone, T* prevX, bool* updateDone, const typename EnergyOps<T>::LoopHeadArgs* headArgs) override {
+        if (!loopTW || L < 2) { if (headArgs) EnergyOps<T>::unsupported("pcgLoopOnChip with the head after pcgLoopTakesHead said yes"); return 0; }
+        SfsLoopHead<T> head{};
+        if (headArgs) { head.on = 1; head.saveSSq = headArgs->saveSSq ? 1 : 0; head.minDiag = headArgs->minDiag; head.maxDiag = headArgs->maxDiag; head.SSq = headArgs->SSq;
+                        head.pre = const_cast<T*>(pre); head.CtC = const_cast<T*>(CtC); head.b = const_cast<T*>(b); }
         int withModel = (lm && fuseModel && modelCostDone) ? 1 : 0;
         if (modelCostDone) *modelCostDone = withModel != 0;
-        T* xUpdate = (updateDone && fuseUpdate && (!lm || prevX)) ? const_cast<T*>(P.X) : nullptr;   // the one unknown array of this energy, offset 0 in the plan's vectors
+        // the one unknown array of this energy, offset 0 in the plan's vectors.  LM: only together with the model cost, which must see the old X
+        T* xUpdate = (updateDone && fuseUpdate && (!lm || (prevX && withModel))) ? const_cast<T*>(P.X) : nullptr;
         T* xSaved = lm ? prevX : nullptr;
         if (updateDone) *updateDone = xUpdate != nullptr;
         ReduceWorkspace ws = c.ws;
         unsigned long long* arrivals = loopWords + 2 * 4 * (kMaxLLCtas + 1); unsigned long long* seqWord = arrivals + 1;
         int usePre = this->usePreconditioner ? 1 : 0, lmi = lm ? 1 : 0;
-        void* args[] = { (void*)&P, (void*)&ws, (void*)&loopWords, (void*)&arrivals, (void*)&seqWord, (void*)&L, (void*)&loopTW, (void*)&loopTH, (void*)&loopTilesX, (void*)&usePre, (void*)&lmi,
-                         (void*)&resetPeriod, (void*)&withModel, (void*)&qTol, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre, (void*)&b, (void*)&CtC, (void*)&xUpdate, (void*)&xSaved };
+        unsigned long long* zLL = loopEdge; unsigned long long* dLL = loopEdge + (size_t)N * LLWords<T>::N;
+        void* args[] = { (void*)&P, (void*)&ws, (void*)&loopWords, (void*)&arrivals, (void*)&seqWord, (void*)&zLL, (void*)&dLL, (void*)&L, (void*)&loopTW, (void*)&loopTH, (void*)&loopTilesX, (void*)&usePre, (void*)&lmi,
+                         (void*)&resetPeriod, (void*)&withModel, (void*)&qTol, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre, (void*)&b, (void*)&CtC, (void*)&xUpdate, (void*)&xSaved, (void*)&head };
         OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(loopFn(), dim3((unsigned)loopGrid), dim3((unsigned)loopNT), args, loopSmem, c.stream));
         return L;
     }

@@ -101,11 +101,9 @@ template <class T> SFS_HD SfsDual<T> sfsB(const SfsData<T>& P, int x, int y) {
     return SfsDual<T>{ sh.v - I, sh.d0, sh.d1, sh.d2 };
 }
 
-// precompute, pass 1: B, dB and the flag byte of pixel (x, y)
-template <class T> SFS_HD void sfsPrecomputeB(const SfsData<T>& P, int x, int y) {
-    const long c = (long)y * P.W + x, N = sfsN(P);
-    const SfsDual<T> b = sfsB(P, x, y);
-    P.B[c] = b.v; P.dB[c] = b.d0; P.dB[N + c] = b.d1; P.dB[2 * N + c] = b.d2;
+// flag byte of the in-image pixel (x, y)
+template <class T> SFS_HD unsigned sfsFlagsAt(const SfsData<T>& P, int x, int y) {
+    const long c = (long)y * P.W + x;
     unsigned f = 0;
     if (sfsHasDepth(P, x, y)) f |= kSfsIncluded;
     if (sfsInside1(P, x, y)) {
@@ -115,7 +113,14 @@ template <class T> SFS_HD void sfsPrecomputeB(const SfsData<T>& P, int x, int y)
             && sfsAbs(v - P.X[c - P.W]) < thre && sfsAbs(v - P.X[c + P.W]) < thre && sfsAbs(v - P.X[c - 1]) < thre && sfsAbs(v - P.X[c + 1]) < thre;
         if (flat) f |= kSfsFlat;
     }
-    P.fl[c] = (unsigned char)f;
+    return f;
+}
+// precompute, pass 1: B, dB and the flag byte of pixel (x, y)
+template <class T> SFS_HD void sfsPrecomputeB(const SfsData<T>& P, int x, int y) {
+    const long c = (long)y * P.W + x, N = sfsN(P);
+    const SfsDual<T> b = sfsB(P, x, y);
+    P.B[c] = b.v; P.dB[c] = b.d0; P.dB[N + c] = b.d1; P.dB[2 * N + c] = b.d2;
+    P.fl[c] = (unsigned char)sfsFlagsAt(P, x, y);
 }
 // precompute, pass 2 (needs pass 1 of the right and lower neighbours): coefficients of the r_gR / r_gC rows centred at (x, y)
 template <class T> SFS_HD void sfsBuildRows(const SfsData<T>& P, int x, int y) {
@@ -149,9 +154,14 @@ template <class T> SFS_HD T sfsCoefS(const SfsData<T>& P, int x, int y, int comp
     const T a = comp == 0 ? sfsAx(P, qx) : (comp == 1 ? sfsAy(P, qy) : T(1));
     return sfsCoefFromA(P, a, k);
 }
+template <class T> SFS_HD T sfsFSWithFlag(const SfsData<T>& P, int x, int y, int comp);
 template <class T> SFS_HD T sfsFS(const SfsData<T>& P, int x, int y, int comp) {   // value of r_s,comp centred at (x, y)
     const long c = (long)y * P.W + x;
     if (!(P.fl[c] & kSfsFlat)) return T(0);
+    return sfsFSWithFlag(P, x, y, comp);
+}
+template <class T> SFS_HD T sfsFSWithFlag(const SfsData<T>& P, int x, int y, int comp) {   // the same for a centre the caller knows to be flat
+    const long c = (long)y * P.W + x;
     // the five coefficients need the factor of three columns (comp 0) or three rows (comp 1): 3 divisions instead of one per coefficient
     const T a3[3] = { comp == 0 ? sfsAx(P, x - 1) : (comp == 1 ? sfsAy(P, y - 1) : T(1)), comp == 0 ? sfsAx(P, x) : (comp == 1 ? sfsAy(P, y) : T(1)),
                       comp == 0 ? sfsAx(P, x + 1) : (comp == 1 ? sfsAy(P, y + 1) : T(1)) };

@@ -691,8 +691,10 @@ struct Plan : PlanBase {
         if (world == 1 && useOnChipLoop && !timingFine) {
             bool mc = false, up = false;
             const bool whole = maxLinIters < 0;   // (the debug hook leaves the PCG state for inspection: no model cost, no update)
+            typename EnergyOps<T>::LoopHeadArgs ha{ SSq, min_lm_diagonal, max_lm_diagonal, headSaveSSq };
             l0 = E->pcgLoopOnChip(c, L, lm, lm ? sp.residual_reset_period : 0, (T)sp.q_tolerance, delta, r, z, cur, Ap, pre, b, ctc, (lm && whole) ? &mc : nullptr,
-                                  lm ? prevX : nullptr, whole ? &up : nullptr);
+                                  lm ? prevX : nullptr, whole ? &up : nullptr, headInLoop ? &ha : nullptr);
+            if (headInLoop && l0 != L) { fprintf(stderr, "opt_b200: the loop kernel was to run the iteration's head but covered %d of %d iterations\n", l0, L); exit(2); }
             if (l0 > 0) ++launches;
             if (l0 > 0 && l0 != L && (mc || up)) { fprintf(stderr, "opt_b200: pcgLoopOnChip covered %d of %d iterations but ran its tail\n", l0, L); exit(2); }
             loopDidModelCost = l0 == L && mc; loopDidUpdate = l0 == L && up;
@@ -733,6 +735,7 @@ struct Plan : PlanBase {
         }
         pFinal = cur;
     }
+    bool loopTakesHead(int L) { return lm && world == 1 && useOnChipLoop && !timingFine && L > 0 && E->pcgLoopTakesHead(L, lm); }
     bool loopFuses() {
         bool fuse = useFusion && !lm;
         if (fuse) fuse = E->step3ApplyJTJ(ctx(), nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, -2);   // capability probe, no launch
@@ -759,8 +762,9 @@ struct Plan : PlanBase {
             // reallocated in bind()/pcgInit(), q_tolerance, the reset period): re-capture whenever any of that differs from what the
             // cached graph was built from.  Same topology => cudaGraphExecUpdate patches the node parameters in place (microseconds).
             unsigned long long key = E->captureKey();
-            { const long v[] = { (long)L, (long)fuse, (long)sp.residual_reset_period, (long)world, (long)rank }; key = EnergyOps<T>::hashBytes(v, sizeof(v), key); }
-            key = EnergyOps<T>::hashValue(sp.q_tolerance, key);
+            { const long v[] = { (long)L, (long)fuse, (long)sp.residual_reset_period, (long)world, (long)rank, (long)headInLoop, (long)headSaveSSq, (long)(maxLinIters >= 0) };
+              key = EnergyOps<T>::hashBytes(v, sizeof(v), key); }
+            key = EnergyOps<T>::hashValue(sp.q_tolerance, key); key = EnergyOps<T>::hashValue(min_lm_diagonal, key); key = EnergyOps<T>::hashValue(max_lm_diagonal, key);
             key = EnergyOps<T>::hashValue(winVec, key); key = EnergyOps<T>::hashValue(ownVec, key);
             if (!loopExec || loopExecKey != key) {
                 cudaGraph_t g;
@@ -840,7 +844,7 @@ struct Plan : PlanBase {
     // the fingerprint of its by-value arguments changes (as for the loop graph).  The reference issues ~15 + 3 L launches and one blocking
     // copy per PCG step here; for shape_from_shading (L = 10) the launches outside the loop were 45 % of an iteration.
     cudaGraphExec_t iterExec = nullptr; unsigned long long iterKey = 0; int iterLaunchCount = 0; T* iterPFinal = nullptr;
-    bool useIterGraph = true, lastLoopPersistent = false, useOnChipLoop = true, loopDidModelCost = false, loopDidUpdate = false;
+    bool useIterGraph = true, lastLoopPersistent = false, useOnChipLoop = true, loopDidModelCost = false, loopDidUpdate = false, headInLoop = false, headSaveSSq = false;
     double* hRadius = nullptr;
     void uploadRadius() {
         if (!hRadius) OPT_CUDA_CHECK(cudaMallocHost((void**)&hRadius, sizeof(double)));
@@ -850,8 +854,10 @@ struct Plan : PlanBase {
     void enqueueIterationForCapture(int L) {   // the launch sequence of step() without its timing hooks; nIter >= 1 (no PCGSaveSSq)
         LaunchCtx c = ctx();
         if (lm) OPT_CUDA_CHECK(cudaMemcpyAsync(ws.scalars + kRadius, hRadius, sizeof(double), cudaMemcpyHostToDevice, stream));
-        const bool fusedHead = lm && world == 1 && E->pcgInitLM(c, delta, r, pre, p, CtC, SSq, b, kRz0, min_lm_diagonal, max_lm_diagonal, false);
-        if (fusedHead) ++launches;
+        headInLoop = loopTakesHead(L); headSaveSSq = false;
+        const bool fusedHead = headInLoop || (lm && world == 1 && E->pcgInitLM(c, delta, r, pre, p, CtC, SSq, b, kRz0, min_lm_diagonal, max_lm_diagonal, false));
+        if (headInLoop) {}
+        else if (fusedHead) ++launches;
         else { E->pcgInit(c, delta, r, pre, p, kRz0); ++launches; }
         if (lm && !fusedHead) {
             E->computeCtC(c, CtC, T(1)); ++launches;
@@ -940,9 +946,11 @@ struct Plan : PlanBase {
         if (lm) uploadRadius();
         tBegin("PCGInit1");
         // one launch for PCGInit1 and the LM head (:1038-1053) where the energy offers it
-        const bool fusedHead = lm && world == 1 && E->pcgInitLM(c, delta, r, pre, p, CtC, SSq, b, kRz0, min_lm_diagonal, max_lm_diagonal, nIter == 0);
+        int Lh = sp.lIterations; if (maxLinIters >= 0 && maxLinIters < Lh) Lh = maxLinIters;
+        headInLoop = loopTakesHead(Lh); headSaveSSq = nIter == 0;        // the one-launch loop may run the head on its tiles itself
+        const bool fusedHead = headInLoop || (lm && world == 1 && E->pcgInitLM(c, delta, r, pre, p, CtC, SSq, b, kRz0, min_lm_diagonal, max_lm_diagonal, nIter == 0));
         if (!fusedHead) E->pcgInit(c, delta, r, pre, p, kRz0);          // PCGInit1 (+_Graph,+_Finish)
-        ++launches;
+        if (!headInLoop) ++launches;
         tEnd();
         if (lm && !fusedHead) {   // :1038-1053
             if (nIter == 0) { k_copy<T><<<gridStream, kBlock, 0, stream>>>(n, SSq, pre); ++launches; }   // PCGSaveSSq

@@ -106,8 +106,13 @@ struct EnergyOps {
     // modelCostDone != nullptr (LM, the call covers the whole loop): the kernel may also leave computeModelCost (:666-678) of the delta
     // it found in scalars[kModelCost] and says so there; the caller then skips modelCost().  updateDone != nullptr: likewise for
     // savePreviousUnknowns (LM, into prevX, laid out like the plan's vectors) + PCGLinearUpdate of every unknown array.
+    // headArgs != nullptr (only after pcgLoopTakesHead(L, lm) answered true; the caller then launched neither pcgInit nor pcgInitLM): the
+    // kernel also runs the LM head of pcgInitLM on its tiles first and leaves pre / CtC / b / SSq in memory as that call would.
+    struct LoopHeadArgs { T* SSq; T minDiag, maxDiag; bool saveSSq; };
+    virtual bool pcgLoopTakesHead(int /*L*/, bool /*lm*/) { return false; }
     virtual int pcgLoopOnChip(const LaunchCtx&, int /*L*/, bool /*lm*/, int /*resetPeriod*/, T /*qTolerance*/, T* /*delta*/, T* /*r*/, T* /*z*/, T* /*p*/, T* /*Ap*/,
-                              const T* /*pre*/, const T* /*b*/, const T* /*CtC*/, bool* /*modelCostDone*/, T* /*prevX*/, bool* /*updateDone*/) { return 0; }
+                              const T* /*pre*/, const T* /*b*/, const T* /*CtC*/, bool* /*modelCostDone*/, T* /*prevX*/, bool* /*updateDone*/,
+                              const LoopHeadArgs* /*headArgs*/) { return 0; }
     // computeCost (+_Graph): scalars[kCost] = 1/2 sum r^2
     virtual void cost(const LaunchCtx& c) = 0;
     // LM: CtC <- diag(J^T J)/radius (PCGComputeCtC), scalars[kModelCost] = 1/2 sum (r + J delta)^2

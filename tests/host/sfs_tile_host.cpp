@@ -2,7 +2,7 @@
 // k_sfsInitTiled and k_sfsLoopResident (energy_sfs.cu) call, driven "CTA by CTA, thread by thread" on the CPU with the barriers
 // and all-reduces of the kernels replaced by loop boundaries.  tests/test_sfs_host_parity.py compares the outputs with the CPU oracle
 // (LM, k PCG steps) and with the per-pixel functions of sfs_device.cuh.
-//   run: sfs_tile_host <dataDir> <out.bin> W H tw th NT k lm
+//   run: sfs_tile_host <dataDir> <out.bin> W H tw th NT k lm headInLoop
 // out.bin (doubles, N each): r0, CtC, pre, p0 (after the fused PCGInit1 + CtC + FinalizeDiagonal), then delta, r, p, z after k PCG steps.
 #include <cmath>
 #include <cstdio>
@@ -28,14 +28,14 @@ static std::vector<char> readFile(const std::string& path) {
 }
 
 int main(int argc, char** argv) {
-    if (argc != 10) { fprintf(stderr, "usage: sfs_tile_host dataDir out.bin W H tw th NT k lm\n"); return 2; }
+    if (argc != 11) { fprintf(stderr, "usage: sfs_tile_host dataDir out.bin W H tw th NT k lm headInLoop\n"); return 2; }
     const std::string dir = argv[1];
     std::vector<std::vector<char>> blobs(21);
     for (int k = 0; k <= 20; ++k) blobs[k] = readFile(dir + "/p" + std::to_string(k) + ".bin");
     auto fl = [&](int k) { return (T) * (const float*)blobs[k].data(); };
     SfsData<T> P{};
     P.W = atoi(argv[3]); P.H = atoi(argv[4]);
-    const int tw = atoi(argv[5]), th = atoi(argv[6]), NT = atoi(argv[7]), K = atoi(argv[8]), lm = atoi(argv[9]);
+    const int tw = atoi(argv[5]), th = atoi(argv[6]), NT = atoi(argv[7]), K = atoi(argv[8]), lm = atoi(argv[9]), headInLoop = atoi(argv[10]);
     const long N = (long)P.W * P.H;
     P.wp = std::sqrt(fl(0)); P.ws = std::sqrt(fl(1)); P.wg = std::sqrt(fl(2));      // same binding as energy_sfs.cu
     if (sizeof(T) == 4) { P.wp = sqrtf(*(const float*)blobs[0].data()); P.ws = sqrtf(*(const float*)blobs[1].data()); P.wg = sqrtf(*(const float*)blobs[2].data()); }
@@ -47,6 +47,30 @@ int main(int argc, char** argv) {
     P.B = B.data(); P.dB = dB.data(); P.cR = cR.data(); P.cC = cC.data(); P.fl = flags.data();
     for (int y = 0; y < P.H; ++y) for (int x = 0; x < P.W; ++x) sfsPrecomputeB(P, x, y);
     for (int y = 0; y < P.H; ++y) for (int x = 0; x < P.W; ++x) sfsBuildRows(P, x, y);
+
+    // ------------------------------------------------------------------ precompute + cost in one tiled pass against the two per-pixel passes above
+    double preErr = 0.0, costTiled = 0.0, costRef = 0.0;
+    {
+        std::vector<T> B2(N, T(-5)), cR2(5 * N, T(-5)), cC2(5 * N, T(-5)); std::vector<unsigned char> fl2(N, 255);
+        SfsData<T> Q = P; Q.B = B2.data(); Q.cR = cR2.data(); Q.cC = cC2.data(); Q.fl = fl2.data(); Q.dB = nullptr;
+        const int itw = 32, ith = 8, block = 256;
+        const int tX = (P.W + itw - 1) / itw, tY = (P.H + ith - 1) / ith;
+        std::vector<unsigned char> planes(sfsPrePlaneBytes<T>(itw, ith) + 64);
+        for (int tile = 0; tile < tX * tY; ++tile) {
+            SfsPreView<T> V = sfsCarvePre<T>(planes.data(), (tile % tX) * itw, (tile / tX) * ith, itw, ith);
+            for (int tid = 0; tid < block; ++tid) for (int c = tid; c < V.bcells(); c += block) sfsPreCell(Q, V, c);
+            for (int tid = 0; tid < block; ++tid) {
+                const int tx = tid % itw, ty = tid / itw;
+                if (V.x0 + tx < P.W && V.y0 + ty < P.H) costTiled += (double)sfsPrePixel(Q, V, ty, tx);
+            }
+        }
+        for (long i = 0; i < N; ++i) {
+            preErr = std::fmax(preErr, std::fabs((double)B2[i] - (double)B[i]));
+            if (fl2[i] != flags[i]) preErr = 1e30;
+            for (int k = 0; k < 5; ++k) { preErr = std::fmax(preErr, std::fabs((double)cR2[k * N + i] - (double)cR[k * N + i])); preErr = std::fmax(preErr, std::fabs((double)cC2[k * N + i] - (double)cC[k * N + i])); }
+        }
+        for (int y = 0; y < P.H; ++y) for (int x = 0; x < P.W; ++x) costRef += (double)sfsCostAt<T, false>(P, x, y, nullptr);
+    }
 
     // ------------------------------------------------------------------ fused PCGInit1 (+ CtC + FinalizeDiagonal), 32 x 8 tiles of 256 "threads"
     std::vector<T> delta(N, T(7)), r(N, T(7)), pre(N, T(7)), p(N, T(7)), CtC(N, T(7)), SSq(N, T(7)), b(N, T(7)), z(N, T(0)), Ap(N, T(0));
@@ -91,15 +115,28 @@ int main(int argc, char** argv) {
     std::vector<std::vector<unsigned char>> planes(nCta, std::vector<unsigned char>(sfsTilePlaneBytes<T>(tw, th, true) + 64));
     std::vector<SfsTileView<T>> V(nCta);
     std::vector<std::vector<SfsLoopRegs<T, KMAX>>> R(nCta, std::vector<SfsLoopRegs<T, KMAX>>(NT));
+    std::vector<unsigned long long> zLL(2 * N, 0ull), dLL(2 * N, 0ull);   // tile-edge words (value, tag)
+    unsigned long long kRed = 1000;                                      // all-reduces completed so far (the kernel continues the plan's sequence)
+    bool tailPhase = false;
+    std::vector<T> SSqLoop(N, T(7));
+    double rzHead = 0.0;
     for (int cta = 0; cta < nCta; ++cta) {
         V[cta] = sfsCarveTile<T>(planes[cta].data(), (cta % tilesX) * tw, (cta / tilesX) * th, tw, th, true);
         for (int tid = 0; tid < NT; ++tid) {
             for (int i = tid; i < V[cta].PW() + V[cta].PH(); i += NT) sfsTileFactors(P, V[cta], i);
             for (int c = tid; c < V[cta].cells(); c += NT) sfsTileStageCell(P, V[cta], c);
-            sfsLoopLoad<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, delta.data(), r.data(), b.data(), CtC.data(), pre.data(), p.data(), 0, lm);
+            if (!headInLoop) sfsLoopLoad<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, delta.data(), r.data(), b.data(), CtC.data(), pre.data(), p.data(), 0, lm);
+            else for (int c = tid; c < V[cta].PW() * V[cta].PH(); c += NT) { V[cta].sp[c] = T(0); V[cta].sd[c] = T(0); }
         }
     }
-    double dRz = rz0, dRzPrev = 0.0, dPAp = 0.0, dQ = 0.0;
+    if (headInLoop) {   // the LM head inside the loop kernel: residual rows, head per pixel (direction published on the tile edges), ring, r . p
+        for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) for (int c = tid; c < V[cta].cells(); c += NT) sfsTileRowResiduals(P, V[cta], c);
+        for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid)
+            rzHead += (double)sfsLoopHead<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, 0, 1, radius, minDiag, maxDiag, SSqLoop.data(), zLL.data(), sfsEdgeTag(kRed, 0));
+        for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopFetchRing<T>(P, V[cta], tid, NT, V[cta].sp, zLL.data(), sfsEdgeTag(kRed, 0));
+        ++kRed;
+    }
+    double dRz = headInLoop ? rzHead : rz0, dRzPrev = 0.0, dPAp = 0.0, dQ = 0.0;
     T Q0 = T(0);
     int done = 0, broke = -1;
     const int resetPeriod = 10;   // residual_reset_period, solver default
@@ -107,32 +144,32 @@ int main(int argc, char** argv) {
         if (l > 0) {
             T beta = T(0);
             { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
-            for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopUpdateDirection<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, beta, z.data());
+            for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopUpdateDirection<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, beta, zLL.data(), sfsEdgeTag(kRed - 1, 1));
         }
         for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) for (int c = tid; c < V[cta].cells(); c += NT) sfsTileRowsTimesVec(P, V[cta], c, V[cta].sp);
         double s = 0.0;
         for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) s += (double)sfsLoopApply<T, KMAX>(P, V[cta], R[cta][tid], tid, NT);
-        dPAp = s;
+        dPAp = s; ++kRed;
         T alpha = T(0);
         { const T num = (T)dRz, den = (T)dPAp; if (den > T(0)) alpha = num / den; }
         double s0 = 0.0, s1 = 0.0;
         // (the kernel's z stores of step l land before any ring read of step l + 1: separated here by the loop structure)
         if (lm && ((l + 1) % resetPeriod) == 0) {
-            for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopResetFirstHalf<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, alpha, delta.data());
-            for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopFetchRing<T>(P, V[cta], tid, NT, V[cta].sd, delta.data());
+            for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopResetFirstHalf<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, alpha, dLL.data(), sfsEdgeTag(kRed, 2));
+            for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopFetchRing<T>(P, V[cta], tid, NT, V[cta].sd, dLL.data(), sfsEdgeTag(kRed, tailPhase ? 3 : 2));
             for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) for (int c = tid; c < V[cta].cells(); c += NT) sfsTileRowsTimesVec(P, V[cta], c, V[cta].sd);
             for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) {
                 T a0 = T(0), a1 = T(0);
-                sfsLoopResetSecondHalf<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, 0, z.data(), a0, a1);
+                sfsLoopResetSecondHalf<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, 0, zLL.data(), sfsEdgeTag(kRed, 1), a0, a1);
                 s0 += (double)a0; s1 += (double)a1;
             }
         } else
         for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) {
             T a0 = T(0), a1 = T(0);
-            sfsLoopStep2<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, alpha, 0, z.data(), a0, a1);
+            sfsLoopStep2<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, alpha, 0, zLL.data(), sfsEdgeTag(kRed, 1), a0, a1);
             s0 += (double)a0; s1 += (double)a1;
         }
-        dRzPrev = dRz; dRz = s0; dQ = s1;
+        dRzPrev = dRz; dRz = s0; dQ = s1; ++kRed;
         done = l + 1;
         if (lm) {
             const T Q1 = (T)dQ;
@@ -142,9 +179,10 @@ int main(int argc, char** argv) {
         }
     }
     double model = 0.0;
+    tailPhase = true;
     if (lm) {   // computeModelCost inside the loop kernel
-        for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopPublishDelta<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, delta.data());
-        for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopFetchRing<T>(P, V[cta], tid, NT, V[cta].sd, delta.data());
+        for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopPublishDelta<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, dLL.data(), sfsEdgeTag(kRed, 3));
+        for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopFetchRing<T>(P, V[cta], tid, NT, V[cta].sd, dLL.data(), sfsEdgeTag(kRed, tailPhase ? 3 : 2));
         for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) for (int c = tid; c < V[cta].cells(); c += NT) sfsTileRowsTimesVec(P, V[cta], c, V[cta].sd);
         for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) model += (double)sfsLoopModelCost<T, KMAX>(P, V[cta], R[cta][tid], tid, NT);
     }
@@ -152,13 +190,23 @@ int main(int argc, char** argv) {
     { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
     // poison the vectors first: the epilogue must rewrite every in-image entry
     std::vector<T> z2(N, T(-777)), delta2(N, T(-777)), r2(N, T(-777)), p2(N, T(-777)), Ap2(N, T(-777));
+    std::vector<T> pre2(N, T(-777)), ctc2(N, T(-777)), b2(N, T(-777));
     for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid)
-        sfsLoopStore<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, done > 0, beta, delta2.data(), r2.data(), z2.data(), p2.data(), Ap2.data());
+        sfsLoopStore<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, done > 0, beta, delta2.data(), r2.data(), z2.data(), p2.data(), Ap2.data(), (T*)nullptr, (T*)nullptr,
+                              headInLoop ? pre2.data() : nullptr, ctc2.data(), b2.data());
+    double headErr = 0.0;   // head inside the loop against the stand-alone fused head (same functions, same order: identical)
+    if (headInLoop) {
+        for (long i = 0; i < N; ++i) {
+            headErr = std::fmax(headErr, std::fabs((double)pre2[i] - (double)pre[i])); headErr = std::fmax(headErr, std::fabs((double)ctc2[i] - (double)CtC[i]));
+            headErr = std::fmax(headErr, std::fabs((double)b2[i] - (double)b[i])); headErr = std::fmax(headErr, std::fabs((double)SSqLoop[i] - (double)SSq[i]));
+        }
+        headErr = std::fmax(headErr, std::fabs(rzHead - rz0));
+    }
     dump(delta2); dump(r2); dump(p2); dump(z2);
     fclose(out);
     double modelRef = 0.0;   // the per-pixel form (sfs_device.cuh), itself checked against the oracle by test_sfs_per_pixel_math_matches_oracle
     for (int y = 0; y < P.H; ++y) for (int x = 0; x < P.W; ++x) modelRef += (double)sfsCostAt<T, true>(P, x, y, delta2.data());
-    printf("RZ0 %.17g RZ %.17g PAP %.17g Q %.17g DONE %d BROKE %d JTFERR %.3g DIAGERR %.3g CTAS %d MODEL %.17g MODELREF %.17g\n", rz0, dRz, dPAp, dQ, done, broke, maxJtf, maxDiagErr, nCta,
-           model, modelRef);
+    printf("RZ0 %.17g RZ %.17g PAP %.17g Q %.17g DONE %d BROKE %d JTFERR %.3g DIAGERR %.3g CTAS %d MODEL %.17g MODELREF %.17g PREERR %.3g COST %.17g COSTREF %.17g HEADERR %.3g\n", rz0, dRz, dPAp, dQ, done, broke, maxJtf, maxDiagErr, nCta,
+           model, modelRef, preErr, costTiled, costRef, headErr);
     return 0;
 }

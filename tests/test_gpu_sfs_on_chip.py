@@ -67,7 +67,8 @@ def test_loop_on_chip_matches_per_step_path_and_oracle(built, W, H, kind):
         for name in ("delta", "r", "p"):
             b = o.get_vector(name)
             scale = max(1e-30, float(np.abs(b).max()))
-            floor = 2e-5 * r0max if name == "r" else 0.0     # r = b - A delta after a reset: a few ulp of |J^T F|, measured 1.1e-5 at 64x48, k = 25
+            # r = b - A delta after a reset: a few ulp of |J^T F| (measured 1.1e-5 at 64x48, k = 25); p = z + beta p carries the same absolute noise
+            floor = 2e-5 * r0max if name in ("r", "p") else 0.0
             assert np.abs(got[name][:b.size] - b).max() <= max(5e-4 * scale, floor), (name, k, "oracle")
             assert np.abs(got[name] - ref[name]).max() <= max(5e-4 * scale, floor), (name, k, "per-step path")
         if lm:
@@ -110,6 +111,9 @@ def test_full_solve_matches_oracle_and_per_step_path(built, W, H):
 
     c1, x1 = solve({})
     c0, x0 = solve(PER_STEP)
+    for env in ({"OPTB_SFS_NO_HEAD_IN_LOOP": "1"}, {"OPTB_SFS_NO_FUSED_PRECOMPUTE": "1"}, {"OPTB_SFS_LOOP_NT": "1024"}):
+        c2, x2 = solve(env)
+        assert abs(c2 - c0) <= 5e-4 * abs(c0), (env, c2, c0)
     o = Oracle("shape_from_shading", "LMGPU", [W, H])
     for k, v in sp.items():
         o.set_solver_parameter(k, v)
@@ -140,7 +144,7 @@ def test_model_cost_from_loop_kernel(built, W, H):
     """computeModelCost folded into the loop kernel's tail against the stand-alone kernel, after one and after three LM iterations"""
     host = workloads.shape_from_shading(W, H)
     vals = {}
-    for tag, env in (("fused", {}), ("separate", {"OPTB_SFS_NO_FUSED_MODEL": "1"}), ("per_step", PER_STEP)):
+    for tag, env in (("fused", {}), ("head_separate", {"OPTB_SFS_NO_HEAD_IN_LOOP": "1"}), ("separate", {"OPTB_SFS_NO_FUSED_MODEL": "1"}), ("per_step", PER_STEP)):
         dev = workloads.to_device(workloads.clone_params(host))
         s = _plan(W, H, "LMGPU", env)
         s.set_solver_parameters({"nIterations": 5, "lIterations": 10})
@@ -151,6 +155,6 @@ def test_model_cost_from_loop_kernel(built, W, H):
             out.append((s.read_scalar("modelCost"), s.current_cost(), s.read_scalar("trust_region_radius")))
         vals[tag] = out
         s.close()
-    for tag in ("separate", "per_step"):
+    for tag in ("head_separate", "separate", "per_step"):
         for (m1, c1, t1), (m0, c0, t0) in zip(vals["fused"], vals[tag]):
-            assert abs(m1 - m0) <= 2e-5 * abs(m0) and abs(c1 - c0) <= 2e-4 * abs(c0) and t1 == t0, (tag, vals)
+            assert abs(m1 - m0) <= 1e-4 * abs(m0) and abs(c1 - c0) <= 2e-4 * abs(c0) and abs(t1 - t0) <= 1e-3 * t0, (tag, vals["fused"], vals[tag])

@@ -65,11 +65,12 @@ def _dump_params(host, data):
             np.array([v], np.float32).tofile(str(data / f"p{k}.bin"))
 
 
+@pytest.mark.parametrize("head_in_loop", [0, 1])
 @pytest.mark.parametrize("dp", [True, False])
 @pytest.mark.parametrize("W,H,tw,th,NT,k", [(40, 31, 32, 8, 96, 5), (45, 37, 16, 12, 64, 7), (26, 22, 32, 24, 256, 3), (70, 19, 8, 4, 11, 9),
                                             (5, 4, 32, 8, 128, 4), (64, 48, 64, 16, 352, 9), (33, 9, 32, 4, 64, 1), (40, 31, 32, 8, 96, 0),
                                             (40, 31, 32, 8, 96, 10), (45, 37, 16, 12, 64, 13), (64, 48, 32, 35, 400, 20), (26, 22, 32, 4, 43, 21), (64, 48, 32, 35, 400, 40)])
-def test_sfs_tile_algorithms_match_oracle(tmp_path, W, H, tw, th, NT, k, dp):
+def test_sfs_tile_algorithms_match_oracle(tmp_path, W, H, tw, th, NT, k, dp, head_in_loop):
     """sfs_tile.cuh: the fused PCGInit1 + CtC + FinalizeDiagonal pass and the tile-resident PCG loop (the bodies of k_sfsInitTiled and
     k_sfsLoopResident), emulated CTA by CTA on the CPU, against the oracle's LM state after k PCG steps"""
     from oracle.oracle import Oracle
@@ -80,13 +81,16 @@ def test_sfs_tile_algorithms_match_oracle(tmp_path, W, H, tw, th, NT, k, dp):
     data = tmp_path / "params"; data.mkdir()
     _dump_params(host, data)
     res = tmp_path / "out.bin"
-    r = subprocess.run([str(exe), str(data), str(res), str(W), str(H), str(tw), str(th), str(NT), str(k), "1"], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([str(exe), str(data), str(res), str(W), str(H), str(tw), str(th), str(NT), str(k), "1", str(head_in_loop)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith("RZ0 "), r.stdout + r.stderr
     tok = r.stdout.split()
     val = {tok[i]: float(tok[i + 1]) for i in range(0, len(tok), 2)}
     # the tile gathers against the per-pixel gathers of sfs_device.cuh: same products, same order
     ref_scale = 1.0
     assert val["JTFERR"] <= (1e-12 if dp else 1e-5) * 1e3 and val["DIAGERR"] <= (1e-12 if dp else 1e-5) * 1e3, r.stdout
+    # precompute + cost in one tiled pass (k_sfsPrecomputeTiled): B, flags and row coefficients identical to the two per-pixel passes
+    assert val["PREERR"] == 0.0 and abs(val["COST"] - val["COSTREF"]) <= (1e-13 if dp else 1e-6) * max(1.0, abs(val["COSTREF"])), r.stdout
+    assert val["HEADERR"] <= (1e-12 if dp else 1e-6) * max(1.0, abs(val["RZ0"])), r.stdout       # the head inside the loop kernel against the stand-alone one
     out = np.fromfile(str(res), np.float64).reshape(8, -1)
     o = Oracle("shape_from_shading", "LMGPU", [W, H], dp)
     ref = workloads.clone_params(host)
@@ -109,7 +113,8 @@ def test_sfs_tile_algorithms_match_oracle(tmp_path, W, H, tw, th, NT, k, dp):
     for idx, name in ((4, "delta"), (5, "r"), (6, "p"), (7, "z")):
         b = o2.get_vector(name).astype(np.float64)
         assert not np.any(out[idx] == -777.0), name                     # the epilogue rewrote every pixel
-        floor = (1e-12 if dp else 5e-6) * r0max if name in ("r", "z") else 0.0
+        # r = b - A delta after a reset: a few fp32 ulp of |J^T F|; z = r and p = z + beta p carry the same absolute noise
+        floor = (1e-12 if dp else 2e-5) * r0max if name in ("r", "z", "p") else 0.0
         assert np.abs(out[idx] - b).max() <= max(tol * max(1e-30, np.abs(b).max()), floor), (name, k, float(np.abs(out[idx] - b).max()), float(np.abs(b).max()))
     assert abs(val["MODEL"] - val["MODELREF"]) <= (1e-12 if dp else 2e-6) * max(1.0, abs(val["MODELREF"])), r.stdout     # model cost inside the loop kernel
     if k == 40:

@@ -263,8 +263,8 @@ __global__ void __launch_bounds__(NT, 1) k_sfsLoopResident(SfsData<T> P, ReduceW
         __syncthreads();
         for (int c = tid; c < V.cells(); c += NT) sfsTileRowResiduals(P, V, c);
         __syncthreads();
-        const T a0 = sfsLoopHead<T, KMAX>(P, V, R, tid, NT, usePre, head.saveSSq, (T)ws.scalars[kRadius], head.minDiag, head.maxDiag, head.SSq, zLL, sfsEdgeTag(k, 0));
-        sfsLoopFetchRing<T>(P, V, tid, NT, V.sp, zLL, sfsEdgeTag(k, 0));   // the neighbours' first direction on the ring
+        const T a0 = sfsLoopHead<T, KMAX>(P, V, R, tid, NT, usePre, head.saveSSq, (T)ws.scalars[kRadius], head.minDiag, head.maxDiag, head.SSq, zLL, sfsEdgeTag(k, kSfsEdgeFirstDirection));
+        sfsLoopFetchRing<T>(P, V, tid, NT, V.sp, zLL, sfsEdgeTag(k, kSfsEdgeFirstDirection));   // the neighbours' first direction on the ring
         gridAllReduce2LL<NT, false, false>((double)a0, 0.0, llWords, arrivals, ++k, ws.comm, 0, dRz, unused);   // r . p (its barriers also order the planes)
     } else {
         sfsLoopLoad<T, KMAX>(P, V, R, tid, NT, delta, r, b, CtC, pre, p, usePre, lm);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(NT, 1) k_sfsLoopResident(SfsData<T> P, ReduceW
         if (l > 0) {   // PCGStep3 of iteration l - 1
             T beta = T(0);
             { const T rn = (T)dRz, ro = (T)dRzPrev; if (ro > T(0)) beta = rn / ro; }
-            sfsLoopUpdateDirection<T, KMAX>(P, V, R, tid, NT, beta, zLL, sfsEdgeTag(k - 1, 1));   // the z published before the last all-reduce
+            sfsLoopUpdateDirection<T, KMAX>(P, V, R, tid, NT, beta, zLL, sfsEdgeTag(k - 1, kSfsEdgeZ));   // the z published before the last all-reduce
             __syncthreads();
         }
         for (int c = tid; c < V.cells(); c += NT) sfsTileRowsTimesVec(P, V, c, V.sp);
@@ -287,14 +287,14 @@ __global__ void __launch_bounds__(NT, 1) k_sfsLoopResident(SfsData<T> P, ReduceW
         { const T num = (T)dRz, den = (T)dPAp; if (den > T(0)) alpha = num / den; }
         T accRz = T(0), accQ = T(0);
         if (lm && resetPeriod > 0 && ((l + 1) % resetPeriod) == 0) {   // residual reset (:1077-1083): r = b - A delta instead of r -= alpha A p
-            sfsLoopResetFirstHalf<T, KMAX>(P, V, R, tid, NT, alpha, dLL, sfsEdgeTag(k, 2));
-            sfsLoopFetchRing<T>(P, V, tid, NT, V.sd, dLL, sfsEdgeTag(k, 2));   // waits word by word for the neighbours' delta
+            sfsLoopResetFirstHalf<T, KMAX>(P, V, R, tid, NT, alpha, dLL, sfsEdgeTag(k, kSfsEdgeDeltaReset));
+            sfsLoopFetchRing<T>(P, V, tid, NT, V.sd, dLL, sfsEdgeTag(k, kSfsEdgeDeltaReset));   // waits word by word for the neighbours' delta
             __syncthreads();
             for (int c = tid; c < V.cells(); c += NT) sfsTileRowsTimesVec(P, V, c, V.sd);
             __syncthreads();
-            sfsLoopResetSecondHalf<T, KMAX>(P, V, R, tid, NT, usePre, zLL, sfsEdgeTag(k, 1), accRz, accQ);
+            sfsLoopResetSecondHalf<T, KMAX>(P, V, R, tid, NT, usePre, zLL, sfsEdgeTag(k, kSfsEdgeZ), accRz, accQ);
         } else {
-            sfsLoopStep2<T, KMAX>(P, V, R, tid, NT, alpha, usePre, zLL, sfsEdgeTag(k, 1), accRz, accQ);
+            sfsLoopStep2<T, KMAX>(P, V, R, tid, NT, alpha, usePre, zLL, sfsEdgeTag(k, kSfsEdgeZ), accRz, accQ);
         }
         dRzPrev = dRz;
         gridAllReduce2LL<NT, false, false>((double)accRz, (double)accQ, llWords, arrivals, ++k, ws.comm, 0, dRz, dQ);
@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(NT, 1) k_sfsLoopResident(SfsData<T> P, ReduceW
     }
     if (withModelCost) {   // computeModelCost (:666-678) for the delta just found: its rows need delta on a 1-pixel ring
         double u1, dModel;
-        sfsLoopPublishDelta<T, KMAX>(P, V, R, tid, NT, dLL, sfsEdgeTag(k, 3));
-        sfsLoopFetchRing<T>(P, V, tid, NT, V.sd, dLL, sfsEdgeTag(k, 3));
+        sfsLoopPublishDelta<T, KMAX>(P, V, R, tid, NT, dLL, sfsEdgeTag(k, kSfsEdgeDeltaModel));
+        sfsLoopFetchRing<T>(P, V, tid, NT, V.sd, dLL, sfsEdgeTag(k, kSfsEdgeDeltaModel));
         __syncthreads();
         for (int c = tid; c < V.cells(); c += NT) sfsTileRowsTimesVec(P, V, c, V.sd);
         __syncthreads();

@@ -292,7 +292,8 @@ template <class T> SFS_HD bool sfsLoopPixel(const SfsData<T>& P, const SfsTileVi
 // Tile-edge values cross CTAs as self-validating words (payload | 32-bit tag in one 8-byte store, llStore / llLoad of common.cuh): the
 // reader polls the word until it carries the tag of the exchange it is in, so no fence and no barrier orders the data -- the two
 // all-reduces of a PCG step stay pure reductions.  One word (float) or two (double) per pixel, indexed like the image.
-// Tags grow monotonically per slot: 4 x (all-reduces completed so far) + {1: z of this step, 2: delta of a reset step, 3: delta for the model cost}.
+// Tags grow monotonically per slot: 8 x (all-reduces completed so far) + {1: z of this step, 2: delta of a reset step, 3: delta for the model
+// cost, 4: the first direction when the iteration's head runs inside the kernel}.
 #if defined(__CUDA_ARCH__)
 template <class T> SFS_HD void sfsEdgeStore(unsigned long long* ll, long gi, T v, unsigned tag) { llStore(ll + gi * LLWords<T>::N, v, tag); }
 template <class T> SFS_HD T sfsEdgeLoad(const unsigned long long* ll, long gi, unsigned tag) { T v; llLoad(ll + gi * LLWords<T>::N, tag, v); return v; }
@@ -304,11 +305,14 @@ template <class T> inline void sfsEdgeStore(unsigned long long* ll, long gi, T v
     ll[gi * 2] = bits; ll[gi * 2 + 1] = tag;
 }
 template <class T> inline T sfsEdgeLoad(const unsigned long long* ll, long gi, unsigned tag) {
-    if ((unsigned)ll[gi * 2 + 1] != tag) { fprintf(stderr, "edge word %ld carries tag %u, expected %u\n", gi, (unsigned)ll[gi * 2 + 1], tag); abort(); }
+    if ((unsigned)ll[gi * 2 + 1] != tag || tag == 0u) { fprintf(stderr, "edge word %ld carries tag %u, expected %u\n", gi, (unsigned)ll[gi * 2 + 1], tag); abort(); }
     double d; memcpy(&d, &ll[gi * 2], 8); return (T)d;
 }
 #endif
-SFS_HD unsigned sfsEdgeTag(unsigned long long reductionsDone, int what) { return (unsigned)(4ull * reductionsDone + (unsigned long long)what); }
+// kinds 1..4, never 0: the buffers start zeroed, and a reader of the plan's very first exchange (no all-reduce done yet) must not take an
+// untouched word for a published one (it did with tag 4 k + 0: the first nonlinear iteration of a plan read zeros for some ring cells)
+SFS_HD unsigned sfsEdgeTag(unsigned long long reductionsDone, int what) { return (unsigned)(8ull * reductionsDone + (unsigned long long)what); }
+constexpr int kSfsEdgeZ = 1, kSfsEdgeDeltaReset = 2, kSfsEdgeDeltaModel = 3, kSfsEdgeFirstDirection = 4;
 
 // prologue: the direction with its ring, this thread's pixels
 template <class T, int KMAX>

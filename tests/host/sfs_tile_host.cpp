@@ -116,7 +116,7 @@ int main(int argc, char** argv) {
     std::vector<SfsTileView<T>> V(nCta);
     std::vector<std::vector<SfsLoopRegs<T, KMAX>>> R(nCta, std::vector<SfsLoopRegs<T, KMAX>>(NT));
     std::vector<unsigned long long> zLL(2 * N, 0ull), dLL(2 * N, 0ull);   // tile-edge words (value, tag)
-    unsigned long long kRed = 1000;                                      // all-reduces completed so far (the kernel continues the plan's sequence)
+    unsigned long long kRed = 0;                                         // all-reduces completed so far (the kernel continues the plan's sequence)
     bool tailPhase = false;
     std::vector<T> SSqLoop(N, T(7));
     double rzHead = 0.0;
@@ -132,8 +132,8 @@ int main(int argc, char** argv) {
     if (headInLoop) {   // the LM head inside the loop kernel: residual rows, head per pixel (direction published on the tile edges), ring, r . p
         for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) for (int c = tid; c < V[cta].cells(); c += NT) sfsTileRowResiduals(P, V[cta], c);
         for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid)
-            rzHead += (double)sfsLoopHead<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, 0, 1, radius, minDiag, maxDiag, SSqLoop.data(), zLL.data(), sfsEdgeTag(kRed, 0));
-        for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopFetchRing<T>(P, V[cta], tid, NT, V[cta].sp, zLL.data(), sfsEdgeTag(kRed, 0));
+            rzHead += (double)sfsLoopHead<T, KMAX>(P, V[cta], R[cta][tid], tid, NT, 0, 1, radius, minDiag, maxDiag, SSqLoop.data(), zLL.data(), sfsEdgeTag(kRed, kSfsEdgeFirstDirection));
+        for (int cta = 0; cta < nCta; ++cta) for (int tid = 0; tid < NT; ++tid) sfsLoopFetchRing<T>(P, V[cta], tid, NT, V[cta].sp, zLL.data(), sfsEdgeTag(kRed, kSfsEdgeFirstDirection));
         ++kRed;
     }
     double dRz = headInLoop ? rzHead : rz0, dRzPrev = 0.0, dPAp = 0.0, dQ = 0.0;

@@ -18,3 +18,6 @@ fi
 if [ ! -f "$HERE/_ref/libref_sfs.so" ] || [ "$HERE/ref_sfs_shim.cpp" -nt "$HERE/_ref/libref_sfs.so" ]; then
   $CXX $FLAGS -I"$REF/examples/shape_from_shading/src" -o "$HERE/_ref/libref_sfs.so" "$HERE/ref_sfs_shim.cpp"
 fi
+if [ ! -f "$HERE/_ref/libref_poisson.so" ] || [ "$HERE/ref_poisson_shim.cpp" -nt "$HERE/_ref/libref_poisson.so" ]; then
+  $CXX $FLAGS -I"$REF/examples/poisson_image_editing/src" -o "$HERE/_ref/libref_poisson.so" "$HERE/ref_poisson_shim.cpp"
+fi

@@ -47,6 +47,24 @@ def shape_from_shading_from_files(prefix, dtype=np.float32):
     return [float(v) for v in scal] + [c(X), c(D), c(Im), eR, eC], (W, H)
 
 
+def poisson_from_files(image0_png, image1_png, mask_png, dtype=np.float32):
+    """examples/poisson_image_editing/src/main.cpp:5-67 + CombinedSolver.h:66-90 (BASELINE.json configs[0]): X0 = the base image
+    (RGB as floats 0..255, alpha forced to 255), T = the image to insert (same treatment, placed at offset 0 on a black canvas of the
+    base image's size), M = 0 where the mask file's red channel is 255 (the blend region: those pixels are solved for) and 255 elsewhere
+    (excluded).  The app solves with nIterations = 1, lIterations = 100.  Returns (params, (W, H))."""
+    a = io.read_png(image0_png).astype(dtype); b = io.read_png(image1_png).astype(dtype); m = io.read_png(mask_png)[..., 0]
+    H, W = a.shape[:2]
+    X = a[..., :4].copy(); X[..., 3] = 255
+    T = np.zeros_like(X); T[..., 3] = 255
+    h, w = min(H, b.shape[0]), min(W, b.shape[1])
+    T[:h, :w, :3] = b[:h, :w, :3]
+    M = np.zeros((H, W), dtype)
+    hm, wm = min(H, m.shape[0]), min(W, m.shape[1])
+    M[:hm, :wm] = m[:hm, :wm]                              # imageR32MaskLarge: the mask file on a zero canvas
+    M = np.where(M == 255, 0, 255).astype(dtype)
+    return [np.ascontiguousarray(X.reshape(-1, 4)), np.ascontiguousarray(T.reshape(-1, 4)), np.ascontiguousarray(M.reshape(-1))], (W, H)
+
+
 def sqrt3_subdivide(v, faces):
     """One step of Kobbelt's sqrt(3) subdivision of a closed triangle mesh -- what the reference app applies to its input once
     before solving (OpenMesh::Subdivider::Uniform::Sqrt3T, examples/arap_mesh_deformation/src/main.cpp:60-73; the marker file indexes

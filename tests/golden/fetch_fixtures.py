@@ -9,7 +9,7 @@ import shutil
 
 SRC = "/root/reference/examples/data"
 DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures")
-FILES = ["cat512_mask.png", "cat512.constraints", "small_armadillo.ply", "small_armadillo.mrk",
+FILES = ["cat512_mask.png", "cat512.constraints", "small_armadillo.ply", "small_armadillo.mrk", "poisson0.png", "poisson1.png", "poisson_mask.png",
          "shape_from_shading/default.SFSSolverParameters", "shape_from_shading/default_initialUnknown.imagedump",
          "shape_from_shading/default_maskEdgeMap.imagedump", "shape_from_shading/default_targetDepth.imagedump",
          "shape_from_shading/default_targetIntensity.imagedump"]

@@ -103,6 +103,7 @@ void Opt_ProblemInit(Opt_State*, Opt_Plan* plan, void** problemparams) { plan->i
 int Opt_ProblemStep(Opt_State*, Opt_Plan* plan, void** problemparams) { return plan->impl->step(problemparams); }
 void Opt_ProblemSolve(Opt_State* s, Opt_Plan* plan, void** problemparams) {   // o.t:2548-2551
     Opt_ProblemInit(s, plan, problemparams);
+    plan->impl->runDeviceIterations(problemparams);   // no-op unless the plan keeps the LM decision on the device (OPTB_DEVICE_LM=1)
     while (Opt_ProblemStep(s, plan, problemparams)) {}
 }
 double Opt_ProblemCurrentCost(Opt_State*, Opt_Plan* plan) { return plan->impl->currentCost(); }

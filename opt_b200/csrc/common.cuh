@@ -38,6 +38,13 @@ enum Scalar : int {
     kQPrev = 6,     // previous q (LM zeta test on device)
     kFlags = 7,     // device-side control word (LM early-out), stored as a double 0/1
     kRadius = 10,   // LM trust-region radius of the current nonlinear iteration (host decides, kernels read it here: the iteration graph stays the same)
+    // LM decision on the device (OPTB_DEVICE_LM=1, lm_decide.cuh / k_lmDecide in solver.cu): the nonlinear state the host keeps otherwise.
+    // All zero unless that mode runs, so a kernel that tests kLmGate / kLmReject behaves as before everywhere else.
+    kLmPrevCost = 11, // cost of the last accepted iterate
+    kLmFactor = 12,   // radius_decrease_factor
+    kLmGate = 13,     // != 0: the solve has ended (LmVerdict that ended it); gated kernels of the remaining enqueued iterations return at once
+    kLmReject = 14,   // 1: the iteration just decided was rejected (revert the unknowns, redo precompute)
+    kLmIters = 15,    // nonlinear iterations completed on the device since the state was uploaded
     kNumScalars = 16
 };
 

@@ -185,8 +185,10 @@ __global__ void __launch_bounds__(kBlock) k_sfsApplyJTJTiled(SfsData<T> P, Reduc
 // kernels.precompute (:607-614) and computeCost (:580-592) in one pass over 32x8 tiles (sfsPreCell / sfsPrePixel in sfs_tile.cuh): dB never
 // goes through global memory and the three launches of the per-pixel path (k_sfsPrecomputeB, k_sfsBuildRows, k_sfsCost) become one.
 template <class T>
-__global__ void __launch_bounds__(kBlock) k_sfsPrecomputeTiled(SfsData<T> P, ReduceWorkspace ws, int slot, int tilesX, int numTiles) {
+__global__ void __launch_bounds__(kBlock) k_sfsPrecomputeTiled(SfsData<T> P, ReduceWorkspace ws, int slot, int tilesX, int numTiles, int gate) {
     __shared__ __align__(16) unsigned char planes[sfsPrePlaneBytes<T>(kSfsTW, kSfsTH)];
+    // LM decision on the device (LaunchCtx::gate): the same answer in every thread of the grid, before anything is touched
+    if (gate && (ws.scalars[kLmGate] != 0.0 || (gate == 2 && ws.scalars[kLmReject] == 0.0))) return;
     const int tid = threadIdx.x, tx = tid % kSfsTW, ty = tid / kSfsTW;
     T acc = T(0);
     for (int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
@@ -245,9 +247,12 @@ template <class T, int KMAX, int NT>
 __global__ void __launch_bounds__(NT, 1) k_sfsLoopResident(SfsData<T> P, ReduceWorkspace ws, unsigned long long* llWords, unsigned long long* arrivals, unsigned long long* seqWord,
                                                            unsigned long long* zLL, unsigned long long* dLL,
                                                              int L, int tw, int th, int tilesX, int usePre, int lm, int resetPeriod, int withModelCost, T qTol,
-                                                             T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC, T* xUpdate, T* xSaved, SfsLoopHead<T> head) {
+                                                             T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC, T* xUpdate, T* xSaved, SfsLoopHead<T> head, int gate) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int tid = threadIdx.x;
+    // LM decision on the device: an iteration enqueued behind the one that ended the solve does nothing -- every CTA reads the same word
+    // (written by k_lmDecide, an earlier kernel on this stream) and leaves before the first all-reduce, so the sequence word stays put
+    if (gate && ws.scalars[kLmGate] != 0.0) return;
     const SfsTileView<T> V = sfsCarveTile<T>(smemRaw, ((int)blockIdx.x % tilesX) * tw, ((int)blockIdx.x / tilesX) * th, tw, th, true);
     SfsLoopRegs<T, KMAX> R;
     unsigned long long k = ldVolatileU64(seqWord);   // written by the previous launch on this stream; every CTA reads it before the first all-reduce can complete
@@ -461,7 +466,8 @@ struct SfsOps : EnergyOps<T> {
     // solver.cu pairs them) is then free
     bool fuseCost = true, fusePre = true, costFresh = false; int gridPre = 1;
     void precompute(const LaunchCtx& c) override {
-        if (fusePre) { k_sfsPrecomputeTiled<T><<<gridPre, kBlock, 0, c.stream>>>(P, c.ws, kCost, tilesX, numTiles); costFresh = true; return; }
+        if (fusePre) { k_sfsPrecomputeTiled<T><<<gridPre, kBlock, 0, c.stream>>>(P, c.ws, kCost, tilesX, numTiles, c.gate); costFresh = true; return; }
+        if (c.gate) EnergyOps<T>::unsupported("a gated precompute without the fused precompute + cost pass");
         k_sfsPrecomputeB<T><<<grid, kBlock, 0, c.stream>>>(P);
         if (fuseCost) { k_sfsBuildRowsCost<T><<<grid, kBlock, 0, c.stream>>>(P, c.ws, kCost); costFresh = true; }
         else k_sfsBuildRows<T><<<grid, kBlock, 0, c.stream>>>(P);
@@ -483,6 +489,8 @@ struct SfsOps : EnergyOps<T> {
     bool fuseModel = true, fuseUpdate = true;
     bool fuseHeadInLoop = true;
     bool pcgLoopTakesHead(int L, bool lm) override { return loopTW && L >= 2 && lm && fuseHeadInLoop && fusedHead; }
+    // head + loop + model cost + update in the loop kernel, precompute + cost in one pass: both kernels test LaunchCtx::gate
+    bool deviceLmCapable() const override { return loopTW && fusedHead && fuseHeadInLoop && fuseModel && fuseUpdate && fusePre; }
     int pcgLoopOnChip(const LaunchCtx& c, int L, bool lm, int resetPeriod, T qTol, T* delta, T* r, T* z, T* p, T* Ap, const T* pre, const T* b, const T* CtC,
                       bool* modelCostDone, T* prevX, bool* updateDone, const typename EnergyOps<T>::LoopHeadArgs* headArgs) override {
         if (!loopTW || L < 2) { if (headArgs) EnergyOps<T>::unsupported("pcgLoopOnChip with the head after pcgLoopTakesHead said yes"); return 0; }
@@ -497,10 +505,10 @@ struct SfsOps : EnergyOps<T> {
         if (updateDone) *updateDone = xUpdate != nullptr;
         ReduceWorkspace ws = c.ws;
         unsigned long long* arrivals = loopWords + 2 * 4 * (kMaxLLCtas + 1); unsigned long long* seqWord = arrivals + 1;
-        int usePre = this->usePreconditioner ? 1 : 0, lmi = lm ? 1 : 0;
+        int usePre = this->usePreconditioner ? 1 : 0, lmi = lm ? 1 : 0, gate = c.gate;
         unsigned long long* zLL = loopEdge; unsigned long long* dLL = loopEdge + (size_t)N * LLWords<T>::N;
         void* args[] = { (void*)&P, (void*)&ws, (void*)&loopWords, (void*)&arrivals, (void*)&seqWord, (void*)&zLL, (void*)&dLL, (void*)&L, (void*)&loopTW, (void*)&loopTH, (void*)&loopTilesX, (void*)&usePre, (void*)&lmi,
-                         (void*)&resetPeriod, (void*)&withModel, (void*)&qTol, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre, (void*)&b, (void*)&CtC, (void*)&xUpdate, (void*)&xSaved, (void*)&head };
+                         (void*)&resetPeriod, (void*)&withModel, (void*)&qTol, (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&Ap, (void*)&pre, (void*)&b, (void*)&CtC, (void*)&xUpdate, (void*)&xSaved, (void*)&head, (void*)&gate };
         OPT_CUDA_CHECK(cudaLaunchCooperativeKernel(loopFn(), dim3((unsigned)loopGrid), dim3((unsigned)loopNT), args, loopSmem, c.stream));
         return L;
     }

@@ -19,6 +19,7 @@
 #include <map>
 #include "solver.h"
 #include "frontend.h"
+#include "lm_decide.cuh"
 
 namespace optb {
 
@@ -264,6 +265,24 @@ template <class T> __global__ void __launch_bounds__(kBlock) k_axpyInto(long n, 
 template <class T> __global__ void __launch_bounds__(kBlock) k_saveAndUpdate(long n, T* __restrict__ saved, T* __restrict__ x, const T* __restrict__ d) {
     for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long)gridDim.x * kBlock) { const T v = x[i]; saved[i] = v; x[i] = v + d[i]; }
 }
+// ---- LM accept / reject / trust-region update on the device (OPTB_DEVICE_LM=1; Plan::runDeviceIterations).  One thread: the decision
+// is a dozen scalar operations (lm_decide.cuh = :1119-1157); what it buys is that no host round trip separates two nonlinear iterations.
+template <class T>
+__global__ void k_lmDecide(ReduceWorkspace ws, LmLimits<T> lim) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double* s = ws.scalars;
+    if (s[kLmGate] != 0.0) { s[kLmReject] = 0.0; return; }   // the solve ended in an earlier enqueued iteration
+    LmState<T> st{ (T)s[kLmPrevCost], (T)s[kRadius], (T)s[kLmFactor] };
+    const int v = lmDecide<T>((T)s[kCost], (T)s[kModelCost], st, lim);
+    s[kLmPrevCost] = (double)st.prevCost; s[kRadius] = (double)st.radius; s[kLmFactor] = (double)st.decreaseFactor;
+    s[kLmReject] = (v == kLmRejected || v == kLmRadiusTooSmall) ? 1.0 : 0.0;
+    if (v == kLmFunctionTolerance || v == kLmRadiusTooSmall) s[kLmGate] = (double)v;   // the host's step() returns 0 here, before ++nIter
+    else s[kLmIters] += 1.0;
+}
+template <class T> __global__ void __launch_bounds__(kBlock) k_copyIfRejected(long n, T* __restrict__ dst, const T* __restrict__ src, ReduceWorkspace ws) {   // revertUpdate :559-564
+    if (ws.scalars[kLmReject] == 0.0) return;
+    for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long)gridDim.x * kBlock) dst[i] = src[i];
+}
 template <class T> __global__ void __launch_bounds__(kBlock) k_copy(long n, T* __restrict__ dst, const T* __restrict__ src) {
     for (long i = (long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long)gridDim.x * kBlock) dst[i] = src[i];
 }
@@ -432,6 +451,8 @@ struct Plan : PlanBase {
         dropTimedLaunches();
         if (loopExec) cudaGraphExecDestroy(loopExec);
         if (iterExec) cudaGraphExecDestroy(iterExec);
+        if (devIterExec) cudaGraphExecDestroy(devIterExec);
+        if (hLmState) cudaFreeHost(hLmState);
         if (hRadius) cudaFreeHost(hRadius);
         for (T* v : { delta, r, z, p, p2, Ap, pre, b, Adelta, CtC, SSq, prevX }) if (v) cudaFree(v);
         for (void* q : ipcOpened) cudaIpcCloseMemHandle(q);
@@ -441,7 +462,8 @@ struct Plan : PlanBase {
         if (ownStream) cudaStreamDestroy(stream);
         delete E;
     }
-    LaunchCtx ctx() const { return LaunchCtx{ stream, ws, numSMs, usePdl }; }
+    int ctxGate = 0;   // LaunchCtx::gate of the launches being enqueued (non-zero only while runDeviceIterations captures its graph)
+    LaunchCtx ctx() const { return LaunchCtx{ stream, ws, numSMs, usePdl, ctxGate }; }
 
     void setParameter(const char* name, const void* v) override {   // :1205-1221
         std::string s(name);
@@ -991,6 +1013,78 @@ struct Plan : PlanBase {
         OPT_CUDA_CHECK(cudaEventElapsedTime(&loopMs, evLoop0, evLoop1)); loopMsPending = false;
         return decide(newCost, c);
     }
+    // ---- LM with the decision on the device (opt-in: OPTB_DEVICE_LM=1; single GPU; energies that answer deviceLmCapable()).
+    // Opt_ProblemSolve calls this after Init.  The first nonlinear iteration runs through step() (PCGSaveSSq, and the host needs one
+    // decision to seed the state); the nonlinear state (radius, previous cost, decrease factor) then moves into the scalar block and ALL
+    // remaining iterations are enqueued back to back, each one graph launch:
+    //     loop kernel (head, PCG loop, model cost, save + update)   -- returns at once when scalars[kLmGate] != 0
+    //     precompute + cost                                         -- likewise
+    //     k_lmDecide          accept / reject / radius / end of solve (lm_decide.cuh, the arithmetic of decide() below)
+    //     k_copyIfRejected    revertUpdate
+    //     precompute + cost   only after a rejection
+    // and the host waits ONCE, for the state, when they are all through.  An iteration enqueued behind the one that ended the solve
+    // costs five empty launches.  Opt_ProblemStep keeps the host-side decision (it has to return it).
+    cudaGraphExec_t devIterExec = nullptr; unsigned long long devIterKey = 0; int devIterLaunchCount = 0; T* devIterPFinal = nullptr;
+    double* hLmState = nullptr; int deviceIterationsRun = 0;
+    void runDeviceIterations(void** params) override {
+        deviceIterationsRun = 0;
+        const char* want = getenv("OPTB_DEVICE_LM");
+        if (!want || atoi(want) == 0 || !lm || world != 1 || finished) return;
+        if (!useIterGraph || !useGraph || timingOn || maxLinIters >= 0 || verbosity > 0 || !E->capturable()) return;
+        const int L = sp.lIterations;
+        if (nIter == 0) { if (!(nIter < sp.nIterations) || !step(params)) return; }
+        if (finished || !(nIter < sp.nIterations)) return;
+        E->bind(params);
+        if (!E->deviceLmCapable() || !loopTakesHead(L)) return;
+        enter();
+        const LmLimits<T> lim{ (T)sp.min_relative_decrease, (T)sp.function_tolerance, (T)sp.max_trust_region_radius, (T)sp.min_trust_region_radius };
+        unsigned long long key = E->captureKey();
+        { const long v[] = { (long)L, (long)sp.residual_reset_period, (long)n }; key = EnergyOps<T>::hashBytes(v, sizeof(v), key); }
+        key = EnergyOps<T>::hashValue(sp.q_tolerance, key); key = EnergyOps<T>::hashValue(min_lm_diagonal, key); key = EnergyOps<T>::hashValue(max_lm_diagonal, key);
+        key = EnergyOps<T>::hashValue(lim, key);
+        if (!devIterExec || devIterKey != key) {
+            cudaGraph_t g;
+            const int saved = launches;
+            OPT_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            ctxGate = 1;
+            headInLoop = true; headSaveSSq = false;
+            emitLoop(L, false);
+            const bool whole = loopDidModelCost && loopDidUpdate;
+            E->precompute(ctx()); ++launches;
+            k_lmDecide<T><<<1, 1, 0, stream>>>(ws, lim); ++launches;
+            for (auto& u : E->unknowns) { long cnt = u.elements * u.channels; k_copyIfRejected<T><<<gridFor(cnt), kBlock, 0, stream>>>(cnt, (T*)u.user, prevX + u.offset, ws); ++launches; }
+            ctxGate = 2;
+            E->precompute(ctx()); ++launches;
+            ctxGate = 0;
+            OPT_CUDA_CHECK(cudaStreamEndCapture(stream, &g));
+            const int count = launches - saved; launches = saved;
+            if (!whole) { OPT_CUDA_CHECK(cudaGraphDestroy(g)); return; }   // the loop kernel left its tail to separate launches: host path
+            bool updated = false;
+            if (devIterExec) {
+                cudaGraphExecUpdateResultInfo info{};
+                if (cudaGraphExecUpdate(devIterExec, g, &info) == cudaSuccess) updated = true;
+                else { cudaGetLastError(); cudaGraphExecDestroy(devIterExec); devIterExec = nullptr; }
+            }
+            if (!updated) OPT_CUDA_CHECK(cudaGraphInstantiate(&devIterExec, g, 0));
+            OPT_CUDA_CHECK(cudaGraphDestroy(g));
+            devIterKey = key; devIterLaunchCount = count; devIterPFinal = pFinal; ++graphBuilds;
+        }
+        if (!hLmState) OPT_CUDA_CHECK(cudaMallocHost((void**)&hLmState, sizeof(double) * 6));
+        static_assert(kLmPrevCost == kRadius + 1 && kLmFactor == kRadius + 2 && kLmGate == kRadius + 3 && kLmReject == kRadius + 4 && kLmIters == kRadius + 5 && kLmIters + 1 == kNumScalars,
+                      "the nonlinear state is uploaded as one block behind kRadius");
+        hLmState[0] = (double)trust_region_radius; hLmState[1] = (double)prevCost; hLmState[2] = (double)radius_decrease_factor;
+        hLmState[3] = hLmState[4] = hLmState[5] = 0.0;
+        OPT_CUDA_CHECK(cudaMemcpyAsync(ws.scalars + kRadius, hLmState, sizeof(double) * 6, cudaMemcpyHostToDevice, stream));
+        const int remaining = sp.nIterations - nIter;
+        for (int i = 0; i < remaining; ++i) OPT_CUDA_CHECK(cudaGraphLaunch(devIterExec, stream));
+        OPT_CUDA_CHECK(cudaMemcpyAsync(hScalars, ws.scalars, sizeof(double) * kNumScalars, cudaMemcpyDeviceToHost, stream));
+        OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
+        pFinal = devIterPFinal; launches = devIterLaunchCount; loopMs = 0;
+        prevCost = (T)hScalars[kLmPrevCost]; trust_region_radius = (T)hScalars[kRadius]; radius_decrease_factor = (T)hScalars[kLmFactor];
+        deviceIterationsRun = (int)hScalars[kLmIters];
+        nIter += deviceIterationsRun;
+        if (hScalars[kLmGate] != 0.0) { finished = true; if (!reported) { finishSolve(); reported = true; } }
+    }
     // the host side of the nonlinear iteration: accept / reject / trust-region update (:1119-1157), with the cost and model cost already read back
     int decide(T newCost, const LaunchCtx& c) {
         T model_cost_change = 0;
@@ -1114,6 +1208,7 @@ struct Plan : PlanBase {
         if (s == "q") return hScalars[kQ]; if (s == "flags") return hScalars[kFlags];
         if (s == "trust_region_radius") return (double)trust_region_radius;
         if (s == "cost") return hScalars[kCost]; if (s == "modelCost") return hScalars[kModelCost];
+        if (s == "deviceIterations") return (double)deviceIterationsRun; if (s == "nIter") return (double)nIter;
         return NAN;
     }
 };

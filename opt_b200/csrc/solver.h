@@ -60,6 +60,10 @@ struct LaunchCtx {
     ReduceWorkspace ws;
     int numSMs;
     bool pdl;   // launch inner-loop kernels with programmatic dependent launch (common.cuh)
+    // LM decision on the device (solver.cu runDeviceIterations): 0 = launch as always; 1 = the kernels return at once when scalars[kLmGate] != 0
+    // (the solve ended in an earlier enqueued iteration); 2 = they run only if the iteration just decided was rejected (scalars[kLmReject])
+    // and the solve has not ended.  Only energies that answer deviceLmCapable() look at it.
+    int gate = 0;
 };
 
 // Per-energy kernels ("function map").  T = opt_float (float or double).
@@ -120,6 +124,9 @@ struct EnergyOps {
     virtual void modelCost(const LaunchCtx&, const T* /*delta*/) { unsupported("modelCost (LM)"); }
     // ComputedArray refresh (kernels.precompute, solverGPUGaussNewton.t:607-614)
     virtual void precompute(const LaunchCtx&) {}
+    // optional: with the current toggles a whole LM iteration is pcgLoopOnChip (head, loop, model cost, update) + precompute (which also
+    // leaves the cost), and both honour LaunchCtx::gate -- the plan may then keep the accept / reject decision on the device
+    virtual bool deviceLmCapable() const { return false; }
     // multi-GPU: can THIS rank run pcgLoop's multi-rank form for its slab (tile shape fits the shared memory, all tiles co-resident,
     // cooperative launch available)?  Asked once per OptB200_PlanConnect, after setSlab(); the plan combines the answers of all ranks
     // so that either every rank takes the collective kernel or none does.  After a "yes" a refusal inside pcgLoop is fatal.
@@ -172,6 +179,9 @@ struct PlanBase {
     virtual void setParameter(const char* name, const void* value) = 0;
     virtual void init(void** params) = 0;
     virtual int step(void** params) = 0;
+    // Opt_ProblemSolve calls this between Init and its Step loop: a plan may run nonlinear iterations here without returning to the
+    // caller in between (LM with the decision on the device); whatever is left is done by the Step loop
+    virtual void runDeviceIterations(void** /*params*/) {}
     virtual double currentCost() const = 0;
     // ---- extension entry points (include/OptB200.h)
     virtual long numUnknowns() const = 0;

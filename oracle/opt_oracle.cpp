@@ -380,6 +380,7 @@ struct Oracle : OracleBase {
     T scanAlphaNum = 0, scanAlphaDen = 0, scanBetaNum = 0, q = 0;
     T prevCost = 0;
     T trust_region_radius = 0, radius_decrease_factor = 0, min_lm_diagonal = 0, max_lm_diagonal = 0;
+    T lastNewCost = 0, lastModelCost = 0;
     int nIter = 0;
 
     Oracle(Energy<T>* e, bool isLM) : E(e), lm(isLM) {}
@@ -656,7 +657,8 @@ struct Oracle : OracleBase {
         if (maxLinIters >= 0) return 1;   // debugging: leave PCG state for inspection, no update
         T model_cost_change = 0;
         if (lm) {   // :1108-1113
-            model_cost_change = prevCost - computeModelCost();
+            lastModelCost = computeModelCost();
+            model_cost_change = prevCost - lastModelCost;
             for (size_t a = 0; a < E->U.size(); ++a) { const UArr<T>& u = E->U[a]; for (long k = 0; k < u.n * u.ch; ++k) if (active[u.off + k]) prevX[u.off + k] = u.data[k]; }
         }
         for (size_t a = 0; a < E->U.size(); ++a) {   // PCGLinearUpdate :552-557
@@ -665,6 +667,7 @@ struct Oracle : OracleBase {
             for (long k = 0; k < u.n * u.ch; ++k) if (active[u.off + k]) u.data[k] = u.data[k] + delta[u.off + k];
         }
         T newCost = computeCost();
+        lastNewCost = newCost;
         if (lm) {   // :1119-1157
             T cost_change = prevCost - newCost;
             T relative_decrease = cost_change / model_cost_change;
@@ -724,6 +727,7 @@ struct Oracle : OracleBase {
         if (s == "scanAlphaNumerator") return scanAlphaNum; if (s == "scanAlphaDenominator") return scanAlphaDen;
         if (s == "scanBetaNumerator") return scanBetaNum; if (s == "q") return q; if (s == "trust_region_radius") return trust_region_radius;
         if (s == "secondsLinear") return secondsLinear; if (s == "linearSteps") return (double)linearSteps;
+        if (s == "newCost") return (double)lastNewCost; if (s == "modelCost") return (double)lastModelCost;   // of the last nonlinear iteration (before the accept / reject decision)
         return NAN;
     }
 };

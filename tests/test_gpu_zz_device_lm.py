@@ -9,6 +9,8 @@ Written after this round's GPU budget was spent: never run on hardware, hence th
 the evidence, a failure does not hide the verified suite.  The mode is opt-in and touches no default launch."""
 import contextlib
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -16,6 +18,18 @@ import pytest
 from opt_b200 import workloads
 
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent; first hardware run is the driver's")]
+
+
+@pytest.fixture
+def child(request):
+    """These tests have never run on hardware, and a CUDA failure inside libOpt.so ends the process (printf + exit, like the reference,
+    util.t:739-768): so each one runs in its own python.  In the parent this fixture runs the very same test id in a child (xfail marks
+    off) and hands its result to the body, which only checks the exit code; in the child it returns None and the body runs."""
+    if os.environ.get("OPTB_TEST_CHILD") == "1":
+        return None
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "--runxfail", "-m", "gpu", "-p", "no:cacheprovider", request.node.nodeid],
+                          cwd=root, env=dict(os.environ, OPTB_TEST_CHILD="1"), capture_output=True, text=True, timeout=900)
 
 
 @contextlib.contextmanager
@@ -55,7 +69,10 @@ CASES = {
 
 @pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.parametrize("W,H", [(64, 48), (640, 480)])
-def test_device_decision_ends_where_the_host_decision_ends(built, W, H, case):
+def test_device_decision_ends_where_the_host_decision_ends(built, W, H, case, child):
+    if child is not None:
+        assert child.returncode == 0, (child.stdout + child.stderr)[-3000:]
+        return
     host = workloads.shape_from_shading(W, H)
     sp = CASES[case]
     (c0, x0, n0, r0, d0), = _solve(W, H, sp, False, host)
@@ -76,7 +93,10 @@ def test_device_decision_ends_where_the_host_decision_ends(built, W, H, case):
         assert n0 < sp["nIterations"] and np.array_equal(x0, host[16]) and np.array_equal(x1, host[16])
 
 
-def test_device_decision_against_the_oracle_and_twice_on_one_plan(built):
+def test_device_decision_against_the_oracle_and_twice_on_one_plan(built, child):
+    if child is not None:
+        assert child.returncode == 0, (child.stdout + child.stderr)[-3000:]
+        return
     from oracle.oracle import Oracle
     W, H = 200, 150
     host = workloads.shape_from_shading(W, H)

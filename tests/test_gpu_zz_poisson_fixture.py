@@ -7,6 +7,8 @@ Written after this round's GPU budget was spent: it has never run on hardware, h
 at 21x17 in test_gpu_generic_energies.py; what is new here is the size, the real image statistics and the app's schedule).  An XPASS in the
 driver's run is the evidence; a failure does not hide the verified suite."""
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -14,6 +16,20 @@ import pytest
 from opt_b200 import examples, workloads
 
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent; first hardware run is the driver's")]
+
+
+@pytest.fixture
+def child(request):
+    """These tests have never run on hardware, and a CUDA failure inside libOpt.so ends the process (printf + exit, like the reference,
+    util.t:739-768): so each one runs in its own python.  In the parent this fixture runs the very same test id in a child (xfail marks
+    off) and hands its result to the body, which only checks the exit code; in the child it returns None and the body runs."""
+    if os.environ.get("OPTB_TEST_CHILD") == "1":
+        return None
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "--runxfail", "-m", "gpu", "-p", "no:cacheprovider", request.node.nodeid],
+                          cwd=root, env=dict(os.environ, OPTB_TEST_CHILD="1"), capture_output=True, text=True, timeout=900)
+
+
 F = examples.FIXTURES
 
 
@@ -29,7 +45,10 @@ def _flat(s, vec):
 
 
 @pytest.mark.parametrize("route", ["registry", "frontend"])
-def test_poisson_shipped_images_kernel_level(built, route):
+def test_poisson_shipped_images_kernel_level(built, route, child):
+    if child is not None:
+        assert child.returncode == 0, (child.stdout + child.stderr)[-3000:]
+        return
     from opt_b200 import OptSolver, spec_path
     from oracle.oracle import Oracle
     host, (W, H) = _problem()
@@ -54,8 +73,11 @@ def test_poisson_shipped_images_kernel_level(built, route):
     s.close()
 
 
-def test_poisson_shipped_images_app_schedule(built):
+def test_poisson_shipped_images_app_schedule(built, child):
     """nIterations = 1, lIterations = 100 as the app runs it; fp32 on both sides, different summation orders"""
+    if child is not None:
+        assert child.returncode == 0, (child.stdout + child.stderr)[-3000:]
+        return
     from opt_b200 import OptSolver, spec_path
     from oracle.oracle import Oracle
     host, (W, H) = _problem()

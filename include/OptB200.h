@@ -34,7 +34,9 @@ void OptB200_ApplyJTJ(Opt_Plan* plan, void** problemparams, const void* x, void*
 void OptB200_SetMaxLinearIterations(Opt_Plan* plan, int k);
 /* name in {delta,r,z,p,Ap_X,preconditioner,CtC,b}; returns 0 on success */
 int OptB200_ReadVector(Opt_Plan* plan, const char* name, void* hostOut);
-/* name in {scanAlphaDenominator,rz0,rz1,q,flags,trust_region_radius,cost,modelCost} */
+/* name in {scanAlphaDenominator,rz0,rz1,q,flags,trust_region_radius,cost,modelCost,nIter,deviceIterations}
+ * (nIter: nonlinear iterations completed in the current solve, solverGPUGaussNewton.t:1173; deviceIterations: how many of them the last
+ * Opt_ProblemSolve ran with the LM decision on the device, OPTB_DEVICE_LM=1 -- 0 otherwise) */
 double OptB200_ReadScalar(Opt_Plan* plan, const char* name);
 
 /* Order the plan's work after `stream` (a cudaStream_t) instead of the legacy NULL stream. */

@@ -110,6 +110,72 @@ def arap_from_files(mesh_file, marker_file, alpha=1.0, dtype=np.float32, w_fit=4
     return [float(np.sqrt(np.float32(w_fit))), float(np.sqrt(np.float32(w_reg))), c(v), np.zeros((N, 3), dtype), c(v), cons, int(len(head)), head, tail], N
 
 
+def read_tets(ele_file):
+    """TetGen .ele file as the reference reads it (robust_nonrigid_alignment/src/main.cpp:17-31): `count 4 0`, then `index a b c d` per line"""
+    with open(ele_file) as f:
+        tok = f.read().split("#")[0].split()
+    n = int(tok[0])
+    return np.asarray(tok[3:3 + 5 * n], np.int64).reshape(n, 5)[:, 1:].astype(np.int32)
+
+
+def vertex_normals(v, faces):
+    """what OpenMesh's update_normals() leaves at the vertices (the harness's source of normals): the normalised sum of the unit normals
+    of the incident faces"""
+    v = np.asarray(v, np.float64); f = np.asarray(faces, np.int64)
+    fn = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
+    fn /= np.maximum(np.linalg.norm(fn, axis=1, keepdims=True), 1e-30)
+    n = np.zeros_like(v)
+    for k in range(3):
+        np.add.at(n, f[:, k], fn)
+    return (n / np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-30)).astype(np.float32)
+
+
+def rna_correspondences(src, src_normals, tgt, tgt_normals, position_threshold, cos_normal_threshold=0.7, max_k=20):
+    """setConstraints of the harness (robust_nonrigid_alignment/src/CombinedSolver.h:261-346) on the host: for every source vertex the
+    max_k nearest target vertices in order of distance; stop at the first one farther than position_threshold; take the first whose normal
+    agrees (dot > cos_normal_threshold).  Returns (constraints with -inf rows where none was found, constraint normals)."""
+    from scipy.spatial import cKDTree
+    d, idx = cKDTree(np.asarray(tgt, np.float64)).query(np.asarray(src, np.float64), k=max_k)
+    cons = np.full((len(src), 3), -np.inf, np.float32); cn = np.zeros((len(src), 3), np.float32)
+    for i in range(len(src)):
+        for dist, t in zip(d[i], idx[i]):
+            if dist > position_threshold:
+                break
+            if float(np.dot(tgt_normals[t], src_normals[i])) > cos_normal_threshold:
+                cons[i] = tgt[t]; cn[i] = tgt_normals[t]
+                break
+    return cons, cn
+
+
+def rna_from_files(source_mesh, target_mesh, tet_file=None, dtype=np.float64, w_fit=10.0, w_reg=64.0):
+    """examples/robust_nonrigid_alignment/src/main.cpp:33-63 + CombinedSolver.h:73-118,:142-170,:261-346,:349-424 for ONE target frame at its
+    first outer iteration: Offset0 = UrShape = the source vertices, Angle0 = 0, RobustWeights0 = 1, graph = one directed edge per (vertex,
+    neighbour) -- neighbours through the tetrahedra when a .ele file is given (sorted, as the harness's std::set walks them), else through
+    the surface edges --, Constraints / ConstraintNormals = the correspondences of setConstraints with positionThreshold = 5 x the average
+    edge length, weights w_fit = 10, w_reg = 64 (the start of the harness's continuation 64 -> 4) passed as square roots.  The harness
+    also displaces 5 % of the targets by noise drawn from std::normal_distribution (implementation-defined sequence): not reproduced here.
+    Returns (params, N, info)."""
+    v, faces = io.read_mesh(source_mesh)
+    tv, tfaces = io.read_mesh(target_mesh)
+    N = len(v)
+    if tet_file:
+        tets = read_tets(tet_file)
+        pairs = np.concatenate([np.stack([tets[:, i], tets[:, (i + j) % 4]], 1) for i in range(4) for j in range(1, 4)], 0)
+        pairs = np.unique(pairs, axis=0)                         # (head, tail) sorted by head, then tail: std::set order per vertex
+        head, tail = pairs[:, 0].astype(np.int32).copy(), pairs[:, 1].astype(np.int32).copy()
+    else:
+        head, tail = io.mesh_neighbour_edges(v, faces)
+    f = np.asarray(faces, np.int64)
+    und = np.unique(np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], 0), axis=1), axis=0)
+    avg_edge = float(np.linalg.norm(v[und[:, 0]].astype(np.float64) - v[und[:, 1]], axis=1).mean())
+    sn, tn = vertex_normals(v, faces), vertex_normals(tv, tfaces)
+    cons, cn = rna_correspondences(v, sn, tv, tn, 5.0 * avg_edge)
+    c = lambda a: np.ascontiguousarray(np.asarray(a).astype(dtype))
+    params = [float(np.sqrt(np.float32(w_fit))), float(np.sqrt(np.float32(w_reg))), c(v), np.zeros((N, 3), dtype), np.ones((N, 1), dtype), c(v), c(cons), c(cn),
+              int(len(head)), head, tail]
+    return params, N, {"average_edge_length": avg_edge, "correspondences": int(np.isfinite(cons[:, 0]).sum()), "edges": int(len(head))}
+
+
 # ------------------------------------------------------------------------------------------------ per-outer-iteration pre-steps on the GPU
 # (include/OptB200Examples.h; thin wrappers over torch CUDA tensors -- device memory plumbing only)
 def _ptr(t):

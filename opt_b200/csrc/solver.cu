@@ -1022,7 +1022,7 @@ struct Plan : PlanBase {
     //     k_lmDecide          accept / reject / radius / end of solve (lm_decide.cuh, the arithmetic of decide() below)
     //     k_copyIfRejected    revertUpdate
     //     precompute + cost   only after a rejection
-    // and the host waits ONCE, for the state, when they are all through.  An iteration enqueued behind the one that ended the solve
+    // and the host waits once per chunk of iterations (8), for the state.  An iteration enqueued behind the one that ended the solve
     // costs five empty launches.  Opt_ProblemStep keeps the host-side decision (it has to return it).
     cudaGraphExec_t devIterExec = nullptr; unsigned long long devIterKey = 0; int devIterLaunchCount = 0; T* devIterPFinal = nullptr;
     double* hLmState = nullptr; int deviceIterationsRun = 0;
@@ -1075,10 +1075,15 @@ struct Plan : PlanBase {
         hLmState[0] = (double)trust_region_radius; hLmState[1] = (double)prevCost; hLmState[2] = (double)radius_decrease_factor;
         hLmState[3] = hLmState[4] = hLmState[5] = 0.0;
         OPT_CUDA_CHECK(cudaMemcpyAsync(ws.scalars + kRadius, hLmState, sizeof(double) * 6, cudaMemcpyHostToDevice, stream));
-        const int remaining = sp.nIterations - nIter;
-        for (int i = 0; i < remaining; ++i) OPT_CUDA_CHECK(cudaGraphLaunch(devIterExec, stream));
-        OPT_CUDA_CHECK(cudaMemcpyAsync(hScalars, ws.scalars, sizeof(double) * kNumScalars, cudaMemcpyDeviceToHost, stream));
-        OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
+        // enqueued in chunks (default 8 iterations; OPTB_DEVICE_LM=n > 1 sets n): one wait per chunk instead of one per iteration, and a solve
+        // that ends early leaves at most chunk - 1 gated (empty) iterations behind it
+        const int chunk = atoi(want) > 1 ? atoi(want) : 8;
+        for (int left = sp.nIterations - nIter; left > 0; left -= chunk) {
+            for (int i = 0; i < chunk && i < left; ++i) OPT_CUDA_CHECK(cudaGraphLaunch(devIterExec, stream));
+            OPT_CUDA_CHECK(cudaMemcpyAsync(hScalars, ws.scalars, sizeof(double) * kNumScalars, cudaMemcpyDeviceToHost, stream));
+            OPT_CUDA_CHECK(cudaStreamSynchronize(stream));
+            if (hScalars[kLmGate] != 0.0) break;
+        }
         pFinal = devIterPFinal; launches = devIterLaunchCount; loopMs = 0;
         prevCost = (T)hScalars[kLmPrevCost]; trust_region_radius = (T)hScalars[kRadius]; radius_decrease_factor = (T)hScalars[kLmFactor];
         deviceIterationsRun = (int)hScalars[kLmIters];

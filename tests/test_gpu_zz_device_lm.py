@@ -1,6 +1,6 @@
 """GPU: Levenberg-Marquardt with the accept / reject / trust-region decision ON THE DEVICE (OPTB_DEVICE_LM=1; SURVEY.md 8(f) rank 2:
 "cost, model cost, accept/reject, radius update ... without host syncs").  Opt_ProblemSolve then enqueues every nonlinear iteration after
-the first back to back -- loop kernel, precompute + cost, k_lmDecide, revert-if-rejected, precompute-if-rejected -- and waits once.  The
+the first back to back -- loop kernel, precompute + cost, k_lmDecide, revert-if-rejected, precompute-if-rejected -- and waits once per chunk of eight iterations.  The
 kernels are the default path's (they only gained a gate argument) and the decision is the arithmetic of Plan::decide (lm_decide.cuh,
 checked bit for bit against the reference's lines on the CPU: tests/test_lm_decide_host.py), so a solve must end where the default solve
 ends: same number of iterations, same radius, same cost, same unknowns.
